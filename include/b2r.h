@@ -1,0 +1,171 @@
+/* b2r.h -- C ABI of the B200-native frame pipeline for py-numpy-renderer.
+ *
+ * The reference (Denizantip/py-numpy-renderer) has no FFI of its own: its hot path is the body of
+ * `Scene.render()` (obj/core.py:587-640) calling `rasterize` (obj/triangular.py:29-132), `general_shading`
+ * (triangular.py:135-171), `shadow_volumes` (triangular.py:294-302), `resterize_quadrangle`
+ * (triangular.py:319-368), `clipping` (obj/plane_intersection.py:59-86) and `fill_frame_from_skybox`
+ * (obj/cube_map.py:83-101) on caller-owned NumPy arrays.  This header is the boundary a maintainer would bind
+ * (ctypes stub in INTEGRATION.md) to replace exactly that body:
+ *
+ *   b2r_scene_create   <- the data `Scene.add_model(Model)` accumulates            (core.py:231-256, 584-585)
+ *                         + `TextureMaps.register` / `parse_mtl` textures          (core.py:90-105, 321-348)
+ *                         + `CubeMap(...)`                                         (cube_map.py:22-61)
+ *   b2r_render         <- `Scene.render()`                                         (core.py:587-640)
+ *   b2r_scene_reset_silhouette <- the persistent `model.silhouette` set            (core.py:251, 605)
+ *
+ * Plain pointers and sizes only; no torch / Python types.  All matrices are float64, row-major, ROW-VECTOR
+ * convention (v' = v @ M) and are computed by the host with the reference's own NumPy expressions
+ * (core.py:394-429), so the library never re-derives a camera.
+ *
+ * Error model: every call returns 0 on success, non-zero on failure; `b2r_last_error()` gives the message
+ * (thread-local).  The library never frees or keeps caller memory: create() copies what it needs to the device.
+ * There is NO CPU fallback: without a CUDA device every entry point except b2r_last_error/b2r_abi_version fails.
+ */
+#ifndef B2R_H_
+#define B2R_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2R_ABI_VERSION 1
+#define B2R_MAX_POLY 12 /* a quad clipped by 6 planes has at most 10 vertices */
+
+/* Light kinds: obj/lightning.py:4-7 */
+enum { B2R_LIGHT_DIRECTIONAL = 0, B2R_LIGHT_POINT = 1, B2R_LIGHT_SPOT = 2 };
+/* Texel decode: core.py:96-104 -- f32(u8/255) or f32(u8/255*2-1) */
+enum { B2R_TEX_UNORM = 0, B2R_TEX_SNORM = 1 };
+/* vertex storage of Model.vertices: float32 straight from the loader, float64 after an `@` chain (core.py:350-352) */
+enum { B2R_F32 = 0, B2R_F64 = 1 };
+/* background: core.py:595-600 */
+enum { B2R_BG_COLOR = 0, B2R_BG_CUBEMAP = 1 };
+/* per-face status of pass 3, triangular.py:15-20 (bit values of the reference's `Errors` Flag; 0 = rendered) */
+enum { B2R_FACE_RENDERED = 0, B2R_FACE_BACK_FACE_CULLING = 1, B2R_FACE_WRONG_MIN_MAX = 2, B2R_FACE_EMPTY_B = 4,
+       B2R_FACE_EMPTY_Z = 8, B2R_FACE_CLIPPED = 16 };
+
+typedef struct b2r_texture_desc {
+    const uint8_t* rgb; /* host, height*width*3, row-major, as PIL `convert('RGB')` yields (core.py:100-105) */
+    int32_t height, width;
+    int32_t decode;  /* B2R_TEX_UNORM | B2R_TEX_SNORM */
+    int32_t tangent; /* normal maps: dtype metadata 'tangent' (core.py:94, 180) */
+} b2r_texture_desc;
+
+/* obj/materials.py:47-55 + the maps Face.get_object_color/get_specular/get_normals look up (core.py:145-189) */
+typedef struct b2r_material {
+    double Kd[3];
+    double Ks[3];
+    double Ns;
+    int32_t map_Kd; /* index into the scene texture table or -1 */
+    int32_t map_Ks;
+    int32_t norm;
+    int32_t reserved;
+} b2r_material;
+
+/* One `Model` (core.py:231-256).  faces is the reference's (F,3,4) int32 array: per corner [v, vt, vn, mtl]. */
+typedef struct b2r_model_desc {
+    const void* vertices; /* (V,4) vertex_dtype */
+    const void* uv;       /* (T,3) uv_dtype or NULL */
+    const void* normals;  /* (N,3) normal_dtype or NULL */
+    const int32_t* faces; /* (F,3,4) */
+    const b2r_material* materials; /* indexed by faces[f][0][3] (out of range -> materials[0] = 'default') */
+    int32_t n_vertices, n_uv, n_normals, n_faces, n_materials;
+    int32_t vertex_dtype, uv_dtype, normal_dtype; /* B2R_F32 | B2R_F64 */
+    int32_t clip;       /* Model.clip (triangular.py:80) */
+    int32_t depth_test; /* Model.depth_test (triangular.py:117); only 1 is supported (order-independent z) */
+} b2r_model_desc;
+
+/* CubeMap.textures after the constructor's flips/rotations (cube_map.py:22-44): 6 faces ordered
+ * right,left,top,bottom,front,back, each size*size*3 uint8. */
+typedef struct b2r_cubemap_desc {
+    const uint8_t* faces;
+    int32_t size;
+    int32_t reserved;
+} b2r_cubemap_desc;
+
+/* Per camera view: everything `rasterize`/`resterize_quadrangle`/`fill_frame_from_skybox` read from the camera. */
+typedef struct b2r_view {
+    double mvp[16];       /* camera.MVP             core.py:419-421 */
+    double mvp_dbg[16];   /* debug_camera.MVP       triangular.py:39 */
+    double viewport[16];  /* camera.viewport        core.py:427-429, transformation.py:123-136 */
+    double planes[24];    /* camera.frustum_planes  plane_intersection.py:43-56 */
+    double sky_inv[16];   /* inv(lookat_without_translation @ projection)  cube_map.py:94-97 */
+    double cam_pos[3];    /* camera.position        triangular.py:156 */
+    double near_, far_;   /* camera.near/far        core.py:226-228 */
+    int32_t system;           /* +1 RH, -1 LH      constants.py:29-31 */
+    int32_t backface_culling; /* triangular.py:47 */
+} b2r_view;
+
+/* core.py:444-524 */
+typedef struct b2r_light {
+    double position[3];
+    double direction[3]; /* normalize(position - center), core.py:364-366 */
+    double color[3];
+    double ambient[3];   /* ambient_strength * color, core.py:464 */
+    double specular_strength, constant, linear, quadratic;
+    double spot_cos_outer, spot_cos_inner; /* cos(20 deg), cos(10 deg): triangular.py:158-159 */
+    int32_t type;
+    int32_t reserved;
+} b2r_light;
+
+typedef struct b2r_frame_params {
+    b2r_light light;
+    float background[3]; /* used when bg_mode == B2R_BG_COLOR (core.py:597-600, already float32) */
+    int32_t bg_mode;
+    int32_t height, width; /* Scene.resolution = (height, width), core.py:397 */
+    int32_t row_begin, row_end; /* screen-row band [row_begin,row_end) in BUFFER rows (pre-flip); 0,height = all */
+    int32_t persist_silhouette; /* 1: toggle the scene's persistent silhouette like core.py:605 (Appendix B-3);
+                                   0: every view starts from an empty set (fresh-Model semantics) */
+    int32_t reserved;
+} b2r_frame_params;
+
+/* Optional per-view debug planes, each NULL or n_views * height * width elements (device or host pointer as the
+ * `out_on_device` flag says).  Row r = buffer row r (NOT flipped), i.e. the reference's z_buffer[row, col]. */
+typedef struct b2r_debug_out {
+    double* z;           /* z_buffer          core.py:590 */
+    int16_t* stencil;    /* stencil_buffer    core.py:591 */
+    int32_t* winner;     /* global face index that coloured the pixel, -1 = background */
+    uint8_t* face_status;/* n_views * total_faces: B2R_FACE_* of pass 3 (core.py:624-636) */
+    int32_t* n_silhouette; /* n_views * n_models: silhouette edges extruded for that view */
+} b2r_debug_out;
+
+typedef struct b2r_scene b2r_scene;
+
+int b2r_abi_version(void);
+const char* b2r_last_error(void);
+
+/* Select the CUDA device and create the library's stream.  Must precede everything else. */
+int b2r_init(int device);
+int b2r_shutdown(void);
+
+int b2r_scene_create(const b2r_model_desc* models, int32_t n_models,
+                     const b2r_texture_desc* textures, int32_t n_textures,
+                     const b2r_cubemap_desc* skybox /* nullable */,
+                     b2r_scene** out_scene);
+int b2r_scene_destroy(b2r_scene* scene);
+int b2r_scene_reset_silhouette(b2r_scene* scene);
+int64_t b2r_scene_device_bytes(const b2r_scene* scene);
+
+/* Render n_views frames of `scene`.  out_rgb: n_views*height*width*3 uint8, final image rows (flipped,
+ * tonemapped: core.py:640).  With out_on_device=0 the pointers are host memory and the call returns after the
+ * copies completed; with out_on_device=1 they are device memory and the call only enqueues on the library
+ * stream (use b2r_sync, or order against `b2r_stream()`). */
+int b2r_render(b2r_scene* scene, const b2r_frame_params* params, const b2r_view* views, int32_t n_views,
+               uint8_t* out_rgb, const b2r_debug_out* debug /* nullable */, int32_t out_on_device);
+int b2r_sync(void);
+void* b2r_stream(void); /* the cudaStream_t the library launches on */
+
+/* Number of kernel launches issued by this library since init (bench.py `gpu_launches`). */
+int64_t b2r_launch_count(void);
+
+/* Stage timing of the most recent b2r_render in milliseconds (CUDA events on the library stream); valid after
+ * a sync.  names/ms arrays sized >= B2R_MAX_STAGES; returns the number of stages. */
+#define B2R_MAX_STAGES 16
+int b2r_last_stage_ms(const char** names, float* ms);
+int b2r_set_stage_timing(int enabled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2R_H_ */
