@@ -146,6 +146,9 @@ int b2r_scene_create(const b2r_model_desc* models, int32_t n_models,
 int b2r_scene_destroy(b2r_scene* scene);
 int b2r_scene_reset_silhouette(b2r_scene* scene);
 int64_t b2r_scene_device_bytes(const b2r_scene* scene);
+/* Read the persistent silhouette set back (`model.silhouette`, core.py:251): out_pairs (capacity,2) scene-global
+ * vertex indices in stored orientation, out_model (capacity) owning model.  Returns the number of edges. */
+int b2r_scene_get_silhouette(b2r_scene* scene, int32_t* out_pairs, int32_t* out_model, int32_t capacity);
 
 /* Render n_views frames of `scene`.  out_rgb: n_views*height*width*3 uint8, final image rows (flipped,
  * tonemapped: core.py:640).  With out_on_device=0 the pointers are host memory and the call returns after the

@@ -1,0 +1,215 @@
+"""ctypes binding of `libb2r.so` (C ABI: include/b2r.h) -- the only road from the Python API to the GPU.
+
+There is NO fallback path: if the shared library is missing, cannot be loaded, or no CUDA device is present,
+importing / using this module raises.  (The CPU oracle under `oracle/` is test infrastructure and is never
+imported from here.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from enum import Flag, auto
+
+import numpy as np
+
+from . import _abi
+from ._abi import (B2R_BG_COLOR, B2R_BG_CUBEMAP, DebugOut, FrameParams, PackedScene, View,  # noqa: F401
+                   pack_frame_params, pack_view)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb2r.so")
+
+
+class Errors(Flag):
+    """Per-face discard reasons printed by the reference's render loop (triangular.py:15-20)."""
+    BACK_FACE_CULLING = auto()
+    WRONG_MIN_MAX = auto()
+    EMPTY_B = auto()
+    EMPTY_Z = auto()
+    CLIPPED = auto()
+
+
+_lib = None
+_inited_device = None
+
+_SYMBOLS = {
+    "b2r_abi_version": (C.c_int, []),
+    "b2r_last_error": (C.c_char_p, []),
+    "b2r_init": (C.c_int, [C.c_int]),
+    "b2r_shutdown": (C.c_int, []),
+    "b2r_scene_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "b2r_scene_destroy": (C.c_int, [C.c_void_p]),
+    "b2r_scene_reset_silhouette": (C.c_int, [C.c_void_p]),
+    "b2r_scene_device_bytes": (C.c_int64, [C.c_void_p]),
+    "b2r_scene_get_silhouette": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "b2r_render": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]),
+    "b2r_sync": (C.c_int, []),
+    "b2r_stream": (C.c_void_p, []),
+    "b2r_launch_count": (C.c_int64, []),
+    "b2r_last_stage_ms": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "b2r_set_stage_timing": (C.c_int, [C.c_int]),
+}
+
+
+def load_library():
+    """dlopen libb2r.so and bind every symbol include/b2r.h declares (no CUDA call is made)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -m py_numpy_renderer_b200.build` "
+                              f"(there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SYMBOLS.items():
+            fn = getattr(lib, name)  # AttributeError if the library does not export it
+            fn.restype, fn.argtypes = res, args
+        if lib.b2r_abi_version() != _abi.B2R_ABI_VERSION:
+            raise ImportError("libb2r.so ABI version mismatch; rebuild")
+        _lib = lib
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError("b2r: " + (load_library().b2r_last_error() or b"").decode())
+
+
+def init(device=None):
+    """Bind the library to a CUDA device (default: LOCAL_RANK or 0)."""
+    global _inited_device
+    lib = load_library()
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0")) if _inited_device is None else _inited_device
+    if _inited_device != device:
+        _check(lib.b2r_init(int(device)))
+        _inited_device = device
+    return lib
+
+
+def sync():
+    _check(init().b2r_sync())
+
+
+def launch_count() -> int:
+    return int(init().b2r_launch_count())
+
+
+def set_stage_timing(flag: bool):
+    init().b2r_set_stage_timing(int(flag))
+
+
+def last_stage_ms() -> dict:
+    lib = init()
+    names = (C.c_char_p * _abi.B2R_MAX_STAGES)()
+    ms = (C.c_float * _abi.B2R_MAX_STAGES)()
+    n = lib.b2r_last_stage_ms(names, ms)
+    out = {}
+    for i in range(n):
+        key = names[i].decode()
+        out[key] = out.get(key, 0.0) + float(ms[i])
+    return out
+
+
+def stream_ptr() -> int:
+    return int(init().b2r_stream() or 0)
+
+
+def _dev_ptr(t):
+    """Address of a device buffer: torch tensor (data_ptr) or a raw int."""
+    if t is None:
+        return None
+    return C.c_void_p(int(t.data_ptr()) if hasattr(t, "data_ptr") else int(t))
+
+
+class DeviceScene:
+    """Device mirror of a list of host `Model`s (+ optional CubeMap)."""
+
+    def __init__(self, models, skybox=None, device=None):
+        self.lib = init(device)
+        self.packed = PackedScene(models, skybox)
+        self.handle = C.c_void_p()
+        p = self.packed
+        _check(self.lib.b2r_scene_create(C.cast(p.models, C.c_void_p), p.n_models, C.cast(p.textures, C.c_void_p),
+                                         p.n_textures, C.cast(p.sky_ptr, C.c_void_p) if p.sky is not None else None,
+                                         C.byref(self.handle)))
+        self.has_sky = skybox is not None
+        self.vertex_base = np.cumsum([0] + [int(m.n_vertices) for m in p.models[:p.n_models]])
+
+    def close(self):
+        if self.handle:
+            self.lib.b2r_scene_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def device_bytes(self):
+        return int(self.lib.b2r_scene_device_bytes(self.handle))
+
+    def reset_silhouette(self):
+        _check(self.lib.b2r_scene_reset_silhouette(self.handle))
+
+    def silhouette_of(self, model_index):
+        cap = 1 << 16
+        while True:
+            pairs = np.empty((cap, 2), np.int32)
+            owner = np.empty(cap, np.int32)
+            n = self.lib.b2r_scene_get_silhouette(self.handle, pairs.ctypes.data, owner.ctypes.data, cap)
+            if n < 0:
+                raise RuntimeError("b2r_scene_get_silhouette failed")
+            if n <= cap:
+                break
+            cap = n
+        sel = owner[:n] == model_index
+        base = int(self.vertex_base[model_index])
+        return {(int(a) - base, int(b) - base) for a, b in pairs[:n][sel]}
+
+    def render(self, cameras, debug_camera, light, resolution, system, background, persist_silhouette=False,
+               want_debug=False, out=None, band=None):
+        """-> (frames, info).  frames: uint8 (n, H, W, 3) NumPy array, or `out` (a CUDA tensor / device pointer,
+        written asynchronously on the library stream) when given."""
+        n = len(cameras)
+        H, W = int(resolution[0]), int(resolution[1])
+        fp = pack_frame_params(light, (H, W), background, persist_silhouette, band)
+        views = (View * n)(*[pack_view(c, debug_camera, system, self.has_sky) for c in cameras])
+        info = {}
+        dbg = None
+        on_device = out is not None
+        if want_debug:
+            if on_device:
+                raise ValueError("debug planes are only returned to host memory")
+            F, M = self.packed.total_faces, self.packed.n_models
+            info = dict(face_status=np.zeros((n, max(F, 1)), np.uint8), n_silhouette=np.zeros((n, max(M, 1)), np.int32))
+            if want_debug != 'status':  # full planes
+                info.update(z=np.empty((n, H, W), np.float64), stencil=np.empty((n, H, W), np.int16),
+                            winner=np.empty((n, H, W), np.int32))
+            dbg = DebugOut(*[info[k].ctypes.data if k in info else None
+                             for k in ('z', 'stencil', 'winner', 'face_status', 'n_silhouette')])
+        if on_device:
+            target = _dev_ptr(out)
+            frames = out
+        else:
+            frames = np.zeros((n, H, W, 3), np.uint8) if band is not None else np.empty((n, H, W, 3), np.uint8)
+            target = C.c_void_p(frames.ctypes.data)
+        _check(self.lib.b2r_render(self.handle, C.byref(fp), C.cast(views, C.c_void_p), n, target,
+                                   C.byref(dbg) if dbg is not None else None, int(on_device)))
+        if want_debug:
+            info['face_status'] = info['face_status'][:, :self.packed.total_faces]
+            info['n_silhouette'] = info['n_silhouette'][:, :self.packed.n_models]
+        return frames, info
+
+
+def status_report(models, face_status):
+    """The three lines per model the reference prints during pass 3 (core.py:624-636)."""
+    lines = []
+    start = 0
+    for m in models:
+        n = len(m._faces)
+        st = np.asarray(face_status[start:start + n])
+        start += n
+        counts = {err: int((st == err.value).sum()) for err in Errors}
+        lines += [f"Total faces {n}", f"Face rendered {int((st == 0).sum())}", f"Discarded {counts}"]
+    return lines

@@ -345,7 +345,7 @@ class Scene:
         dev = self._device_scene()
         frames, info = dev.render([self.camera], self.debug_camera, self.light, self.resolution, self.system,
                                   self._background(), persist_silhouette=self.persist_silhouette,
-                                  want_debug=(debug is not None) or self.verbose)
+                                  want_debug=True if debug is not None else ('status' if self.verbose else False))
         if isinstance(self.skybox, CubeMap):
             # fill_frame_from_skybox zeroes the translation row of the *cached* camera.lookat in place
             # (cube_map.py:94-96, Appendix B-3); keep the side effect for callers that look at it afterwards.

@@ -1,0 +1,587 @@
+// b2r_api.cu -- host side of the C ABI declared in include/b2r.h (scene upload, per-frame orchestration).
+//
+// One stream, no host synchronisation inside a frame: every stage is a kernel launch on `g.stream`; sizes that
+// are only known on the device (silhouette length, tile-list totals) stay on the device (grid-stride kernels read
+// them), with capacity overflow reported through a flag that is read back with the frame.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "b2r_kernels.cuh"
+
+using namespace b2r;
+
+namespace {
+
+thread_local std::string t_error;
+
+struct Globals {
+    bool ready = false;
+    int device = -1;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+    bool timing = false;
+    int n_stage = 0;
+    const char* stage_name[B2R_MAX_STAGES];
+    cudaEvent_t stage_ev[B2R_MAX_STAGES + 1];
+    int* pinned_flags = nullptr;  // overflow read-back
+} g;
+
+int fail(const std::string& msg) {
+    t_error = msg;
+    return 1;
+}
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" +   \
+                        std::to_string(__LINE__) + ")");                                                \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t reserve(size_t count) {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T) + 16);
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+void stage_mark(const char* name) {
+    if (!g.timing || g.n_stage >= B2R_MAX_STAGES) return;
+    g.stage_name[g.n_stage] = name;
+    cudaEventRecord(g.stage_ev[g.n_stage + 1], g.stream);
+    ++g.n_stage;
+}
+
+}  // namespace
+
+struct b2r_scene {
+    // static geometry
+    DevBuf<double4> pos;
+    DevBuf<double2> uv;
+    DevBuf<double> nrm;
+    DevBuf<FaceStatic> faces;
+    DevBuf<MaterialDev> mats;
+    DevBuf<TextureDev> tex;
+    std::vector<uchar4*> tex_data;
+    DevBuf<uchar4> sky;
+    int sky_size = 0;
+    DevBuf<int2> edge_v;
+    DevBuf<int> edge_ptr, edge_inc, edge_model;
+    DevBuf<int8_t> sil_state;
+    int n_faces = 0, n_edges = 0, n_models = 0;
+    std::vector<int> model_faces;
+    size_t static_bytes = 0;
+    // per-render scratch (grown on demand)
+    DevBuf<uint8_t> facing;
+    DevBuf<SilEdge> sil;
+    DevBuf<int> counters;  // [0] silhouette count, [1..n_models] per-model counts
+    DevBuf<ViewDev> views;
+    DevBuf<TriRec> tris;
+    DevBuf<QuadRec> quads;
+    DevBuf<int> tile_counts, tile_offs, tri_list, quad_list, overflow;
+    DevBuf<int> winner;
+    DevBuf<short> stencil;
+    DevBuf<double> zplane;
+    DevBuf<uint8_t> status;
+    DevBuf<uint8_t> rgb;
+    int tri_cap = 0, quad_cap = 0;
+    int views_cap = 0;
+
+    SceneDev dev() const {
+        SceneDev S;
+        S.pos = pos.p; S.uv = uv.p; S.nrm = nrm.p; S.faces = faces.p; S.mats = mats.p; S.tex = tex.p; S.sky = sky.p;
+        S.edge_v = edge_v.p; S.edge_ptr = edge_ptr.p; S.edge_inc = edge_inc.p;
+        S.n_faces = n_faces; S.n_edges = n_edges;
+        return S;
+    }
+};
+
+extern "C" {
+
+int b2r_abi_version(void) { return B2R_ABI_VERSION; }
+const char* b2r_last_error(void) { return t_error.c_str(); }
+
+int b2r_init(int device) {
+    if (g.ready && g.device == device) return 0;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                    "); this library has no CPU fallback");
+    if (device < 0 || device >= count) return fail("device index out of range");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    g.sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    for (int i = 0; i <= B2R_MAX_STAGES; ++i) CK(cudaEventCreate(&g.stage_ev[i]));
+    CK(cudaMallocHost(&g.pinned_flags, 4096));
+    float lut[2][256];
+    for (int i = 0; i < 256; ++i) {  // core.py:96-104: f32(u8/255), f32(u8/255*2-1) with float64 intermediates
+        const double t = (double)i / 255;
+        lut[0][i] = (float)t;
+        lut[1][i] = (float)(t * 2 - 1);
+    }
+    CK(cudaMemcpyToSymbol(c_lut, lut, sizeof(lut)));
+    g.device = device;
+    g.ready = true;
+    g.launches = 0;
+    return 0;
+}
+
+int b2r_shutdown(void) {
+    if (!g.ready) return 0;
+    cudaStreamSynchronize(g.stream);
+    cudaStreamDestroy(g.stream);
+    for (int i = 0; i <= B2R_MAX_STAGES; ++i) cudaEventDestroy(g.stage_ev[i]);
+    cudaFreeHost(g.pinned_flags);
+    g = Globals();
+    return 0;
+}
+
+int b2r_sync(void) {
+    if (!g.ready) return fail("b2r_init was not called");
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+void* b2r_stream(void) { return (void*)g.stream; }
+int64_t b2r_launch_count(void) { return (int64_t)g.launches; }
+int b2r_set_stage_timing(int enabled) { g.timing = enabled != 0; return 0; }
+int b2r_last_stage_ms(const char** names, float* ms) {
+    for (int i = 0; i < g.n_stage; ++i) {
+        names[i] = g.stage_name[i];
+        ms[i] = 0.f;
+        cudaEventElapsedTime(&ms[i], g.stage_ev[i], g.stage_ev[i + 1]);
+    }
+    return g.n_stage;
+}
+
+static inline double load_real(const void* base, int dtype, size_t idx) {
+    return dtype == B2R_F32 ? (double)((const float*)base)[idx] : ((const double*)base)[idx];
+}
+
+int b2r_scene_create(const b2r_model_desc* models, int32_t n_models, const b2r_texture_desc* textures,
+                     int32_t n_textures, const b2r_cubemap_desc* skybox, b2r_scene** out_scene) {
+    if (!g.ready) return fail("b2r_init was not called");
+    if (!out_scene) return fail("out_scene is NULL");
+    b2r_scene* sc = new b2r_scene();
+    sc->n_models = n_models;
+    size_t nv = 0, nt = 0, nn = 0, nf = 0, nm = 0;
+    for (int i = 0; i < n_models; ++i) {
+        const b2r_model_desc& m = models[i];
+        if (!m.depth_test) { delete sc; return fail("Model.depth_test=False is order dependent; not supported"); }
+        if (!m.vertices || !m.faces || m.n_vertices <= 0) { delete sc; return fail("model without vertices/faces"); }
+        nv += m.n_vertices; nt += m.uv ? m.n_uv : 0; nn += m.normals ? m.n_normals : 0; nf += m.n_faces;
+        nm += std::max(1, m.n_materials);
+        sc->model_faces.push_back(m.n_faces);
+    }
+    if (nf > (size_t)1 << 30) { delete sc; return fail("too many faces"); }
+    std::vector<double4> pos(nv);
+    std::vector<double2> uv(nt);
+    std::vector<double> nrm(nn * 3);
+    std::vector<FaceStatic> faces(nf);
+    std::vector<MaterialDev> mats(nm);
+    struct HalfEdge { int model, lo, hi, face, corner, rev; };
+    std::vector<HalfEdge> half;
+    half.reserve(nf * 3);
+    std::vector<size_t> vbase(n_models);
+    size_t v0 = 0, t0 = 0, n0 = 0, f0 = 0, m0 = 0;
+    for (int mi = 0; mi < n_models; ++mi) {
+        const b2r_model_desc& m = models[mi];
+        vbase[mi] = v0;
+        for (size_t i = 0; i < (size_t)m.n_vertices; ++i)
+            pos[v0 + i] = make_double4(load_real(m.vertices, m.vertex_dtype, i * 4), load_real(m.vertices, m.vertex_dtype, i * 4 + 1),
+                                       load_real(m.vertices, m.vertex_dtype, i * 4 + 2), load_real(m.vertices, m.vertex_dtype, i * 4 + 3));
+        if (m.uv) for (size_t i = 0; i < (size_t)m.n_uv; ++i)
+            uv[t0 + i] = make_double2(load_real(m.uv, m.uv_dtype, i * 3), load_real(m.uv, m.uv_dtype, i * 3 + 1));
+        if (m.normals) for (size_t i = 0; i < (size_t)m.n_normals * 3; ++i) nrm[n0 * 3 + i] = load_real(m.normals, m.normal_dtype, i);
+        const int nmat = std::max(1, m.n_materials);
+        for (int s = 0; s < nmat; ++s) {
+            MaterialDev& M = mats[m0 + s];
+            b2r_material src;
+            if (m.materials && s < m.n_materials) src = m.materials[s];
+            else { std::memset(&src, 0, sizeof(src)); src.Kd[0] = src.Kd[1] = src.Kd[2] = 0.8; src.Ks[0] = src.Ks[1] = src.Ks[2] = 1; src.Ns = 64; src.map_Kd = src.map_Ks = src.norm = -1; }
+            for (int k = 0; k < 3; ++k) { M.Kd[k] = src.Kd[k]; M.Ks255[k] = src.Ks[k] * 255; }
+            M.Ns = src.Ns;
+            M.map_Kd = src.map_Kd < n_textures ? src.map_Kd : -1;
+            M.map_Ks = src.map_Ks < n_textures ? src.map_Ks : -1;
+            M.norm = src.norm < n_textures ? src.norm : -1;
+            M.ns_int = (src.Ns >= 0 && src.Ns <= 4096 && src.Ns == std::floor(src.Ns)) ? (int)src.Ns : -1;
+        }
+        const int base_flags = (m.clip ? FS_CLIP : 0) | (m.vertex_dtype == B2R_F32 ? FS_VTX_F32 : 0) |
+                               (m.uv ? FS_HAS_UV : 0) | (m.uv && m.uv_dtype == B2R_F32 ? FS_UV_F32 : 0) |
+                               (m.normals ? FS_HAS_NORMALS : 0);
+        auto wrap = [](int idx, int n) { if (idx < 0) idx += n; return (idx < 0 || idx >= n) ? 0 : idx; };
+        for (size_t f = 0; f < (size_t)m.n_faces; ++f) {
+            const int32_t* r = m.faces + f * 12;
+            FaceStatic& F = faces[f0 + f];
+            for (int c = 0; c < 3; ++c) {
+                F.v[c] = (int)(v0 + wrap(r[c * 4 + 0], m.n_vertices));
+                F.t[c] = m.uv ? (int)(t0 + wrap(r[c * 4 + 1], m.n_uv)) : 0;
+                F.n[c] = m.normals ? (int)(n0 + wrap(r[c * 4 + 2], m.n_normals)) : 0;
+            }
+            int slot = r[3];
+            if (slot < 0) slot += nmat;
+            if (slot < 0 || slot >= nmat) slot = 0;
+            F.material = (int)(m0 + slot);
+            F.flags = base_flags;
+            F.model = mi;
+            for (int c = 0; c < 3; ++c) {  // Edge((vi[c], vi[c+1])), undirected equality on the RAW indices
+                const int a = r[c * 4 + 0], b = r[((c + 1) % 3) * 4 + 0];
+                half.push_back({mi, std::min(a, b), std::max(a, b), (int)(f0 + f), c, a > b ? 1 : 0});
+            }
+        }
+        v0 += m.n_vertices; t0 += m.uv ? m.n_uv : 0; n0 += m.normals ? m.n_normals : 0; f0 += m.n_faces; m0 += nmat;
+    }
+    // static edge table: undirected edges -> incident (face, direction) in (face, corner) order
+    std::sort(half.begin(), half.end(), [](const HalfEdge& x, const HalfEdge& y) {
+        if (x.model != y.model) return x.model < y.model;
+        if (x.lo != y.lo) return x.lo < y.lo;
+        if (x.hi != y.hi) return x.hi < y.hi;
+        if (x.face != y.face) return x.face < y.face;
+        return x.corner < y.corner;
+    });
+    std::vector<int2> edge_v;
+    std::vector<int> edge_ptr, edge_inc(half.size()), edge_model;
+    for (size_t i = 0; i < half.size(); ++i) {
+        const HalfEdge& h = half[i];
+        if (i == 0 || h.model != half[i - 1].model || h.lo != half[i - 1].lo || h.hi != half[i - 1].hi) {
+            const b2r_model_desc& m = models[h.model];
+            auto wrap = [&](int idx) { if (idx < 0) idx += m.n_vertices; return (idx < 0 || idx >= m.n_vertices) ? 0 : idx; };
+            edge_v.push_back(make_int2((int)(vbase[h.model] + wrap(h.lo)), (int)(vbase[h.model] + wrap(h.hi))));
+            edge_ptr.push_back((int)i);
+            edge_model.push_back(h.model);
+        }
+        edge_inc[i] = (h.face << 1) | h.rev;
+    }
+    edge_ptr.push_back((int)half.size());
+    sc->n_faces = (int)nf;
+    sc->n_edges = (int)edge_v.size();
+
+#define UP(buf, vec)                                                                                          \
+    do {                                                                                                      \
+        cudaError_t e_ = sc->buf.reserve((vec).size());                                                       \
+        if (e_ == cudaSuccess && !(vec).empty())                                                              \
+            e_ = cudaMemcpyAsync(sc->buf.p, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice, g.stream); \
+        if (e_ != cudaSuccess) { std::string m_ = cudaGetErrorString(e_); b2r_scene_destroy(sc); return fail("upload " #buf ": " + m_); } \
+        sc->static_bytes += (vec).size() * sizeof((vec)[0]);                                                  \
+    } while (0)
+    UP(pos, pos); UP(uv, uv); UP(nrm, nrm); UP(faces, faces); UP(mats, mats);
+    UP(edge_v, edge_v); UP(edge_ptr, edge_ptr); UP(edge_inc, edge_inc); UP(edge_model, edge_model);
+    // textures: uint8 RGB -> RGBX so that one texel is one aligned 32-bit load
+    std::vector<TextureDev> tex(std::max(1, n_textures));
+    std::vector<std::vector<uchar4>> staging(n_textures);
+    for (int i = 0; i < n_textures; ++i) {
+        const b2r_texture_desc& t = textures[i];
+        const size_t n = (size_t)t.height * t.width;
+        staging[i].resize(n);
+        for (size_t k = 0; k < n; ++k) staging[i][k] = make_uchar4(t.rgb[k * 3], t.rgb[k * 3 + 1], t.rgb[k * 3 + 2], 255);
+        uchar4* d = nullptr;
+        if (cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(uchar4)) != cudaSuccess) { b2r_scene_destroy(sc); return fail("texture alloc"); }
+        sc->tex_data.push_back(d);
+        cudaMemcpyAsync(d, staging[i].data(), n * sizeof(uchar4), cudaMemcpyHostToDevice, g.stream);
+        tex[i].texels = d; tex[i].height = t.height; tex[i].width = t.width;
+        tex[i].decode = t.decode == B2R_TEX_SNORM ? 1 : 0; tex[i].tangent = t.tangent;
+        sc->static_bytes += n * sizeof(uchar4);
+    }
+    UP(tex, tex);
+    std::vector<uchar4> sky;
+    if (skybox && skybox->faces && skybox->size > 0) {
+        const size_t n = (size_t)6 * skybox->size * skybox->size;
+        sky.resize(n);
+        for (size_t k = 0; k < n; ++k) sky[k] = make_uchar4(skybox->faces[k * 3], skybox->faces[k * 3 + 1], skybox->faces[k * 3 + 2], 255);
+        sc->sky_size = skybox->size;
+        UP(sky, sky);
+    }
+#undef UP
+    if (sc->sil_state.reserve(std::max(1, sc->n_edges)) != cudaSuccess) { b2r_scene_destroy(sc); return fail("alloc sil_state"); }
+    cudaMemsetAsync(sc->sil_state.p, 0, std::max(1, sc->n_edges), g.stream);
+    cudaError_t e = cudaStreamSynchronize(g.stream);  // staging vectors die here
+    if (e != cudaSuccess) { b2r_scene_destroy(sc); return fail(std::string("scene upload: ") + cudaGetErrorString(e)); }
+    *out_scene = sc;
+    return 0;
+}
+
+int b2r_scene_destroy(b2r_scene* sc) {
+    if (!sc) return 0;
+    if (g.ready) cudaStreamSynchronize(g.stream);
+    sc->pos.release(); sc->uv.release(); sc->nrm.release(); sc->faces.release(); sc->mats.release(); sc->tex.release();
+    for (uchar4* d : sc->tex_data) cudaFree(d);
+    sc->sky.release(); sc->edge_v.release(); sc->edge_ptr.release(); sc->edge_inc.release(); sc->edge_model.release();
+    sc->sil_state.release(); sc->facing.release(); sc->sil.release(); sc->counters.release(); sc->views.release();
+    sc->tris.release(); sc->quads.release(); sc->tile_counts.release(); sc->tile_offs.release(); sc->tri_list.release();
+    sc->quad_list.release(); sc->overflow.release(); sc->winner.release(); sc->stencil.release(); sc->zplane.release();
+    sc->status.release(); sc->rgb.release();
+    delete sc;
+    return 0;
+}
+
+int b2r_scene_reset_silhouette(b2r_scene* sc) {
+    if (!sc) return fail("scene is NULL");
+    CK(cudaMemsetAsync(sc->sil_state.p, 0, std::max(1, sc->n_edges), g.stream));
+    return 0;
+}
+
+int64_t b2r_scene_device_bytes(const b2r_scene* sc) { return sc ? (int64_t)sc->static_bytes : 0; }
+
+// read the persistent silhouette back: out_pairs (n_edges, 2) GLOBAL vertex ids as stored (a,b); returns count
+int b2r_scene_get_silhouette(b2r_scene* sc, int32_t* out_pairs, int32_t* out_model, int32_t capacity) {
+    if (!sc) return -1;
+    std::vector<int8_t> st(std::max(1, sc->n_edges));
+    std::vector<int2> ev(std::max(1, sc->n_edges));
+    std::vector<int> em(std::max(1, sc->n_edges));
+    if (cudaStreamSynchronize(g.stream) != cudaSuccess) return -1;
+    cudaMemcpy(st.data(), sc->sil_state.p, sc->n_edges, cudaMemcpyDeviceToHost);
+    cudaMemcpy(ev.data(), sc->edge_v.p, sc->n_edges * sizeof(int2), cudaMemcpyDeviceToHost);
+    cudaMemcpy(em.data(), sc->edge_model.p, sc->n_edges * sizeof(int), cudaMemcpyDeviceToHost);
+    int n = 0;
+    for (int e = 0; e < sc->n_edges; ++e) {
+        if (!st[e]) continue;
+        if (n < capacity) {
+            out_pairs[n * 2] = st[e] == 1 ? ev[e].x : ev[e].y;
+            out_pairs[n * 2 + 1] = st[e] == 1 ? ev[e].y : ev[e].x;
+            out_model[n] = em[e];
+        }
+        ++n;
+    }
+    return n;
+}
+
+// ---- host-side evaluation of the view constants (same operation order as the reference) ----------------------------
+static void host_vec4_mat4(const double v[4], const double* M, double out[4]) {
+    for (int j = 0; j < 4; ++j) {
+        double acc = v[0] * M[j];
+        acc = std::fma(v[1], M[4 + j], acc);
+        acc = std::fma(v[2], M[8 + j], acc);
+        acc = std::fma(v[3], M[12 + j], acc);
+        out[j] = acc;
+    }
+}
+
+static void make_view(const b2r_view& v, bool with_sky, ViewDev& D) {
+    std::memcpy(D.mvp, v.mvp, sizeof(D.mvp));
+    std::memcpy(D.mvp_dbg, v.mvp_dbg, sizeof(D.mvp_dbg));
+    std::memcpy(D.viewport, v.viewport, sizeof(D.viewport));
+    std::memcpy(D.planes, v.planes, sizeof(D.planes));
+    std::memcpy(D.cam_pos, v.cam_pos, sizeof(D.cam_pos));
+    D.zl_num = 2 * v.near_ * v.far_;  // core.py:226-228
+    D.zl_sum = v.far_ + v.near_;
+    D.zl_diff = v.far_ - v.near_;
+    D.system = v.system;
+    D.backface = v.backface_culling;
+    std::memset(D.sky, 0, sizeof(D.sky));
+    if (!with_sky) return;
+    // fill_frame_from_skybox (cube_map.py:83-101): two NDC triangles at z = 1
+    static const double corner[2][3][4] = {{{-1, 1, 1, 1}, {1, 1, 1, 1}, {-1, -1, 1, 1}},
+                                           {{1, 1, 1, 1}, {1, -1, 1, 1}, {-1, -1, 1, 1}}};
+    for (int t = 0; t < 2; ++t) {
+        SkyTri& T = D.sky[t];
+        long long a[3][2];
+        for (int i = 0; i < 3; ++i) {
+            double s[4], r[4];
+            host_vec4_mat4(corner[t][i], v.viewport, s);
+            a[i][0] = (long long)s[0];
+            a[i][1] = (long long)s[1];
+            host_vec4_mat4(corner[t][i], v.sky_inv, r);
+            for (int k = 0; k < 3; ++k) T.rays[i][k] = r[k] / r[3];
+        }
+        T.ax = a[0][0]; T.ay = a[0][1];
+        T.v0x = a[1][0] - a[0][0]; T.v0y = a[1][1] - a[0][1];
+        T.v1x = a[2][0] - a[0][0]; T.v1y = a[2][1] - a[0][1];
+        T.d00 = (float)(T.v0x * T.v0x + T.v0y * T.v0y);
+        T.d01 = (float)(T.v0x * T.v1x + T.v0y * T.v1y);
+        T.d11 = (float)(T.v1x * T.v1x + T.v1y * T.v1y);
+        volatile float p0 = T.d00 * T.d11, p1 = T.d01 * T.d01;
+        const float den = p0 - p1;
+        T.ok = den != 0.0f;
+        T.inv = T.ok ? 1.0f / den : 0.0f;
+    }
+}
+
+int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views, int32_t n_views, uint8_t* out_rgb,
+               const b2r_debug_out* dbg, int32_t out_on_device) {
+    if (!g.ready) return fail("b2r_init was not called");
+    if (!sc || !fp || !views || n_views <= 0 || !out_rgb) return fail("b2r_render: bad arguments");
+    const int H = fp->height, W = fp->width;
+    if (H <= 0 || W <= 0 || H > 32000 || W > 32000) return fail("resolution out of range");
+    const int row_begin = std::max(0, fp->row_begin), row_end = std::min(H, fp->row_end <= 0 ? H : fp->row_end);
+    if (row_begin >= row_end) return fail("empty row band");
+    const bool with_sky = fp->bg_mode == B2R_BG_CUBEMAP;
+    if (with_sky && sc->sky_size == 0) return fail("cubemap background requested but the scene has no skybox");
+    const bool want_status = dbg && dbg->face_status;
+    const bool want_z = dbg && dbg->z;
+
+    FrameDev Fr;
+    std::memset(&Fr, 0, sizeof(Fr));
+    std::memcpy(Fr.light.position, fp->light.position, sizeof(double) * 3);
+    std::memcpy(Fr.light.direction, fp->light.direction, sizeof(double) * 3);
+    std::memcpy(Fr.light.color, fp->light.color, sizeof(double) * 3);
+    std::memcpy(Fr.light.ambient, fp->light.ambient, sizeof(double) * 3);
+    Fr.light.specular_strength = fp->light.specular_strength;
+    Fr.light.constant = fp->light.constant; Fr.light.linear = fp->light.linear; Fr.light.quadratic = fp->light.quadratic;
+    Fr.light.spot_cos_outer = fp->light.spot_cos_outer; Fr.light.spot_cos_inner = fp->light.spot_cos_inner;
+    Fr.light.type = fp->light.type;
+    for (int k = 0; k < 3; ++k) Fr.background[k] = fp->background[k];
+    Fr.bg_mode = fp->bg_mode;
+    Fr.H = H; Fr.W = W; Fr.row_begin = row_begin; Fr.row_end = row_end;
+    Fr.tiles_x = (W + TILE_W - 1) / TILE_W;
+    Fr.tile_row0 = row_begin / TILE_H;
+    Fr.tiles_y = (row_end - 1) / TILE_H - Fr.tile_row0 + 1;
+    Fr.n_faces = sc->n_faces;
+    Fr.sky_size = sc->sky_size;
+    Fr.want_status = want_status;
+    const int n_tiles = Fr.tiles_x * Fr.tiles_y;
+    const int F = sc->n_faces, E = std::max(1, sc->n_edges);
+    const size_t npx = (size_t)H * W;
+    const SceneDev S = sc->dev();
+
+    // views per chunk bounded by a scratch budget
+    const size_t per_view = (size_t)F * sizeof(TriRec) + (size_t)E * sizeof(QuadRec) + npx * 6 + (want_z ? npx * 8 : 0);
+    int VB = (int)std::max<size_t>(1, std::min<size_t>(n_views, ((size_t)6 << 30) / std::max<size_t>(per_view, 1)));
+    VB = std::min(VB, 64);
+    if (sc->tri_cap == 0) sc->tri_cap = std::max(1 << 16, 4 * F + 8 * n_tiles);
+    if (sc->quad_cap == 0) sc->quad_cap = std::max(1 << 20, 32 * E);
+    sc->tri_cap = std::max(sc->tri_cap, 8 * n_tiles);
+
+    g.n_stage = 0;
+    if (g.timing) cudaEventRecord(g.stage_ev[0], g.stream);
+
+    // ---- light-dependent, view-independent: facing flags and silhouette quads ----
+    CK(sc->facing.reserve(F + 4));
+    CK(sc->sil.reserve(E));
+    CK(sc->counters.reserve(1 + sc->n_models));
+    CK(cudaMemsetAsync(sc->counters.p, 0, sizeof(int) * (1 + sc->n_models), g.stream));
+    if (F > 0) {
+        k_facing<<<(F + 255) / 256, 256, 0, g.stream>>>(S, Fr.light, sc->facing.p);
+        ++g.launches;
+        if (sc->n_edges > 0) {
+            k_silhouette<<<(sc->n_edges + 255) / 256, 256, 0, g.stream>>>(
+                S, Fr.light, sc->facing.p, fp->persist_silhouette ? sc->sil_state.p : nullptr, sc->sil.p,
+                sc->counters.p, sc->counters.p + 1, sc->edge_model.p);
+            ++g.launches;
+        }
+    }
+    stage_mark("silhouette");
+
+    for (int first = 0; first < n_views; first += VB) {
+        const int nv = std::min(VB, n_views - first);
+        for (int attempt = 0; attempt < 4; ++attempt) {
+            CK(sc->views.reserve(VB));
+            CK(sc->tris.reserve((size_t)VB * F));
+            CK(sc->quads.reserve((size_t)VB * E));
+            CK(sc->tile_counts.reserve((size_t)VB * n_tiles * 2));
+            CK(sc->tile_offs.reserve((size_t)VB * (n_tiles + 1) * 2));
+            CK(sc->tri_list.reserve((size_t)VB * sc->tri_cap));
+            CK(sc->quad_list.reserve((size_t)VB * sc->quad_cap));
+            CK(sc->overflow.reserve((size_t)VB * 2));
+            CK(sc->winner.reserve((size_t)VB * npx));
+            CK(sc->stencil.reserve((size_t)VB * npx));
+            if (want_z) CK(sc->zplane.reserve((size_t)VB * npx));
+            if (want_status) CK(sc->status.reserve((size_t)VB * F + 8));
+            if (!out_on_device) CK(sc->rgb.reserve((size_t)VB * npx * 3));
+
+            std::vector<ViewDev> hv(nv);
+            for (int i = 0; i < nv; ++i) make_view(views[first + i], with_sky, hv[i]);
+            CK(cudaMemcpyAsync(sc->views.p, hv.data(), sizeof(ViewDev) * nv, cudaMemcpyHostToDevice, g.stream));
+            CK(cudaMemsetAsync(sc->tile_counts.p, 0, sizeof(int) * (size_t)VB * n_tiles * 2, g.stream));
+
+            BinDev B;
+            B.tri_count = sc->tile_counts.p; B.quad_count = sc->tile_counts.p + (size_t)VB * n_tiles;
+            B.tri_off = sc->tile_offs.p; B.quad_off = sc->tile_offs.p + (size_t)VB * (n_tiles + 1);
+            B.tri_list = sc->tri_list.p; B.quad_list = sc->quad_list.p;
+            B.tri_cap = sc->tri_cap; B.quad_cap = sc->quad_cap; B.overflow = sc->overflow.p;
+            uint8_t* status = want_status ? sc->status.p : nullptr;
+
+            if (F > 0) {
+                k_tri_setup<<<dim3((F + 127) / 128, nv), 128, 0, g.stream>>>(S, sc->views.p, Fr, sc->tris.p, status);
+                ++g.launches;
+            }
+            stage_mark("tri_setup");
+            const int quad_blocks = std::max(1, std::min((sc->n_edges + 63) / 64, g.sm_count * 4));
+            k_quad_setup<<<dim3(quad_blocks, nv), 64, 0, g.stream>>>(sc->sil.p, sc->counters.p, sc->views.p, Fr, sc->quads.p, E);
+            ++g.launches;
+            stage_mark("quad_setup");
+            const int bin_blocks = g.sm_count * 8;
+            k_bin<false><<<dim3(bin_blocks, nv), 256, 0, g.stream>>>(Fr, sc->tris.p, sc->quads.p, sc->counters.p, E, B);
+            k_scan<<<dim3(nv, 2), 1024, 0, g.stream>>>(Fr, B);
+            k_bin<true><<<dim3(bin_blocks, nv), 256, 0, g.stream>>>(Fr, sc->tris.p, sc->quads.p, sc->counters.p, E, B);
+            g.launches += 3;
+            stage_mark("bin");
+            RasterOut O;
+            O.winner = sc->winner.p; O.stencil = sc->stencil.p; O.z = want_z ? sc->zplane.p : nullptr; O.status = status;
+            k_raster<<<dim3(Fr.tiles_x, Fr.tiles_y, nv), RASTER_THREADS, 0, g.stream>>>(S, sc->views.p, Fr, sc->tris.p,
+                                                                                     sc->quads.p, E, B, O);
+            ++g.launches;
+            if (want_status) {
+                const size_t ns = (size_t)nv * F;
+                k_status_resolve<<<(unsigned)((ns + 255) / 256), 256, 0, g.stream>>>(status, ns);
+                ++g.launches;
+            }
+            stage_mark("raster");
+            uint8_t* rgb_dev = out_on_device ? out_rgb + (size_t)first * npx * 3 : sc->rgb.p;
+            const int rows = row_end - row_begin;
+            k_shade<<<dim3((W + 31) / 32, (rows + 7) / 8, nv), 256, 0, g.stream>>>(S, sc->views.p, Fr, sc->tris.p,
+                                                                               sc->winner.p, sc->stencil.p, rgb_dev);
+            ++g.launches;
+            stage_mark("shade");
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(g.pinned_flags, sc->overflow.p, sizeof(int) * 2 * nv, cudaMemcpyDeviceToHost, g.stream));
+
+            if (out_on_device && !dbg) break;  // asynchronous mode: overflow is reported by the next synchronous call
+            CK(cudaStreamSynchronize(g.stream));
+            int need_tri = 0, need_quad = 0;
+            for (int i = 0; i < nv; ++i) { need_tri = std::max(need_tri, g.pinned_flags[2 * i]); need_quad = std::max(need_quad, g.pinned_flags[2 * i + 1]); }
+            if (need_tri || need_quad) {
+                if (attempt == 3) return fail("tile list capacity overflow");
+                if (need_tri) { sc->tri_cap = need_tri + need_tri / 4; sc->tri_list.release(); }
+                if (need_quad) { sc->quad_cap = need_quad + need_quad / 4; sc->quad_list.release(); }
+                continue;
+            }
+            break;
+        }
+        // outputs of this chunk
+        const cudaMemcpyKind kind = out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+        if (!out_on_device) {
+            // only the rendered band is defined; copy whole frames for simplicity when the band is the frame
+            for (int i = 0; i < nv; ++i) {
+                const size_t off = ((size_t)(first + i) * H + (size_t)(H - row_end)) * W * 3;
+                const size_t src = ((size_t)i * H + (size_t)(H - row_end)) * W * 3;
+                CK(cudaMemcpyAsync(out_rgb + off, sc->rgb.p + src, (size_t)(row_end - row_begin) * W * 3, kind, g.stream));
+            }
+        }
+        if (dbg) {
+            if (dbg->z) CK(cudaMemcpyAsync(dbg->z + (size_t)first * npx, sc->zplane.p, sizeof(double) * nv * npx, kind, g.stream));
+            if (dbg->stencil) CK(cudaMemcpyAsync(dbg->stencil + (size_t)first * npx, sc->stencil.p, sizeof(short) * nv * npx, kind, g.stream));
+            if (dbg->winner) CK(cudaMemcpyAsync(dbg->winner + (size_t)first * npx, sc->winner.p, sizeof(int) * nv * npx, kind, g.stream));
+            if (dbg->face_status) CK(cudaMemcpyAsync(dbg->face_status + (size_t)first * F, sc->status.p, (size_t)nv * F, kind, g.stream));
+            if (dbg->n_silhouette)
+                for (int i = 0; i < nv; ++i)
+                    CK(cudaMemcpyAsync(dbg->n_silhouette + (size_t)(first + i) * sc->n_models, sc->counters.p + 1,
+                                       sizeof(int) * sc->n_models, kind, g.stream));
+        }
+        if (!out_on_device || dbg) CK(cudaStreamSynchronize(g.stream));
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,956 @@
+// b2r_kernels.cuh -- the sm_100a kernels of the frame pipeline (one translation unit with b2r_api.cu).
+//
+// Stage map (reference call sites in parentheses):
+//   k_facing        per face        light-facing flag                      (triangular.py:294-295)
+//   k_silhouette    per edge        parity of facing incident faces, extrusion to a world quad
+//                                                                          (triangular.py:296-302, core.py:610-621)
+//   k_tri_setup     per face x view vertex transform, cull, bbox, f32 bary constants, N==1 flags
+//                                                                          (triangular.py:36-78)
+//   k_quad_setup    per quad x view Sutherland-Hodgman clip, projection, plane, bbox
+//                                                                          (plane_intersection.py:59-86, triangular.py:319-340)
+//   k_bin<FILL>     per primitive   tile lists (count / fill), exact conservative tile test for quads
+//   k_scan          per view        exclusive scan of tile counts
+//   k_raster        per tile        z (64-bit keyed smem atomics) -> stencil spans -> winner id
+//                                                                          (triangular.py:78-118, 341-368)
+//   k_shade         per pixel       Phong + textures + tangent normal maps + skybox + tonemap
+//                                                                          (triangular.py:135-171, core.py:138-228,640; cube_map.py:63-101)
+#pragma once
+#include "b2r_device.cuh"
+
+namespace b2r {
+
+__constant__ float c_lut[2][256];  // [B2R_TEX_UNORM|B2R_TEX_SNORM][u8] -> the reference's float32 texel
+
+struct SceneDev {
+    const double4* pos;      // (Vtot) world positions, exact promotion of the model's storage
+    const double2* uv;       // (Ttot) u, v
+    const double* nrm;       // (Ntot,3)
+    const FaceStatic* faces; // (F)
+    const MaterialDev* mats;
+    const TextureDev* tex;
+    const uchar4* sky;       // (6,S,S) RGBX
+    const int2* edge_v;      // (E) canonical (lo, hi) GLOBAL vertex indices
+    const int* edge_ptr;     // (E+1)
+    const int* edge_inc;     // incidences: face << 1 | reversed, ordered by (face, corner)
+    int n_faces, n_edges;
+};
+
+// =====================================================================================================================
+// light-dependent, view-independent stages
+// =====================================================================================================================
+
+// Face.unit_normal_world_space @ light.position > 0   (core.py:127-130, triangular.py:295)
+__global__ void k_facing(SceneDev S, LightDev L, uint8_t* __restrict__ facing) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= S.n_faces) return;
+    const FaceStatic fs = S.faces[f];
+    const double4 a = S.pos[fs.v[0]], b = S.pos[fs.v[1]], c = S.pos[fs.v[2]];
+    double n[3];
+    if (fs.flags & FS_VTX_F32) {  // cross / norm / divide in float32, every op rounded
+        const float e0x = __fsub_rn((float)b.x, (float)a.x), e0y = __fsub_rn((float)b.y, (float)a.y),
+                    e0z = __fsub_rn((float)b.z, (float)a.z);
+        const float e1x = __fsub_rn((float)c.x, (float)a.x), e1y = __fsub_rn((float)c.y, (float)a.y),
+                    e1z = __fsub_rn((float)c.z, (float)a.z);
+        const float cx = __fsub_rn(__fmul_rn(e0y, e1z), __fmul_rn(e0z, e1y));
+        const float cy = __fsub_rn(__fmul_rn(e0z, e1x), __fmul_rn(e0x, e1z));
+        const float cz = __fsub_rn(__fmul_rn(e0x, e1y), __fmul_rn(e0y, e1x));
+        float l = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz)));
+        if (l == 0.0f) l = 1.0f;
+        n[0] = (double)__fdiv_rn(cx, l); n[1] = (double)__fdiv_rn(cy, l); n[2] = (double)__fdiv_rn(cz, l);
+    } else {
+        const double e0x = b.x - a.x, e0y = b.y - a.y, e0z = b.z - a.z, e1x = c.x - a.x, e1y = c.y - a.y, e1z = c.z - a.z;
+        n[0] = e0y * e1z - e0z * e1y; n[1] = e0z * e1x - e0x * e1z; n[2] = e0x * e1y - e0y * e1x;
+        normalize3(n);
+    }
+    facing[f] = seq3(n[0], n[1], n[2], L.position[0], L.position[1], L.position[2]) > 0 ? 1 : 0;
+}
+
+// One thread per undirected edge: replay the set toggles of shadow_volumes() in face order, then extrude.
+// state: 0 absent, 1 present as (lo,hi), 2 present as (hi,lo); `persist` != nullptr carries it across renders.
+__global__ void k_silhouette(SceneDev S, LightDev L, const uint8_t* __restrict__ facing, int8_t* persist,
+                             SilEdge* __restrict__ out, int* __restrict__ out_count, int* __restrict__ per_model_count,
+                             const int* __restrict__ edge_model) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= S.n_edges) return;
+    int state = persist ? persist[e] : 0;
+    for (int i = S.edge_ptr[e]; i < S.edge_ptr[e + 1]; ++i) {
+        const int inc = S.edge_inc[i];
+        if (facing[inc >> 1]) state = state ? 0 : 1 + (inc & 1);
+    }
+    if (persist) persist[e] = (int8_t)state;
+    if (!state) return;
+    const int2 ev = S.edge_v[e];
+    const double4 A4 = S.pos[state == 1 ? ev.x : ev.y], B4 = S.pos[state == 1 ? ev.y : ev.x];
+    const double A[4] = {A4.x, A4.y, A4.z, A4.w}, B[4] = {B4.x, B4.y, B4.z, B4.w};
+    double Cc[4], Dd[4];
+    if (L.type == B2R_LIGHT_POINT) {
+        const double lp[4] = {L.position[0], L.position[1], L.position[2], 1.0};
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const double* s = q ? B : A;
+            double* d = q ? Dd : Cc;
+            double dv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dv[k] = s[k] - lp[k];
+            double l = sqrt(((dv[0] * dv[0] + dv[1] * dv[1]) + dv[2] * dv[2]) + dv[3] * dv[3]);
+            if (l == 0) l = 1;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) d[k] = s[k] + 1000.0 * (dv[k] / l);
+        }
+    } else {  // DIRECTIONAL and SPOT: + (-1000*direction, 1)  => w = 2  (core.py:617-619)
+        const double off[4] = {L.direction[0] * -1000.0, L.direction[1] * -1000.0, L.direction[2] * -1000.0, 1.0};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { Cc[k] = A[k] + off[k]; Dd[k] = B[k] + off[k]; }
+    }
+    const int slot = atomicAdd(out_count, 1);
+    atomicAdd(per_model_count + edge_model[e], 1);
+    SilEdge& o = out[slot];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { o.q[k] = A[k]; o.q[4 + k] = B[k]; o.q[8 + k] = Dd[k]; o.q[12 + k] = Cc[k]; }
+}
+
+// =====================================================================================================================
+// per-view primitive setup
+// =====================================================================================================================
+__device__ __forceinline__ void load_clip_coords(const SceneDev& S, const ViewDev& V, const FaceStatic& fs, ClipCoords& cc) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double4 p = S.pos[fs.v[i]];
+        const double w[4] = {p.x, p.y, p.z, p.w};
+        vec4_mat4(w, V.mvp, cc.cs[i]);
+        vec4_mat4(w, V.mvp_dbg, cc.csd[i]);
+    }
+}
+
+// covered & unclipped test of one pixel, the predicate `Bi` of triangular.py:78-87
+__device__ __forceinline__ bool tri_pixel_in(const TriRec& r, const ClipCoords& cc, int px, int py, float& bu, float& bv,
+                                             float& bw) {
+    bool in = tri_bary(r, px, py, bu, bv, bw);
+    if (in && (r.flags & TR_NEEDS_CLIP)) {
+        double P[3];
+        persp_bary(r, bu, bv, bw, (r.flags & TR_BOX_ONE) != 0, P);
+        in = pixel_unclipped(cc, P, (r.flags & TR_BOX_ONE) != 0);
+    }
+    return in;
+}
+
+constexpr int COV_SERIAL_MAX = 128;  // boxes up to this many pixels are counted by the owning thread
+
+__global__ void k_tri_setup(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, TriRec* __restrict__ recs,
+                            uint8_t* __restrict__ status) {
+    const int view = blockIdx.y;
+    const ViewDev& V = views[view];
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    TriRec* my = nullptr;
+    bool need_coop = false;
+    FaceStatic fs;
+    ClipCoords cc;
+    if (f < S.n_faces) {
+        fs = S.faces[f];
+        load_clip_coords(S, V, fs, cc);
+        TriRec r;
+        double sx[3], sy[3], sz[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {  // triangular.py:42-45
+            const double dpt = 1.0 / cc.cs[i][3];
+            const double t[4] = {cc.cs[i][0] * dpt, cc.cs[i][1] * dpt, cc.cs[i][2] * dpt, cc.cs[i][3] * dpt};
+            double s[4];
+            vec4_mat4(t, V.viewport, s);
+            sx[i] = s[0]; sy[i] = s[1]; sz[i] = s[2];
+            r.d[i] = dpt;
+        }
+        int st = -1;
+        if (V.backface) {  // normalize(cross(b-a, c-a))[2] < 0 on screen xyz (triangular.py:47, core.py:132-136)
+            const double e0x = sx[1] - sx[0], e0y = sy[1] - sy[0], e0z = sz[1] - sz[0];
+            const double e1x = sx[2] - sx[0], e1y = sy[2] - sy[0], e1z = sz[2] - sz[0];
+            double n[3] = {e0y * e1z - e0z * e1y, e0z * e1x - e0x * e1z, e0x * e1y - e0y * e1x};
+            normalize3(n);
+            if (n[2] < 0) st = B2R_FACE_BACK_FACE_CULLING;
+        }
+        if (st < 0) {  // bound_box (transformation.py:35-43)
+            double mnx = fmin(fmin(sx[0], sx[1]), sx[2]), mxx = fmax(fmax(sx[0], sx[1]), sx[2]);
+            double mny = fmin(fmin(sy[0], sy[1]), sy[2]), mxy = fmax(fmax(sy[0], sy[1]), sy[2]);
+            mnx = mnx < 0 ? 0 : mnx; mxx = mxx > Fr.W ? (double)Fr.W : mxx;
+            mny = mny < 0 ? 0 : mny; mxy = mxy > Fr.H ? (double)Fr.H : mxy;
+            if (mnx > mxx || mny > mxy || !(mnx == mnx) || !(mxx == mxx) || !(mny == mny) || !(mxy == mxy)) {
+                st = B2R_FACE_EMPTY_Z;
+            } else {
+                r.bx0 = (short)(int)ceil(mnx); r.bx1 = (short)(int)ceil(mxx);
+                r.by0 = (short)(int)ceil(mny); r.by1 = (short)(int)ceil(mxy);
+            }
+        }
+        if (st < 0) {  // barycentric constants (transformation.py:16-28)
+            r.ax = sx[0]; r.ay = sy[0];
+            r.v0x = sx[1] - sx[0]; r.v0y = sy[1] - sy[0];
+            r.v1x = sx[2] - sx[0]; r.v1y = sy[2] - sy[0];
+            r.d00 = (float)seq2(r.v0x, r.v0y, r.v0x, r.v0y);
+            r.d01 = (float)seq2(r.v0x, r.v0y, r.v1x, r.v1y);
+            r.d11 = (float)seq2(r.v1x, r.v1y, r.v1x, r.v1y);
+            const float den = __fsub_rn(__fmul_rn(r.d00, r.d11), __fmul_rn(r.d01, r.d01));
+            if (den == 0.0f) st = B2R_FACE_EMPTY_B;
+            else r.inv = __fdiv_rn(1.0f, den);
+        }
+        if (st < 0) {
+            const int nx = r.bx1 > r.bx0 ? r.bx1 - r.bx0 : 0, ny = r.by1 > r.by0 ? r.by1 - r.by0 : 0;
+            const int n_box = nx * ny;
+            if (n_box == 0) st = B2R_FACE_CLIPPED;
+            else {
+                r.flags = TR_VALID | (n_box == 1 ? TR_BOX_ONE : 0);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) r.zl[i] = linearize_z(sz[i], V);
+                if (fs.flags & FS_CLIP) {
+                    // The per-pixel clip test passes for every covered pixel when all three vertices are inside
+                    // both frusta with a relative margin >> 6 ulp (DESIGN.md "clip test elision").
+                    bool inside = true;
+                    const double m = 1.0 - 1e-9;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const double w = cc.cs[i][3] * m, wd = cc.csd[i][3] * m;
+                        inside = inside && w > 0 && wd > 0 && fabs(cc.cs[i][0]) < w && fabs(cc.cs[i][1]) < w &&
+                                 fabs(cc.cs[i][2]) < w && fabs(cc.csd[i][0]) < wd && fabs(cc.csd[i][1]) < wd &&
+                                 fabs(cc.csd[i][2]) < wd;
+                    }
+                    if (!inside) r.flags |= TR_NEEDS_CLIP;
+                }
+                r.pad = 0;
+                // N of `bar_screen[Bi]` decides the evaluation order of the z interpolation: count covered &
+                // unclipped pixels, stopping at 2.
+                if (n_box <= COV_SERIAL_MAX) {
+                    int cnt = 0;
+                    for (int i = 0; i < n_box && cnt < 2; ++i) {
+                        const int px = r.bx0 + i / ny, py = r.by0 + i % ny;
+                        float bu, bv, bw;
+                        cnt += tri_pixel_in(r, cc, px, py, bu, bv, bw) ? 1 : 0;
+                    }
+                    if (cnt == 1) r.flags |= TR_COV_ONE;
+                    if (cnt == 0) { st = B2R_FACE_CLIPPED; r.flags = 0; }
+                } else {
+                    need_coop = true;
+                }
+                my = recs + (size_t)view * S.n_faces + f;
+                *my = r;
+            }
+        }
+        if (st >= 0) {
+            recs[(size_t)view * S.n_faces + f].flags = 0;
+            if (status) status[(size_t)view * S.n_faces + f] = (uint8_t)st;
+        } else if (status) {
+            status[(size_t)view * S.n_faces + f] = 0xE0;  // pending: raster ORs coverage / z / lit bits into the low bits
+        }
+    }
+    // warp-cooperative count for large boxes (ballot queue): lanes stride over the box, stop at 2 hits
+    unsigned queue = __ballot_sync(0xffffffffu, need_coop);
+    while (queue) {
+        const int src = __ffs(queue) - 1;
+        queue &= queue - 1;
+        const int sf = __shfl_sync(0xffffffffu, f, src);
+        __syncwarp();
+        const TriRec r = recs[(size_t)view * S.n_faces + sf];
+        ClipCoords c2;
+        if (r.flags & TR_NEEDS_CLIP) load_clip_coords(S, V, S.faces[sf], c2);
+        const int ny = r.by1 - r.by0, n_box = (r.bx1 - r.bx0) * ny;
+        int cnt = 0;
+        for (int base = 0; base < n_box && cnt < 2; base += 32) {
+            const int i = base + lane;
+            bool in = false;
+            if (i < n_box) {
+                float bu, bv, bw;
+                in = tri_pixel_in(r, c2, r.bx0 + i / ny, r.by0 + i % ny, bu, bv, bw);
+            }
+            cnt += __popc(__ballot_sync(0xffffffffu, in));
+        }
+        if (lane == src) {
+            if (cnt == 1) my->flags |= TR_COV_ONE;
+            if (cnt == 0) { my->flags = 0; if (status) status[(size_t)view * S.n_faces + f] = B2R_FACE_CLIPPED; }
+        }
+    }
+}
+
+// Sutherland-Hodgman against the six camera planes in homogeneous world space (plane_intersection.py:59-86),
+// then projection and plane set-up of resterize_quadrangle (triangular.py:325-340).  One thread per quad.
+__device__ void quad_setup_one(const SilEdge& sil, const ViewDev& V, const FrameDev& Fr, QuadRec& R);
+__global__ void k_quad_setup(const SilEdge* __restrict__ sil, const int* __restrict__ sil_count,
+                             const ViewDev* __restrict__ views, FrameDev Fr, QuadRec* __restrict__ recs, int rec_stride) {
+    const int view = blockIdx.y;
+    const ViewDev& V = views[view];
+    const int n_quads = *sil_count;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n_quads; q += gridDim.x * blockDim.x)
+        quad_setup_one(sil[q], V, Fr, recs[(size_t)view * rec_stride + q]);
+}
+
+__device__ void quad_setup_one(const SilEdge& sil, const ViewDev& V, const FrameDev& Fr, QuadRec& R) {
+    constexpr int CAP = 2 * B2R_MAX_POLY;
+    double bufA[CAP][4], bufB[CAP][4];
+    double (*cur)[4] = bufA;
+    double (*nxt)[4] = bufB;
+    int n = 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cur[i][k] = sil.q[i * 4 + k];
+    for (int p = 0; p < 6 && n > 0; ++p) {
+        const double* pl = V.planes + p * 4;
+        int m = 0;
+        for (int i = 0; i < n; ++i) {
+            const double* c = cur[i];
+            const double* nx = cur[(i + 1 == n) ? 0 : i + 1];
+            const bool cv = dot4_seq(pl, c) >= 0, nv = dot4_seq(pl, nx) >= 0;
+            if (cv && m < CAP) { for (int k = 0; k < 4; ++k) nxt[m][k] = c[k]; ++m; }
+            if (cv != nv) {  // line_plane_intersection(next, current, plane)  (plane_intersection.py:24-36)
+                double dir[4];
+                for (int k = 0; k < 4; ++k) dir[k] = c[k] - nx[k];
+                const double den = dot4_seq(pl, dir);
+                if (!(fabs(den) < 1e-10)) {
+                    const double wgt = -dot4_seq(pl, nx) / den;
+                    if (0 <= wgt && wgt <= 1 && m < CAP) {
+                        for (int k = 0; k < 4; ++k) nxt[m][k] = nx[k] + wgt * dir[k];
+                        ++m;
+                    }
+                }
+            }
+        }
+        n = m;
+        double (*t)[4] = cur; cur = nxt; nxt = t;
+    }
+    if (n < 3 || n > B2R_MAX_POLY) { R.n = 0; return; }
+    double sx[B2R_MAX_POLY], sy[B2R_MAX_POLY], sz[3];
+    for (int i = 0; i < n; ++i) {
+        double c[4], t[4], s[4];
+        vec4_mat4(cur[i], V.mvp, c);
+        for (int k = 0; k < 4; ++k) t[k] = c[k] / c[3];
+        vec4_mat4(t, V.viewport, s);
+        sx[i] = s[0]; sy[i] = s[1];
+        if (i < 3) sz[i] = s[2];
+    }
+    const double abx = sx[0] - sx[1], aby = sy[0] - sy[1], abz = sz[0] - sz[1];
+    const double acx = sx[0] - sx[2], acy = sy[0] - sy[2], acz = sz[0] - sz[2];
+    const double nx_ = aby * acz - abz * acy, ny_ = abz * acx - abx * acz, nz_ = abx * acy - aby * acx;
+    R.front = nz_ < 0 ? 1 : 0;
+    R.nx = nx_; R.ny = ny_; R.nz = nz_;
+    R.D = seq3(-sx[0], -sy[0], -sz[0], nx_, ny_, nz_);
+    double mnx = sx[0], mxx = sx[0], mny = sy[0], mxy = sy[0];
+    bool bad = false;
+    for (int i = 0; i < n; ++i) {
+        R.x[i] = sx[i]; R.y[i] = sy[i];
+        bad = bad || !(sx[i] == sx[i]) || !(sy[i] == sy[i]);
+        mnx = fmin(mnx, sx[i]); mxx = fmax(mxx, sx[i]); mny = fmin(mny, sy[i]); mxy = fmax(mxy, sy[i]);
+    }
+    mnx = mnx < 0 ? 0 : mnx; mxx = mxx > Fr.W ? (double)Fr.W : mxx;
+    mny = mny < 0 ? 0 : mny; mxy = mxy > Fr.H ? (double)Fr.H : mxy;
+    if (bad || mnx > mxx || mny > mxy) { R.n = 0; return; }
+    R.bx0 = (short)(int)ceil(mnx); R.bx1 = (short)(int)ceil(mxx);
+    R.by0 = (short)(int)ceil(mny); R.by1 = (short)(int)ceil(mxy);
+    R.n = (R.bx1 > R.bx0 && R.by1 > R.by0) ? n : 0;
+}
+
+// =====================================================================================================================
+// binning: per-tile primitive lists (count -> scan -> fill)
+// =====================================================================================================================
+// Strict inside test of resterize_quadrangle for one polygon edge (triangular.py:305-316), exactly as NumPy
+// evaluates np.cross on 2-vectors: (px-x0)*(y1-y0) - (py-y0)*(x1-x0), separate roundings.
+__device__ __forceinline__ double edge_fn(double px, double py, double x0, double y0, double ex, double ey) {
+    return (px - x0) * ey - (py - y0) * ex;
+}
+
+// Can the pixel rectangle [x0,x1] x [y0,y1] (inclusive) contain a pixel inside the polygon?  edge_fn is a
+// composition of monotone roundings, so its extreme over the rectangle is attained, EXACTLY, at a corner.
+__device__ __forceinline__ bool quad_may_touch(const QuadRec& R, int x0, int x1, int y0, int y1) {
+    for (int i = 0; i < R.n; ++i) {
+        const int j = (i + 1 == R.n) ? 0 : i + 1;
+        const double ex = R.x[j] - R.x[i], ey = R.y[j] - R.y[i];
+        if (R.front) {  // need f > 0 somewhere: take the corner maximising f
+            const double f = edge_fn(ey >= 0 ? x1 : x0, ex <= 0 ? y1 : y0, R.x[i], R.y[i], ex, ey);
+            if (!(f > 0)) return false;
+        } else {        // need f < 0 somewhere: corner minimising f
+            const double f = edge_fn(ey >= 0 ? x0 : x1, ex <= 0 ? y0 : y1, R.x[i], R.y[i], ex, ey);
+            if (!(f < 0)) return false;
+        }
+    }
+    return true;
+}
+
+struct BinDev {
+    int* tri_count;   // (views, n_tiles)  count, then running cursor during fill
+    int* quad_count;
+    int* tri_off;     // (views, n_tiles + 1) exclusive scan
+    int* quad_off;
+    int* tri_list;    // (views, tri_cap)
+    int* quad_list;   // (views, quad_cap)
+    int tri_cap, quad_cap;
+    int* overflow;    // (views, 2) required sizes when a list does not fit
+};
+
+// One warp per primitive slot: lanes stride over the tiles of the primitive's box.
+template <bool FILL>
+__global__ void k_bin(FrameDev Fr, const TriRec* __restrict__ tris, const QuadRec* __restrict__ quads,
+                      const int* __restrict__ sil_count, int quad_stride, BinDev B) {
+    const int view = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int n_tiles = Fr.tiles_x * Fr.tiles_y;
+    const int n_quads = *sil_count;
+    const int band_y0 = Fr.row_begin, band_y1 = Fr.row_end;
+    if (FILL && (B.overflow[view * 2] | B.overflow[view * 2 + 1])) return;
+    const int total_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; slot < Fr.n_faces + n_quads; slot += total_warps) {
+        int bx0, bx1, by0, by1;
+        const QuadRec* Q = nullptr;
+        int prim;
+        if (slot < Fr.n_faces) {
+            const TriRec& r = tris[(size_t)view * Fr.n_faces + slot];
+            if (!(r.flags & TR_VALID)) continue;
+            bx0 = r.bx0; bx1 = r.bx1; by0 = r.by0; by1 = r.by1;
+            prim = slot;
+        } else {
+            prim = slot - Fr.n_faces;
+            Q = quads + (size_t)view * quad_stride + prim;
+            if (Q->n == 0) continue;
+            bx0 = Q->bx0; bx1 = Q->bx1; by0 = Q->by0; by1 = Q->by1;
+        }
+        by0 = max(by0, band_y0); by1 = min(by1, band_y1);
+        if (by0 >= by1 || bx0 >= bx1) continue;
+        const int tx0 = bx0 / TILE_W, tx1 = (bx1 - 1) / TILE_W, ty0 = by0 / TILE_H, ty1 = (by1 - 1) / TILE_H;
+        const int tw = tx1 - tx0 + 1, nt = tw * (ty1 - ty0 + 1);
+        int* count = (Q ? B.quad_count : B.tri_count) + (size_t)view * n_tiles;
+        const int* off = (Q ? B.quad_off : B.tri_off) + (size_t)view * (n_tiles + 1);
+        int* list = Q ? B.quad_list + (size_t)view * B.quad_cap : B.tri_list + (size_t)view * B.tri_cap;
+        for (int i = lane; i < nt; i += 32) {
+            const int ty = ty0 + i / tw, tx = tx0 + i % tw;
+            if (Q) {
+                const int x0 = max(bx0, tx * TILE_W), x1 = min(bx1, (tx + 1) * TILE_W) - 1;
+                const int y0 = max(by0, ty * TILE_H), y1 = min(by1, (ty + 1) * TILE_H) - 1;
+                if (!quad_may_touch(*Q, x0, x1, y0, y1)) continue;
+            }
+            const int t = (ty - Fr.tile_row0) * Fr.tiles_x + tx;
+            if (FILL) list[off[t] + atomicAdd(count + t, 1)] = prim;
+            else atomicAdd(count + t, 1);
+        }
+    }
+}
+
+// exclusive scan of the tile counts of one (view, kind); resets the counts to 0 so k_bin<true> can reuse them
+// as cursors.  One CTA of 1024 threads.
+__global__ void k_scan(FrameDev Fr, BinDev B) {
+    const int view = blockIdx.x, kind = blockIdx.y;
+    const int n_tiles = Fr.tiles_x * Fr.tiles_y;
+    int* count = (kind ? B.quad_count : B.tri_count) + (size_t)view * n_tiles;
+    int* off = (kind ? B.quad_off : B.tri_off) + (size_t)view * (n_tiles + 1);
+    __shared__ int warp_sum[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int base = 0; base < n_tiles; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < n_tiles ? count[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) warp_sum[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            int s = warp_sum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+            warp_sum[lane] = s;
+        }
+        __syncthreads();
+        const int prefix = carry + (wid ? warp_sum[wid - 1] : 0) + x - v;
+        if (i < n_tiles) { off[i] = prefix; count[i] = 0; }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = prefix + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        off[n_tiles] = carry;
+        const int cap = kind ? B.quad_cap : B.tri_cap;
+        B.overflow[view * 2 + kind] = carry > cap ? carry : 0;
+    }
+}
+
+// =====================================================================================================================
+// tile raster: z -> stencil -> winner, all in shared memory
+// =====================================================================================================================
+struct RasterOut {
+    int* winner;        // (views, H, W)  buffer rows
+    short* stencil;     // (views, H, W)
+    double* z;          // optional
+    uint8_t* status;    // optional (views, F)
+};
+
+__global__ void __launch_bounds__(RASTER_THREADS)
+k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec* __restrict__ tris,
+         const QuadRec* __restrict__ quads, int quad_stride, BinDev B, RasterOut O) {
+    __shared__ unsigned long long s_z[TILE_PX];
+    __shared__ int s_id[TILE_PX];
+    __shared__ int s_st[TILE_PX];
+    const int view = blockIdx.z;
+    const ViewDev& V = views[view];
+    const int tx = blockIdx.x, ty = blockIdx.y + Fr.tile_row0;
+    const int n_tiles = Fr.tiles_x * Fr.tiles_y;
+    const int tile = blockIdx.y * Fr.tiles_x + tx;
+    const int X0 = tx * TILE_W, Y0 = ty * TILE_H;
+    const int X1 = min(X0 + TILE_W, Fr.W), Y1 = min(min(Y0 + TILE_H, Fr.H), Fr.row_end);
+    const int Yb0 = max(Y0, Fr.row_begin);
+    const bool rh = V.system == 1;
+    const unsigned long long z_init = zkey(rh ? __longlong_as_double(0x7FF0000000000000ll)
+                                              : __longlong_as_double(0xFFF0000000000000ll));
+    for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) { s_z[i] = z_init; s_id[i] = -1; s_st[i] = 0; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int NW = RASTER_THREADS / 32;
+    const int* tri_off = B.tri_off + (size_t)view * (n_tiles + 1);
+    const int* tri_list = B.tri_list + (size_t)view * B.tri_cap;
+    const int t_beg = tri_off[tile], t_end = tri_off[tile + 1];
+    const TriRec* vtris = tris + (size_t)view * Fr.n_faces;
+
+    // ---- phase 1: depth.  zbuf = min (RH) / max (LH) of z over covered, unclipped pixels  (triangular.py:96-118) ----
+    for (int t = t_beg + wid; t < t_end; t += NW) {
+        const int face = tri_list[t];
+        const TriRec r = vtris[face];
+        ClipCoords cc;
+        if (r.flags & TR_NEEDS_CLIP) load_clip_coords(S, V, S.faces[face], cc);
+        const int x0 = max((int)r.bx0, X0), x1 = min((int)r.bx1, X1), y0 = max((int)r.by0, Yb0), y1 = min((int)r.by1, Y1);
+        const int w = x1 - x0, n = w * (y1 - y0);
+        const bool cov_one = (r.flags & TR_COV_ONE) != 0;
+        for (int i = lane; i < n; i += 32) {
+            const int yy = i / w, px = x0 + i - yy * w, py = y0 + yy;
+            float bu, bv, bw;
+            if (!tri_pixel_in(r, cc, px, py, bu, bv, bw)) continue;
+            const double b0 = (double)bu, b1 = (double)bv, b2 = (double)bw;
+            const double z = cov_one ? seq3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2])
+                                     : gemv3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2]);
+            if (!(z == z)) continue;
+            const int p = (py - Y0) * TILE_W + (px - X0);
+            if (rh) atomicMin(&s_z[p], zkey(z)); else atomicMax(&s_z[p], zkey(z));
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: stencil.  one warp per quad, one lane per tile row, exact span search  (triangular.py:341-368) ----
+    {
+        const int* quad_off = B.quad_off + (size_t)view * (n_tiles + 1);
+        const int* quad_list = B.quad_list + (size_t)view * B.quad_cap;
+        const int q_beg = quad_off[tile], q_end = quad_off[tile + 1];
+        const QuadRec* vquads = quads + (size_t)view * quad_stride;
+        for (int t = q_beg + wid; t < q_end; t += NW) {
+            const QuadRec& R = vquads[quad_list[t]];
+            const int py = Y0 + lane;
+            int lo = max((int)R.bx0, X0), hi = min((int)R.bx1, X1) - 1;
+            const bool row_ok = py >= max((int)R.by0, Yb0) && py < min((int)R.by1, Y1);
+            if (!row_ok) hi = lo - 1;
+            const bool front = R.front != 0;
+            const int nv = R.n;
+            for (int e = 0; e < nv; ++e) {
+                const int j = (e + 1 == nv) ? 0 : e + 1;
+                const double xi = R.x[e], yi = R.y[e];
+                const double ex = R.x[j] - xi, ey = R.y[j] - yi;
+                if (lo > hi) continue;
+                const double c = ((double)py - yi) * ex;
+                // pred(px) := front ? f > 0 : f < 0, f = (px - xi)*ey - c, monotone in px
+                auto pred = [&](int px) {
+                    const double f = ((double)px - xi) * ey - c;
+                    return front ? (f > 0) : (f < 0);
+                };
+                const bool up = front ? (ey > 0) : (ey < 0);  // true set is upward closed in px
+                if (ey == 0 || !(ey == ey)) {
+                    if (!pred(lo)) hi = lo - 1;
+                } else if (up) {
+                    // smallest px in [lo,hi] with pred true
+                    if (!pred(hi)) { hi = lo - 1; }
+                    else {
+                        int a = lo, b = hi;  // pred(b) true
+                        while (a < b) { const int m = (a + b) >> 1; if (pred(m)) b = m; else a = m + 1; }
+                        lo = b;
+                    }
+                } else {
+                    if (!pred(lo)) { hi = lo - 1; }
+                    else {
+                        int a = lo, b = hi;  // pred(a) true
+                        while (a < b) { const int m = (a + b + 1) >> 1; if (pred(m)) a = m; else b = m - 1; }
+                        hi = a;
+                    }
+                }
+            }
+            const int delta = front ? 1 : -1;
+            for (int px = lo; px <= hi; ++px) {
+                double z = -(R.nx * (double)px + R.ny * (double)py + R.D) / R.nz;
+                z = linearize_z(z, V);
+                if (!(z == z)) continue;
+                const int p = (py - Y0) * TILE_W + (px - X0);
+                const unsigned long long kz = zkey(z), kb = s_z[p];
+                if (rh ? (kb >= kz) : (kb <= kz)) atomicAdd(&s_st[p], delta);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 3: winner = greatest face index among faces whose z equals the final zbuf  (A.5) ----
+    for (int t = t_beg + wid; t < t_end; t += NW) {
+        const int face = tri_list[t];
+        const TriRec r = vtris[face];
+        ClipCoords cc;
+        if (r.flags & TR_NEEDS_CLIP) load_clip_coords(S, V, S.faces[face], cc);
+        const int x0 = max((int)r.bx0, X0), x1 = min((int)r.bx1, X1), y0 = max((int)r.by0, Yb0), y1 = min((int)r.by1, Y1);
+        const int w = x1 - x0, n = w * (y1 - y0);
+        const bool cov_one = (r.flags & TR_COV_ONE) != 0;
+        unsigned bits = 0;
+        for (int i = lane; i < n; i += 32) {
+            const int yy = i / w, px = x0 + i - yy * w, py = y0 + yy;
+            float bu, bv, bw;
+            if (!tri_pixel_in(r, cc, px, py, bu, bv, bw)) continue;
+            bits |= 1;
+            const double b0 = (double)bu, b1 = (double)bv, b2 = (double)bw;
+            const double z = cov_one ? seq3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2])
+                                     : gemv3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2]);
+            if (!(z == z)) continue;
+            const int p = (py - Y0) * TILE_W + (px - X0);
+            if (zkey(z) == s_z[p]) {
+                atomicMax(&s_id[p], face);
+                bits |= 2 | (s_st[p] == 0 ? 4 : 0);
+            }
+        }
+        if (O.status) {
+            bits = __reduce_or_sync(0xffffffffu, bits);
+            if (lane == 0 && bits) {
+                uint8_t* sp = O.status + (size_t)view * Fr.n_faces + face;
+                unsigned* wp = (unsigned*)((uintptr_t)sp & ~(uintptr_t)3);
+                atomicOr(wp, bits << (8 * ((uintptr_t)sp & 3)));
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- write-back (coalesced rows) ----
+    const size_t plane = (size_t)view * Fr.H * Fr.W;
+    for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) {
+        const int px = X0 + (i & (TILE_W - 1)), py = Y0 + i / TILE_W;
+        if (px < X1 && py >= Yb0 && py < Y1) {
+            const size_t g = plane + (size_t)py * Fr.W + px;
+            O.winner[g] = s_id[i];
+            O.stencil[g] = (short)s_st[i];
+            if (O.z) O.z[g] = zkey_decode(s_z[i]);
+        }
+    }
+}
+
+// =====================================================================================================================
+// shading
+// =====================================================================================================================
+__device__ __forceinline__ void texel_fetch(const TextureDev& T, const double P[3], const double uu[3], const double vv[3],
+                                            float out[3]) {
+    // Face.get_UV (core.py:138-143): clip(max=1), scale by (size-1), truncate, python-style negative wrap
+    double cu = gemv3(P[0], P[1], P[2], uu[0], uu[1], uu[2]);
+    double cv = gemv3(P[0], P[1], P[2], vv[0], vv[1], vv[2]);
+    cu = cu > 1.0 ? 1.0 : cu;
+    double rv = 1.0 - cv;
+    rv = rv > 1.0 ? 1.0 : rv;
+    int col = (int)(cu * (double)(T.width - 1));
+    int row = (int)(rv * (double)(T.height - 1));
+    if (col < 0) col += T.width;
+    if (row < 0) row += T.height;
+    if (col < 0 || col >= T.width) col = 0;
+    if (row < 0 || row >= T.height) row = 0;
+    const uchar4 t = __ldg(T.texels + (size_t)row * T.width + col);
+    const float* lut = c_lut[T.decode];
+    out[0] = lut[t.x]; out[1] = lut[t.y]; out[2] = lut[t.z];
+}
+
+// inverse of a 3x3 by LU with partial pivoting + solves against the identity (what np.linalg.inv -> dgesv does)
+__device__ __forceinline__ void inv3(const double A[9], double out[9]) {
+    double a[9];
+    int perm[3] = {0, 1, 2};
+#pragma unroll
+    for (int i = 0; i < 9; ++i) a[i] = A[i];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        int p = k;
+        double best = fabs(a[k * 3 + k]);
+#pragma unroll
+        for (int r = k + 1; r < 3; ++r) if (fabs(a[r * 3 + k]) > best) { best = fabs(a[r * 3 + k]); p = r; }
+        if (p != k) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { const double t = a[k * 3 + c]; a[k * 3 + c] = a[p * 3 + c]; a[p * 3 + c] = t; }
+            const int t = perm[k]; perm[k] = perm[p]; perm[p] = t;
+        }
+        const double piv = 1.0 / a[k * 3 + k];
+#pragma unroll
+        for (int r = k + 1; r < 3; ++r) {
+            a[r * 3 + k] *= piv;
+#pragma unroll
+            for (int c = k + 1; c < 3; ++c) a[r * 3 + c] -= a[r * 3 + k] * a[k * 3 + c];
+        }
+    }
+#pragma unroll
+    for (int col = 0; col < 3; ++col) {
+        double y[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) y[r] = perm[r] == col ? 1.0 : 0.0;
+        y[1] -= a[3] * y[0];
+        y[2] -= a[6] * y[0];
+        y[2] -= a[7] * y[1];
+        y[2] /= a[8];
+        y[1] -= a[5] * y[2];
+        y[1] /= a[4];
+        y[0] -= a[1] * y[1];
+        y[0] -= a[2] * y[2];
+        y[0] /= a[0];
+        out[0 + col] = y[0]; out[3 + col] = y[1]; out[6 + col] = y[2];
+    }
+}
+
+__device__ __forceinline__ double pow_ns(double x, const MaterialDev& M) {
+    if (M.ns_int >= 0) {  // exponentiation by squaring for the usual integer shininess (64, 32, ...)
+        double r = 1.0, b = x;
+        int e = M.ns_int;
+        while (e) { if (e & 1) r *= b; b *= b; e >>= 1; }
+        return r;
+    }
+    return pow(x, M.Ns);
+}
+
+__device__ __forceinline__ float clip01(double v) { return (float)(v < 0.05 ? 0.05 : (v > 1.0 ? 1.0 : v)); }
+
+// general_shading for one pixel (triangular.py:135-171)
+__device__ void shade_face_pixel(const SceneDev& S, const ViewDev& V, const LightDev& L, const TriRec& r, int face,
+                                 int px, int py, bool lit, float out[3]) {
+    const FaceStatic fs = S.faces[face];
+    const MaterialDev& M = S.mats[fs.material];
+    float bu, bv, bw;
+    tri_bary(r, px, py, bu, bv, bw);
+    double P[3];
+    persp_bary(r, bu, bv, bw, false, P);
+    double uu[3] = {0, 0, 0}, vv[3] = {0, 0, 0};
+    if (fs.flags & FS_HAS_UV) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { const double2 t = S.uv[fs.t[c]]; uu[c] = t.x; vv[c] = t.y; }
+    }
+    double albedo[3];
+    if (M.map_Kd >= 0) {
+        float t[3];
+        texel_fetch(S.tex[M.map_Kd], P, uu, vv, t);
+        albedo[0] = (double)t[0]; albedo[1] = (double)t[1]; albedo[2] = (double)t[2];
+    } else {
+        albedo[0] = M.Kd[0]; albedo[1] = M.Kd[1]; albedo[2] = M.Kd[2];
+    }
+    double wp[3][3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { const double4 p = S.pos[fs.v[c]]; wp[c][0] = p.x; wp[c][1] = p.y; wp[c][2] = p.z; }
+    double frag[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) frag[k] = seq3(P[0], P[1], P[2], wp[0][k], wp[1][k], wp[2][k]);
+    double dl[3] = {L.position[0] - frag[0], L.position[1] - frag[1], L.position[2] - frag[2]};
+    const double dist = norm3(dl[0], dl[1], dl[2]);
+    const double att = 1.0 / (L.constant + dist * (L.linear + L.quadratic * dist));  // core.py:517-524
+    if (!lit) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) out[k] = clip01(att * L.ambient[k] * albedo[k]);
+        return;
+    }
+    // Face.get_normals (core.py:175-189)
+    double vn[3][3];
+    if (fs.flags & FS_HAS_NORMALS) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) vn[c][k] = S.nrm[(size_t)fs.n[c] * 3 + k];
+    }
+    double N[3];
+    if (M.norm >= 0) {
+        const TextureDev& T = S.tex[M.norm];
+        float t[3];
+        texel_fetch(T, P, uu, vv, t);
+        if (T.tangent) {  // Face.tangent_ (core.py:191-224)
+            double n[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) n[k] = seq3(P[0], P[1], P[2], vn[0][k], vn[1][k], vn[2][k]);
+            normalize3(n);
+            double A[9], AI[9];
+            if (fs.flags & FS_VTX_F32) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    A[k] = (double)__fsub_rn((float)wp[1][k], (float)wp[0][k]);
+                    A[3 + k] = (double)__fsub_rn((float)wp[2][k], (float)wp[0][k]);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { A[k] = wp[1][k] - wp[0][k]; A[3 + k] = wp[2][k] - wp[0][k]; }
+            }
+            A[6] = n[0]; A[7] = n[1]; A[8] = n[2];
+            inv3(A, AI);
+            double du1, du2, dv1, dv2;
+            if (fs.flags & FS_UV_F32) {
+                du1 = (double)__fsub_rn((float)uu[1], (float)uu[0]); du2 = (double)__fsub_rn((float)uu[2], (float)uu[0]);
+                dv1 = (double)__fsub_rn((float)vv[1], (float)vv[0]); dv2 = (double)__fsub_rn((float)vv[2], (float)vv[0]);
+            } else {
+                du1 = uu[1] - uu[0]; du2 = uu[2] - uu[0]; dv1 = vv[1] - vv[0]; dv2 = vv[2] - vv[0];
+            }
+            double ti[3], tj[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                ti[q] = gemv3(AI[q * 3], AI[q * 3 + 1], AI[q * 3 + 2], du1, du2, 0.0);
+                tj[q] = gemv3(AI[q * 3], AI[q * 3 + 1], AI[q * 3 + 2], dv1, dv2, 0.0);
+            }
+            normalize3(ti); normalize3(tj);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) N[q] = seq3(ti[q], tj[q], n[q], (double)t[0], (double)t[1], (double)t[2]);
+        } else {
+            N[0] = (double)t[0]; N[1] = (double)t[1]; N[2] = (double)t[2];
+        }
+    } else if (fs.flags & FS_HAS_NORMALS) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) N[k] = seq3(P[0], P[1], P[2], vn[0][k], vn[1][k], vn[2][k]);
+    } else {  // flat normal in the vertex dtype (core.py:186-187)
+        double fn[3];
+        if (fs.flags & FS_VTX_F32) {
+            float a[3], b[3], c[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { a[k] = (float)wp[0][k]; b[k] = (float)wp[1][k]; c[k] = (float)wp[2][k]; }
+            const float e0x = __fsub_rn(b[0], a[0]), e0y = __fsub_rn(b[1], a[1]), e0z = __fsub_rn(b[2], a[2]);
+            const float e1x = __fsub_rn(c[0], a[0]), e1y = __fsub_rn(c[1], a[1]), e1z = __fsub_rn(c[2], a[2]);
+            const float cx = __fsub_rn(__fmul_rn(e0y, e1z), __fmul_rn(e0z, e1y));
+            const float cy = __fsub_rn(__fmul_rn(e0z, e1x), __fmul_rn(e0x, e1z));
+            const float cz = __fsub_rn(__fmul_rn(e0x, e1y), __fmul_rn(e0y, e1x));
+            float l = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz)));
+            if (l == 0.0f) l = 1.0f;
+            fn[0] = (double)__fdiv_rn(cx, l); fn[1] = (double)__fdiv_rn(cy, l); fn[2] = (double)__fdiv_rn(cz, l);
+        } else {
+            const double e0x = wp[1][0] - wp[0][0], e0y = wp[1][1] - wp[0][1], e0z = wp[1][2] - wp[0][2];
+            const double e1x = wp[2][0] - wp[0][0], e1y = wp[2][1] - wp[0][1], e1z = wp[2][2] - wp[0][2];
+            fn[0] = e0y * e1z - e0z * e1y; fn[1] = e0z * e1x - e0x * e1z; fn[2] = e0x * e1y - e0y * e1x;
+            normalize3(fn);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) N[k] = seq3(P[0], P[1], P[2], fn[k], fn[k], fn[k]);
+    }
+    normalize3(N);
+    double Ld[3];
+    if (L.type == B2R_LIGHT_DIRECTIONAL) { Ld[0] = L.direction[0]; Ld[1] = L.direction[1]; Ld[2] = L.direction[2]; }
+    else { Ld[0] = dl[0]; Ld[1] = dl[1]; Ld[2] = dl[2]; normalize3(Ld); }
+    double Vd[3] = {V.cam_pos[0] - frag[0], V.cam_pos[1] - frag[1], V.cam_pos[2] - frag[2]};
+    normalize3(Vd);
+    if (L.type == B2R_LIGHT_SPOT) {  // triangular.py:157-161, core.py:497-515
+        double x = dot3_plain(L.direction, Ld);
+        x = (x - L.spot_cos_outer) / (L.spot_cos_inner - L.spot_cos_outer);
+        x = x < 0.0 ? 0.0 : (x > 1.0 ? 1.0 : x);
+        const double s = x * x * (3.0 - 2.0 * x);
+        albedo[0] *= s; albedo[1] *= s; albedo[2] *= s;
+    }
+    double spec_light[3];
+    if (M.map_Ks >= 0) {  // core.py:145-153: float32 texel * 255
+        float t[3];
+        texel_fetch(S.tex[M.map_Ks], P, uu, vv, t);
+        const double s = (double)__fmul_rn(t[0], 255.0f);
+        spec_light[0] = spec_light[1] = spec_light[2] = s;
+    } else {
+        spec_light[0] = M.Ks255[0]; spec_light[1] = M.Ks255[1]; spec_light[2] = M.Ks255[2];
+    }
+    double Hd[3] = {Ld[0] + Vd[0], Ld[1] + Vd[1], Ld[2] + Vd[2]};
+    normalize3(Hd);
+    double nh = dot3_plain(N, Hd);
+    nh = nh < 0 ? 0 : nh;
+    const double sr = pow_ns(nh, M);
+    const double nl = dot3_plain(N, Ld);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double specular = L.color[k] * sr * L.specular_strength * spec_light[k];
+        const double diffuse = nl * L.color[k];
+        out[k] = clip01(att * albedo[k] * (L.ambient[k] + diffuse + specular));
+    }
+}
+
+// cube_map.py:63-101 for one background pixel; returns false when neither screen triangle covers it
+__device__ __forceinline__ bool skybox_pixel(const SceneDev& S, const ViewDev& V, int sky_size, int px, int py, float out[3]) {
+#pragma unroll
+    for (int t = 1; t >= 0; --t) {  // the second triangle is written last in the reference, so it wins
+        const SkyTri& T = V.sky[t];
+        if (!T.ok) continue;
+        const long long v2x = px - T.ax, v2y = py - T.ay;
+        const float d20 = (float)(v2x * T.v0x + v2y * T.v0y), d21 = (float)(v2x * T.v1x + v2y * T.v1y);
+        const float bv = __fmul_rn(__fsub_rn(__fmul_rn(T.d11, d20), __fmul_rn(T.d01, d21)), T.inv);
+        const float bw = __fmul_rn(__fsub_rn(__fmul_rn(T.d00, d21), __fmul_rn(T.d01, d20)), T.inv);
+        const float bu = __fsub_rn(__fsub_rn(1.0f, bv), bw);
+        if (!(bu >= 0.0f && bv >= 0.0f && bw >= 0.0f)) continue;
+        double r[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) r[k] = seq3((double)bu, (double)bv, (double)bw, T.rays[0][k], T.rays[1][k], T.rays[2][k]);
+        int axis = 0;
+        double best = fabs(r[0]);
+        if (fabs(r[1]) > best) { best = fabs(r[1]); axis = 1; }
+        if (fabs(r[2]) > best) { axis = 2; }
+        const double amp = axis == 0 ? r[0] : (axis == 1 ? r[1] : r[2]);
+        const double o0 = axis == 0 ? r[1] : r[0], o1 = axis == 2 ? r[1] : r[2];
+        const double u0 = (o0 / amp + 1.0) / 2.0, u1 = (o1 / amp + 1.0) / 2.0;
+        const int side = (amp < 0 ? 1 : 0) + axis * 2;
+        long long i0 = (long long)(u0 * (double)sky_size - 1.0), i1 = (long long)(u1 * (double)sky_size - 1.0);
+        if (i0 < 0) i0 += sky_size;
+        if (i1 < 0) i1 += sky_size;
+        if (i0 < 0 || i0 >= sky_size) i0 = 0;
+        if (i1 < 0 || i1 >= sky_size) i1 = 0;
+        const uchar4 tx = __ldg(S.sky + ((size_t)side * sky_size + i0) * sky_size + i1);
+        out[0] = c_lut[0][tx.x]; out[1] = c_lut[0][tx.y]; out[2] = c_lut[0][tx.z];
+        return true;
+    }
+    return false;
+}
+
+// One thread per pixel; a warp covers 32 consecutive pixels of one buffer row and packs its 96 output bytes into
+// 24 aligned 32-bit stores.  Output row = H-1-py (core.py:640).
+__global__ void __launch_bounds__(256)
+k_shade(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec* __restrict__ tris,
+        const int* __restrict__ winner, const short* __restrict__ stencil, uint8_t* __restrict__ out_rgb) {
+    const int view = blockIdx.z;
+    const ViewDev& V = views[view];
+    const int lane = threadIdx.x & 31;
+    const int px = blockIdx.x * 32 + lane;
+    const int py = Fr.row_begin + blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (py >= Fr.row_end) return;  // whole warp
+    float c[3] = {0.f, 0.f, 0.f};
+    if (px < Fr.W) {
+        const size_t g = (size_t)view * Fr.H * Fr.W + (size_t)py * Fr.W + px;
+        const int face = winner[g];
+        if (face >= 0) {
+            shade_face_pixel(S, V, Fr.light, tris[(size_t)view * Fr.n_faces + face], face, px, py, stencil[g] == 0, c);
+        } else if (Fr.bg_mode == B2R_BG_CUBEMAP) {
+            skybox_pixel(S, V, Fr.sky_size, px, py, c);
+        } else {
+            c[0] = Fr.background[0]; c[1] = Fr.background[1]; c[2] = Fr.background[2];
+        }
+    }
+    // (frame ** 0.8 * 255).astype(uint8) in float32
+    unsigned packed = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float v = __fmul_rn(powf(c[k], 0.8f), 255.0f);
+        packed |= ((unsigned)(int)v & 0xffu) << (8 * k);
+    }
+    uint8_t* row = out_rgb + ((size_t)view * Fr.H + (size_t)(Fr.H - 1 - py)) * Fr.W * 3;
+    const int x_base = blockIdx.x * 32;
+    if (x_base + 32 <= Fr.W && (((size_t)Fr.W * 3) & 3) == 0) {
+        // lane j < 24 assembles bytes 4j..4j+3 of the warp's 96-byte run
+        unsigned word = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int byte = 4 * lane + b;           // may exceed 95 for lanes >= 24 (ignored)
+            const int src = (byte / 3) & 31, ch = byte % 3;
+            const unsigned v = __shfl_sync(0xffffffffu, packed, src);
+            word |= ((v >> (8 * ch)) & 0xffu) << (8 * b);
+        }
+        if (lane < 24) reinterpret_cast<unsigned*>(row + (size_t)x_base * 3)[lane] = word;
+    } else if (px < Fr.W) {
+        row[(size_t)px * 3 + 0] = (uint8_t)(packed & 0xff);
+        row[(size_t)px * 3 + 1] = (uint8_t)((packed >> 8) & 0xff);
+        row[(size_t)px * 3 + 2] = (uint8_t)((packed >> 16) & 0xff);
+    }
+}
+
+// pass-3 status of every face (core.py:624-636): pending faces carry coverage / z / lit bits ORed in by k_raster
+__global__ void k_status_resolve(uint8_t* __restrict__ status, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t s = status[i];
+    if ((s & 0xE0) != 0xE0) return;
+    status[i] = (s & 4) ? B2R_FACE_RENDERED : ((s & 1) ? B2R_FACE_EMPTY_Z : B2R_FACE_CLIPPED);
+}
+
+}  // namespace b2r
