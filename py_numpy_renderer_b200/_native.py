@@ -167,20 +167,31 @@ class DeviceScene:
         base = int(self.vertex_base[model_index])
         return {(int(a) - base, int(b) - base) for a, b in pairs[:n][sel]}
 
-    def render(self, cameras, debug_camera, light, resolution, system, background, persist_silhouette=False,
-               want_debug=False, out=None, band=None):
-        """-> (frames, info).  frames: uint8 (n, H, W, 3) NumPy array, or `out` (a CUDA tensor / device pointer,
-        written asynchronously on the library stream) when given."""
+    def pack(self, cameras, debug_cameras, light, resolution, system, background, persist_silhouette=False, band=None):
+        """Host-side evaluation of the per-view constants (the reference's NumPy camera maths) -> (fp, views)."""
         n = len(cameras)
-        H, W = int(resolution[0]), int(resolution[1])
-        fp = pack_frame_params(light, (H, W), background, persist_silhouette, band)
-        views = (View * n)(*[pack_view(c, debug_camera, system, self.has_sky) for c in cameras])
+        fp = pack_frame_params(light, (int(resolution[0]), int(resolution[1])), background, persist_silhouette, band)
+        views = (View * n)(*[pack_view(c, d, system, self.has_sky) for c, d in zip(cameras, debug_cameras)])
+        return fp, views
+
+    def render(self, cameras, debug_cameras, light, resolution, system, background, persist_silhouette=False,
+               want_debug=False, out=None, band=None):
+        fp, views = self.pack(cameras, debug_cameras, light, resolution, system, background, persist_silhouette, band)
+        return self.render_packed(fp, views, want_debug=want_debug, out=out)
+
+    def render_packed(self, fp, views, want_debug=False, out=None):
+        """-> (frames, info).  frames: uint8 (n, H, W, 3): a new NumPy array, `out` if it is a NumPy array (filled
+        synchronously; pinned memory makes the copy fast), or `out` if it is a CUDA tensor / device pointer
+        (written asynchronously on the library stream)."""
+        n = len(views)
+        H, W = fp.height, fp.width
+        band = None if (fp.row_begin, fp.row_end) == (0, H) else (fp.row_begin, fp.row_end)
         info = {}
         dbg = None
-        on_device = out is not None
+        on_device = out is not None and not isinstance(out, np.ndarray)
         if want_debug:
             if on_device:
-                raise ValueError("debug planes are only returned to host memory")
+                raise ValueError("debug planes are only returned together with host frames")
             F, M = self.packed.total_faces, self.packed.n_models
             info = dict(face_status=np.zeros((n, max(F, 1)), np.uint8), n_silhouette=np.zeros((n, max(M, 1)), np.int32))
             if want_debug != 'status':  # full planes
@@ -189,10 +200,14 @@ class DeviceScene:
             dbg = DebugOut(*[info[k].ctypes.data if k in info else None
                              for k in ('z', 'stencil', 'winner', 'face_status', 'n_silhouette')])
         if on_device:
-            target = _dev_ptr(out)
-            frames = out
+            target, frames = _dev_ptr(out), out
         else:
-            frames = np.zeros((n, H, W, 3), np.uint8) if band is not None else np.empty((n, H, W, 3), np.uint8)
+            if out is not None:
+                if out.dtype != np.uint8 or out.shape != (n, H, W, 3) or not out.flags.c_contiguous:
+                    raise ValueError("out must be a C-contiguous uint8 array of shape (n, H, W, 3)")
+                frames = out
+            else:
+                frames = np.zeros((n, H, W, 3), np.uint8) if band is not None else np.empty((n, H, W, 3), np.uint8)
             target = C.c_void_p(frames.ctypes.data)
         _check(self.lib.b2r_render(self.handle, C.byref(fp), C.cast(views, C.c_void_p), n, target,
                                    C.byref(dbg) if dbg is not None else None, int(on_device)))

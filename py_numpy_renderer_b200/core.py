@@ -343,7 +343,7 @@ class Scene:
         `debug`, if a dict, receives the z / stencil / winner planes and per-face status of this frame."""
         from . import _native
         dev = self._device_scene()
-        frames, info = dev.render([self.camera], self.debug_camera, self.light, self.resolution, self.system,
+        frames, info = dev.render([self.camera], [self.debug_camera], self.light, self.resolution, self.system,
                                   self._background(), persist_silhouette=self.persist_silhouette,
                                   want_debug=True if debug is not None else ('status' if self.verbose else False))
         if isinstance(self.skybox, CubeMap):
@@ -357,16 +357,21 @@ class Scene:
             debug.update({k: v[0] for k, v in info.items()})
         return frames[0]
 
-    def render_batch(self, cameras, debug=None, out=None, rank_band=None) -> np.ndarray:
-        """Extension: render one frame per camera in `cameras` with this scene's models / light /
-        resolution; returns uint8 (len(cameras), H, W, 3).  Every view starts from an empty silhouette set
-        (fresh-Model semantics), and nothing is printed."""
+    def render_batch(self, cameras, debug_cameras=None, debug=None, out=None, band=None):
+        """Extension: one frame per camera in `cameras` with this scene's models / light /
+        resolution.  `debug_cameras`: one per camera (the second clip frustum of triangular.py:39,83-87), default
+        = the scene's debug camera for all.  Every view starts from an empty silhouette set (fresh-Model semantics)
+        and nothing is printed.  Returns uint8 (len(cameras), H, W, 3): a new NumPy array, or `out` when given --
+        a (pinned) NumPy array is filled synchronously, a CUDA tensor is written asynchronously on the library
+        stream (`_native.sync()` or stream ordering before use).  `band=(row0,row1)` restricts work to buffer rows
+        [row0,row1) (multi-GPU screen split); other rows of the output are left untouched."""
         dev = self._device_scene()
-        for cam in cameras:
+        cameras = list(cameras)
+        dcams = [self.debug_camera] * len(cameras) if debug_cameras is None else list(debug_cameras)
+        for cam in cameras + dcams:
             cam.scene = self
-        frames, info = dev.render(list(cameras), self.debug_camera, self.light, self.resolution, self.system,
-                                  self._background(), persist_silhouette=False, want_debug=debug is not None,
-                                  out=out, band=rank_band)
+        frames, info = dev.render(cameras, dcams, self.light, self.resolution, self.system, self._background(),
+                                  persist_silhouette=False, want_debug=debug is not None, out=out, band=band)
         if debug is not None:
             debug.update(info)
         return frames

@@ -1,0 +1,186 @@
+"""Parity tests proper: the CUDA path (through the Python API -> C ABI -> sm_100a kernels) against
+(1) the committed outputs of the unmodified reference and (2) the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north star): z-buffer (float64), stencil counts, z-test winners and per-face status bit-exact;
+uint8 RGB within 1 LSB on >= 99.9 % of the pixels.  All run on the B200 box:  pytest -m gpu
+"""
+import numpy as np
+import pytest
+
+import golden_util as gu
+import scenes
+import py_numpy_renderer_b200 as b2r
+
+pytestmark = pytest.mark.gpu
+NAMES = gu.fixture_names()
+
+
+def gpu_render(scene):
+    scene.persist_silhouette = False
+    dbg = {}
+    rgb = scene.render(debug=dbg)
+    return dict(rgb=rgb, z=dbg['z'], stencil=dbg['stencil'], winner=dbg['winner'], face_status=dbg['face_status'],
+                n_silhouette=dbg['n_silhouette'])
+
+
+def oracle_render(oracle, scene, cameras=None):
+    out = oracle.render_scene(scene, cameras=cameras, threads=4)
+    return out
+
+
+def assert_parity(got, want, exact_rgb=False):
+    rep = gu.compare_planes(got, want)
+    assert rep['z_mismatch'] == 0, rep
+    assert rep['stencil_mismatch'] == 0, rep
+    assert rep['winner_mismatch'] == 0, rep
+    assert rep['rgb_px_gt1'] == 0, rep                        # never off by more than 1 LSB
+    assert rep['rgb_px_diff'] * 1000 <= rep['pixels'], rep    # >= 99.9 % of the pixels identical
+    if exact_rgb:
+        assert rep['rgb_px_diff'] == 0, rep
+    return rep
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_fixture_vs_reference_and_oracle(name, oracle):
+    scene, exp, meta = gu.load(name)
+    got = gpu_render(scene)
+    assert_parity(got, exp)                                   # vs the unmodified Python reference
+    want = {k: v[0] for k, v in oracle_render(oracle, scene).items()}
+    assert_parity(got, want)                                  # vs the oracle
+    assert np.array_equal(got['face_status'], want['face_status'])
+    assert list(got['n_silhouette']) == meta['n_silhouette']
+
+
+@pytest.mark.parametrize("light", ["POINT_LIGHTNING", "SPOT_LIGHTNING", "DIRECTIONAL_LIGHTNING"])
+def test_c3_synthetic_1080p_vs_oracle(light, oracle):
+    """BASELINE config 3 at its full size (1080x1920, 5000-triangle figure + floor, shadow volumes)."""
+    scene = scenes.c3_synthetic((1080, 1920), light_type=getattr(b2r.Lightning, light))
+    got = gpu_render(scene)
+    want = {k: v[0] for k, v in oracle_render(oracle, scene).items()}
+    assert_parity(got, want)
+    assert np.array_equal(got['face_status'], want['face_status'])
+    assert (got['stencil'] != 0).sum() > 10000 and (got['winner'] >= 0).sum() > 500000
+
+
+@pytest.mark.skipif(scenes.asset_root() is None, reason="reference assets not staged")
+def test_kat2_real_assets_1080p(oracle):
+    """The headline scene itself: diablo3_pose (diffuse + tangent normal map) + floor, 1080p (SURVEY KAT-2)."""
+    scene = scenes.kat2(scenes.asset_root())
+    got = gpu_render(scene)
+    want = {k: v[0] for k, v in oracle_render(oracle, scene).items()}
+    assert_parity(got, want)
+    assert list(got['n_silhouette']) == [1381, 4]
+    assert int((got['winner'] >= 0).sum()) == 619692
+    st = got['face_status'][:5022]
+    assert [(st == v).sum() for v in (0, 1, 8, 16)] == [1409, 2424, 1128, 61]
+
+
+def test_c5_style_many_small_triangles(oracle):
+    """Config-5 regime at reduced count: 2*300*150 = 90k-triangle torus, most faces cover 0-2 pixel centres."""
+    v, uv, n, f = scenes.torus_arrays(300, 150)
+    scene = scenes.c3_synthetic((540, 960))
+    scene.models.clear()
+    scene._invalidate_device()
+    scene.add_model(b2r.Model(v, uv, n, f))
+    cams = scenes.orbit_cameras(2, radius=2.9)
+    dcams = scenes.orbit_cameras(2, radius=2.9, fovy=90, near=0.05, far=20)
+    dbg = {}
+    rgb = scene.render_batch(cams, debug_cameras=dcams, debug=dbg)
+    for k, (cam, dcam) in enumerate(zip(cams, dcams)):
+        scene.camera, scene.debug_camera = cam, dcam
+        want = {kk: vv[0] for kk, vv in oracle_render(oracle, scene, cameras=[cam]).items()}
+        got = dict(rgb=rgb[k], z=dbg['z'][k], stencil=dbg['stencil'][k], winner=dbg['winner'][k])
+        assert_parity(got, want)
+        assert np.array_equal(dbg['face_status'][k], want['face_status'])
+
+
+def test_batch_equals_single_and_is_deterministic():
+    scene = scenes.c3_synthetic((270, 480), tex=128)
+    cams = scenes.orbit_cameras(5)
+    dcams = scenes.orbit_cameras(5, fovy=90, near=0.05, far=20)
+    a = scene.render_batch(cams, debug_cameras=dcams)
+    b = scene.render_batch(cams, debug_cameras=dcams)
+    assert np.array_equal(a, b)
+    assert len({a[k].tobytes() for k in range(5)}) == 5
+    for k in (0, 3):
+        scene.camera, scene.debug_camera = cams[k], dcams[k]
+        scene.persist_silhouette = False
+        assert np.array_equal(scene.render(), a[k])
+
+
+def test_row_bands_compose_to_the_full_frame():
+    """Screen-band sharding is exact: bands rendered separately are byte-identical to one frame."""
+    scene = scenes.c3_synthetic((300, 500), tex=128)
+    cams, dcams = [scene.camera], [scene.debug_camera]
+    full = scene.render_batch(cams, debug_cameras=dcams)
+    H = 300
+    out = np.zeros_like(full)
+    for r0, r1 in ((0, 77), (77, 200), (200, H)):             # deliberately not tile aligned
+        part = scene.render_batch(cams, debug_cameras=dcams, band=(r0, r1))
+        rows = slice(H - r1, H - r0)                           # output rows are flipped buffer rows
+        assert not part[0, :H - r1].any() and not part[0, H - r0:].any()
+        out[0, rows] = part[0, rows]
+    assert np.array_equal(out, full)
+
+
+def test_persistent_silhouette_quirk():
+    """model.silhouette survives render(); the second call toggles it empty (no shadows),
+    the third restores it."""
+    scene, exp, meta = gu.load("g1_diablo_plain")
+    scene.persist_silhouette = True
+    sizes, frames, stencils = [], [], []
+    for _ in range(3):
+        dbg = {}
+        frames.append(scene.render(debug=dbg))
+        stencils.append(dbg['stencil'])
+        sizes.append(len(scene.models[0].silhouette))
+    assert sizes == [1381, 0, 1381]
+    assert np.array_equal(frames[0], exp['rgb']) and np.array_equal(frames[2], exp['rgb'])
+    assert not stencils[1].any() and stencils[0].any()
+    assert not np.array_equal(frames[0], frames[1])
+
+
+def test_device_resident_output_matches_host():
+    torch = pytest.importorskip("torch")
+    from py_numpy_renderer_b200 import _native
+    scene = scenes.c3_synthetic((270, 480), tex=128)
+    cams = scenes.orbit_cameras(3)
+    dcams = scenes.orbit_cameras(3, fovy=90, near=0.05, far=20)
+    host = scene.render_batch(cams, debug_cameras=dcams)
+    dev = torch.zeros((3, 270, 480, 3), dtype=torch.uint8, device="cuda:0")
+    torch.cuda.synchronize()
+    scene.render_batch(cams, debug_cameras=dcams, out=dev)
+    _native.sync()
+    assert np.array_equal(dev.cpu().numpy(), host)
+    pinned = torch.empty((3, 270, 480, 3), dtype=torch.uint8, pin_memory=True).numpy()
+    scene.render_batch(cams, debug_cameras=dcams, out=pinned)
+    assert np.array_equal(pinned, host)
+
+
+@pytest.mark.parametrize("resolution", [(1, 1), (7, 5), (33, 31), (64, 96), (100, 333)])
+def test_odd_resolutions(resolution, oracle):
+    """Ragged sizes: not a multiple of the tile, row length not a multiple of 4 bytes, single pixel."""
+    scene, _, _ = gu.load("g7_cube_mtl_rh_directx", resolution=resolution)
+    got = gpu_render(scene)
+    want = {k: v[0] for k, v in oracle_render(oracle, scene).items()}
+    assert_parity(got, want)
+
+
+def test_empty_and_offscreen_scenes(oracle):
+    cam, dcam = scenes.std_cameras()
+    scene = b2r.Scene(cam, scenes.std_light(), debug_camera=dcam, resolution=(48, 64), system=b2r.SYSTEM.LH,
+                      subsystem=b2r.SUBSYSTEM.OPENGL, skymap=[0.2, 0.4, 0.6])
+    scene.verbose = False
+    scene.persist_silhouette = False
+    empty = scene.render()                                     # no models at all: background only
+    assert empty.shape == (48, 64, 3) and (empty == empty[0, 0]).all()
+    far_away = scenes.floor_model() @ b2r.translation((500.0, 0, 0))       # entirely outside the frustum
+    behind = scenes.floor_model() @ b2r.translation((0, 0, 40.0))          # behind the camera (w < 0)
+    degenerate = b2r.Model(np.array([[0, 0, 0, 1], [0, 0, 0, 1], [1, 1, 0, 1]], np.float32), None, None,
+                           np.zeros((1, 3, 4), np.int32) + np.array([0, 1, 2])[None, :, None] * np.array([1, 0, 0, 0]))
+    for m in (far_away, behind, degenerate):
+        scene.add_model(m)
+    got = gpu_render(scene)
+    want = {k: v[0] for k, v in oracle_render(oracle, scene).items()}
+    assert_parity(got, want)
+    assert np.array_equal(got['face_status'], want['face_status'])

@@ -1,0 +1,143 @@
+"""Host-side mirror of the reference API: loader, transform chain, matrix builders, error behaviour and the
+documented quirks.  No GPU needed."""
+import os
+
+import numpy as np
+import pytest
+
+import py_numpy_renderer_b200 as b2r
+from py_numpy_renderer_b200 import _abi, transformation as T
+from py_numpy_renderer_b200.materials import Material, Texture
+
+OBJ = """mtllib t.mtl
+v 0 0 0
+v 1 0 0
+v 1 1 0
+v 0 1 0.5
+vt 0 0
+vt 1 0 0.25
+vt 1 1
+vn 0 0 1
+usemtl red
+f 1/1/1 2/2/1 3/3/1 4/1/1
+usemtl blue
+f 1/1/1 3/3/1 4//1
+"""
+MTL = """# comment
+newmtl red
+Ns 32.0
+Kd 0.5 0.25 0.125
+Ks 1 1 1
+illum 2
+newmtl blue
+Kd 0 0 1
+"""
+
+
+@pytest.fixture
+def obj_file(tmp_path):
+    (tmp_path / "t.obj").write_text(OBJ)
+    (tmp_path / "t.mtl").write_text(MTL)
+    return str(tmp_path / "t.obj")
+
+
+def test_loader_arrays(obj_file):
+    m = b2r.Model.load_model(obj_file)
+    assert m.vertices.dtype == np.float32 and m.vertices.shape == (4, 4) and (m.vertices[:, 3] == 1).all()
+    assert m.uv.dtype == np.float32 and m.uv.shape == (3, 3) and m.uv[1, 2] == 0.25 and m.uv[0, 2] == 0
+    assert m.normals.shape == (1, 3)
+    assert m._faces.dtype == np.int32 and m._faces.shape == (3, 3, 4)       # quad fan-triangulated + 1 triangle
+    assert m._faces[0, :, 0].tolist() == [0, 1, 2] and m._faces[1, :, 0].tolist() == [0, 2, 3]
+    assert m._faces[2, 2].tolist() == [3, -1, 0, 2]                          # missing vt stays -1; slot 2 = 'blue'
+    assert m.material_group == ['default', 'red', 'blue']
+    assert m.materials['red'].Ns == 32.0 and m.materials['red'].Kd.dtype == np.float32
+    assert m.materials['red'].illum == 2.0
+    packed = _abi.PackedScene([m])
+    mats = packed.models[0].materials
+    assert [mats[1].Kd[k] for k in range(3)] == [0.5, 0.25, 0.125] and mats[1].Ns == 32.0
+    assert [mats[0].Kd[k] for k in range(3)] == [0.8, 0.8, 0.8] and mats[0].Ns == 64.0   # materials.py defaults
+
+
+def test_transform_chain_dtypes_and_values(obj_file):
+    m = b2r.Model.load_model(obj_file)
+    before = m.vertices.copy()
+    assert b2r.scale(2).dtype == np.int64 and b2r.scale(0.5).dtype == np.float64
+    assert b2r.rotate_xyz((10, 20, 30)).dtype == np.float32 and b2r.rotate is b2r.rotate_xyz
+    out = m @ b2r.scale(2) @ b2r.translation((1, 2, 3))
+    assert out is m and m.vertices.dtype == np.float64                      # in place, escalates to float64
+    assert np.array_equal(m.vertices, before.astype(np.float64) * [2, 2, 2, 1] + [1, 2, 3, 0])
+    # row-vector convention: the offset sits in row 3
+    assert b2r.translation((1, 2, 3))[3].tolist() == [1, 2, 3, 1]
+    # rotate_xyz: the matrix built from angle y rotates about x (naming swap of transformation.py:230-251)
+    r = b2r.rotate_xyz((0, 90, 0))
+    assert np.allclose(np.array([0, 1, 0, 1]) @ r, [0, 0, 1, 1], atol=1e-6)
+
+
+def test_material_coercion_and_texture_registration(tmp_path):
+    mat = Material()
+    mat.Ns = ['12.5']
+    mat.name = ['shiny']
+    mat.Kd = ['0.1', '0.2', '0.3']
+    assert mat.Ns == 12.5 and mat.name == 'shiny' and mat.Kd.dtype == np.float32
+    from PIL import Image
+    img = np.random.default_rng(0).integers(0, 255, (8, 4, 3), dtype=np.uint8)
+    path = str(tmp_path / "t.png")
+    Image.fromarray(img).save(path)
+    m = b2r.Model(np.zeros((3, 4), np.float32), np.zeros((3, 3), np.float32), None, np.zeros((1, 3, 4), np.int32))
+    m.textures.register('normals', path, tangent=True)
+    m.textures.register('diffuse', path, normalize=False)
+    nm, kd = m.materials['default'].norm, m.materials['default'].map_Kd
+    assert isinstance(nm, Texture) and nm.signed and nm.tangent and not kd.signed
+    assert np.array_equal(kd.as_float32(), np.array(img / 255, dtype=np.float32))            # core.py:104
+    assert np.array_equal(nm.as_float32(), np.array(img / 255 * 2 - 1, dtype=np.float32))    # core.py:97
+    with pytest.raises(ValueError):
+        m.textures.register('glow', path)
+
+
+def test_scene_quirks():
+    cam = b2r.Camera((0, 0, 3), center=np.array((0, 0, 0)))
+    with pytest.raises(AttributeError):                                      # Appendix B-1
+        b2r.Scene(cam, b2r.Light((1, 1, 1)))
+    dcam = b2r.Camera((0, 0, 3), center=np.array((0, 0, 0)))
+    sc = b2r.Scene(cam, b2r.Light((1, 1, 1)), debug_camera=dcam, resolution=(100, 200), system=b2r.SYSTEM.RH,
+                   subsystem=b2r.SUBSYSTEM.DIRECTX)
+    mvp = cam.MVP
+    cam.position = np.array((5, 5, 5))
+    assert cam.MVP is mvp                                                    # cached_property: moving has no effect
+    ortho = b2r.Camera((0, 0, 3), center=np.array((0, 0, 0)), projection_type=b2r.PROJECTION_TYPE.ORTHOGRAPHIC)
+    assert ortho.near == 3.0                                                 # near := |position| (core.py:387)
+    sc2 = b2r.Scene(ortho, b2r.Light((1, 1, 1)), debug_camera=dcam, resolution=(10, 10), system=b2r.SYSTEM.RH,
+                    subsystem=b2r.SUBSYSTEM.OPENGL)
+    with pytest.raises(KeyError):                                            # only OPENGL/LH has an ortho builder
+        ortho.projection
+    assert sc.resolution == (100, 200) and sc2.models == []
+
+
+def test_matrix_builders_against_closed_forms():
+    vp = T.ViewPort((1080, 1920), 10, 0.1, x_offset=3, y_offset=-2)
+    assert vp[0, 0] == 960 and vp[1, 1] == 540 and vp[3].tolist() == [963, 538, (10 - 0.1) / 2, 1]
+    p = T.opengl_perspectiveLH(60, 16 / 9, 0.1, 10)
+    f = 1.0 / np.tan(np.radians(60) / 2.0)
+    assert p[0, 0] == f / (16 / 9) and p[1, 1] == f and p[2, 3] == 1.0 and p[3, 2] == 2.0 * 10 * 0.1 / (10 - 0.1)
+    assert T.opengl_orthographicLH(60, 1.5, 1, 5).dtype == np.float32
+    planes = T.extract_frustum_planes(np.eye(4))
+    assert np.allclose(np.linalg.norm(planes, axis=1), 1)
+    assert np.array_equal(T.normalize(np.zeros(3)), np.zeros((1, 3)).squeeze()[None] * 0)
+    assert T.bound_box(np.array([[-5., -5.], [-1., -2.], [-3., -4.]]), 10, 10) is None
+    assert T.bound_box(np.array([[0.2, 0.5], [3.1, 9.9], [12., 4.]]), 10, 8).tolist() == [1, 8, 1, 10]
+    assert T.barycentric(np.zeros(2), np.array([1., 1.]), np.array([2., 2.]), np.array([[0, 0]])) is None
+
+
+def test_light_defaults_and_packing():
+    light = b2r.Light((2, 3, 3), ambient_strength=0.1)
+    assert light.light_type is b2r.Lightning.POINT_LIGHTNING and light.linear == 0.14 and light.quadratic == 0.07
+    ld = _abi.pack_light(light)
+    assert ld.type == 1 and [ld.ambient[k] for k in range(3)] == [0.1, 0.1, 0.1]
+    assert np.allclose([ld.direction[k] for k in range(3)], np.array([2, 3, 3]) / np.sqrt(22))
+    assert ld.spot_cos_outer == np.cos(np.deg2rad(20)) and ld.spot_cos_inner == np.cos(np.deg2rad(10))
+
+
+def test_depth_test_false_is_fenced():
+    m = b2r.Model(np.zeros((3, 4), np.float32), None, None, np.zeros((1, 3, 4), np.int32), depth_test=False)
+    with pytest.raises(NotImplementedError):
+        _abi.PackedScene([m])
