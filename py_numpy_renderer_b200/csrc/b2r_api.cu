@@ -450,6 +450,7 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
     Fr.n_faces = sc->n_faces;
     Fr.sky_size = sc->sky_size;
     Fr.want_status = want_status;
+    Fr.full_stencil = (dbg && dbg->stencil) ? 1 : 0;
     const int n_tiles = Fr.tiles_x * Fr.tiles_y;
     const int F = sc->n_faces, E = std::max(1, sc->n_edges);
     const size_t npx = (size_t)H * W;

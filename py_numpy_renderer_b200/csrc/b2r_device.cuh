@@ -14,7 +14,7 @@ namespace b2r {
 constexpr int TILE_W = 32;  // screen tile owned by one CTA of the raster kernel
 constexpr int TILE_H = 32;
 constexpr int TILE_PX = TILE_W * TILE_H;
-constexpr int RASTER_THREADS = 256;
+constexpr int RASTER_THREADS = 128;
 
 // ---- per-face static data (scene lifetime) ------------------------------------------------------------------
 enum : int {
@@ -81,6 +81,7 @@ struct FrameDev {
     int n_faces;                      // total faces of the scene
     int sky_size;
     int want_status;
+    int full_stencil;  // stencil counts are wanted for every pixel (debug plane), not only under faces
 };
 
 // ---- per-view, per-face raster record (written by tri_setup, read by raster + shade) ---------------------------
@@ -186,21 +187,21 @@ __device__ __forceinline__ bool clip_inside(const double q[4]) {
     return (-q[3] < q[0]) && (q[0] < q[3]) && (-q[3] < q[1]) && (q[1] < q[3]) && (-q[3] < q[2]) && (q[2] < q[3]);
 }
 
-// clip-space coordinates of a face's three vertices for both cameras (triangular.py:39-40)
-struct ClipCoords {
-    double cs[3][4], csd[3][4];
-};
-__device__ __forceinline__ bool pixel_unclipped(const ClipCoords& cc, const double P[3], bool n_one) {
-    double q[4], qd[4];
+// clip-space coordinates of a face's three vertices for both cameras (triangular.py:39-40), 24 doubles:
+// cc[v*4 + k] = (vertex v @ MVP)[k],  cc[12 + v*4 + k] = (vertex v @ MVP_debug)[k]
+constexpr int CLIP_DOUBLES = 24;
+__device__ __forceinline__ bool pixel_unclipped(const double* __restrict__ cc, const double P[3], bool n_one) {
+    bool ok = true;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        // (N,3)@(3,4) is a gemm (seq); a single row goes through gemv
-        q[k] = n_one ? gemv3(P[0], P[1], P[2], cc.cs[0][k], cc.cs[1][k], cc.cs[2][k])
-                     : seq3(P[0], P[1], P[2], cc.cs[0][k], cc.cs[1][k], cc.cs[2][k]);
-        qd[k] = n_one ? gemv3(P[0], P[1], P[2], cc.csd[0][k], cc.csd[1][k], cc.csd[2][k])
-                      : seq3(P[0], P[1], P[2], cc.csd[0][k], cc.csd[1][k], cc.csd[2][k]);
+    for (int cam = 0; cam < 2; ++cam) {
+        const double* c = cc + cam * 12;
+        double q[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // (N,3)@(3,4) is a gemm (seq); a single row goes through gemv
+            q[k] = n_one ? gemv3(P[0], P[1], P[2], c[k], c[4 + k], c[8 + k]) : seq3(P[0], P[1], P[2], c[k], c[4 + k], c[8 + k]);
+        ok = ok && clip_inside(q);
     }
-    return clip_inside(q) && clip_inside(qd);
+    return ok;
 }
 
 }  // namespace b2r

@@ -112,18 +112,18 @@ __global__ void k_silhouette(SceneDev S, LightDev L, const uint8_t* __restrict__
 // =====================================================================================================================
 // per-view primitive setup
 // =====================================================================================================================
-__device__ __forceinline__ void load_clip_coords(const SceneDev& S, const ViewDev& V, const FaceStatic& fs, ClipCoords& cc) {
+__device__ __forceinline__ void load_clip_coords(const SceneDev& S, const ViewDev& V, const FaceStatic& fs, double* cc) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         const double4 p = S.pos[fs.v[i]];
         const double w[4] = {p.x, p.y, p.z, p.w};
-        vec4_mat4(w, V.mvp, cc.cs[i]);
-        vec4_mat4(w, V.mvp_dbg, cc.csd[i]);
+        vec4_mat4(w, V.mvp, cc + i * 4);
+        vec4_mat4(w, V.mvp_dbg, cc + 12 + i * 4);
     }
 }
 
 // covered & unclipped test of one pixel, the predicate `Bi` of triangular.py:78-87
-__device__ __forceinline__ bool tri_pixel_in(const TriRec& r, const ClipCoords& cc, int px, int py, float& bu, float& bv,
+__device__ __forceinline__ bool tri_pixel_in(const TriRec& r, const double* cc, int px, int py, float& bu, float& bv,
                                              float& bw) {
     bool in = tri_bary(r, px, py, bu, bv, bw);
     if (in && (r.flags & TR_NEEDS_CLIP)) {
@@ -145,7 +145,7 @@ __global__ void k_tri_setup(SceneDev S, const ViewDev* __restrict__ views, Frame
     TriRec* my = nullptr;
     bool need_coop = false;
     FaceStatic fs;
-    ClipCoords cc;
+    double cc[CLIP_DOUBLES];
     if (f < S.n_faces) {
         fs = S.faces[f];
         load_clip_coords(S, V, fs, cc);
@@ -153,8 +153,9 @@ __global__ void k_tri_setup(SceneDev S, const ViewDev* __restrict__ views, Frame
         double sx[3], sy[3], sz[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {  // triangular.py:42-45
-            const double dpt = 1.0 / cc.cs[i][3];
-            const double t[4] = {cc.cs[i][0] * dpt, cc.cs[i][1] * dpt, cc.cs[i][2] * dpt, cc.cs[i][3] * dpt};
+            const double* ci = cc + i * 4;
+            const double dpt = 1.0 / ci[3];
+            const double t[4] = {ci[0] * dpt, ci[1] * dpt, ci[2] * dpt, ci[3] * dpt};
             double s[4];
             vec4_mat4(t, V.viewport, s);
             sx[i] = s[0]; sy[i] = s[1]; sz[i] = s[2];
@@ -206,10 +207,11 @@ __global__ void k_tri_setup(SceneDev S, const ViewDev* __restrict__ views, Frame
                     const double m = 1.0 - 1e-9;
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
-                        const double w = cc.cs[i][3] * m, wd = cc.csd[i][3] * m;
-                        inside = inside && w > 0 && wd > 0 && fabs(cc.cs[i][0]) < w && fabs(cc.cs[i][1]) < w &&
-                                 fabs(cc.cs[i][2]) < w && fabs(cc.csd[i][0]) < wd && fabs(cc.csd[i][1]) < wd &&
-                                 fabs(cc.csd[i][2]) < wd;
+                        const double* c = cc + i * 4;
+                        const double* cd = cc + 12 + i * 4;
+                        const double w = c[3] * m, wd = cd[3] * m;
+                        inside = inside && w > 0 && wd > 0 && fabs(c[0]) < w && fabs(c[1]) < w && fabs(c[2]) < w &&
+                                 fabs(cd[0]) < wd && fabs(cd[1]) < wd && fabs(cd[2]) < wd;
                     }
                     if (!inside) r.flags |= TR_NEEDS_CLIP;
                 }
@@ -247,16 +249,20 @@ __global__ void k_tri_setup(SceneDev S, const ViewDev* __restrict__ views, Frame
         const int sf = __shfl_sync(0xffffffffu, f, src);
         __syncwarp();
         const TriRec r = recs[(size_t)view * S.n_faces + sf];
-        ClipCoords c2;
+        double c2[CLIP_DOUBLES];
         if (r.flags & TR_NEEDS_CLIP) load_clip_coords(S, V, S.faces[sf], c2);
         const int ny = r.by1 - r.by0, n_box = (r.bx1 - r.bx0) * ny;
+        // visit the box in a scattered order (i * prime mod n is a permutation): a triangle that covers a few
+        // percent of its box yields two hits within the first iterations, the scan stays exhaustive otherwise
+        const long long stride = (n_box % 1000003) ? 1000003 : 999983;
         int cnt = 0;
         for (int base = 0; base < n_box && cnt < 2; base += 32) {
             const int i = base + lane;
             bool in = false;
             if (i < n_box) {
+                const int j = (int)(((long long)i * stride) % n_box);
                 float bu, bv, bw;
-                in = tri_pixel_in(r, c2, r.bx0 + i / ny, r.by0 + i % ny, bu, bv, bw);
+                in = tri_pixel_in(r, c2, r.bx0 + j / ny, r.by0 + j % ny, bu, bv, bw);
             }
             cnt += __popc(__ballot_sync(0xffffffffu, in));
         }
@@ -478,12 +484,96 @@ struct RasterOut {
     uint8_t* status;    // optional (views, F)
 };
 
-__global__ void __launch_bounds__(RASTER_THREADS)
+constexpr int RASTER_WARPS = RASTER_THREADS / 32;
+constexpr int STAGE_TRIS = 48;  // triangle records staged in shared memory per round (48 x 128 B = 6 KB)
+
+struct RasterSmem {
+    unsigned long long z[TILE_PX];   // order-preserving keys of the float64 z-buffer      8 KB
+    int id[TILE_PX];                 // winner face                                        4 KB
+    int st[TILE_PX];                 // stencil count                                      4 KB
+    TriRec tri[STAGE_TRIS];          // staged per-tile triangle list                      6 KB
+    int face[STAGE_TRIS];
+    double clip[RASTER_WARPS][CLIP_DOUBLES];
+};
+
+// One pass over the tile's triangle list.  PASS 1: zbuf = min (RH) / max (LH) of z over covered, unclipped pixels
+// (triangular.py:96-118).  PASS 3: winner = greatest face index whose z equals the final zbuf.
+// Work split: the 32-pixel chunks of triangle t are dealt round-robin to the warps starting at warp t % NW, so both
+// many small triangles and one tile-filling triangle keep every warp busy.
+template <int PASS>
+__device__ __forceinline__ void raster_tris(RasterSmem& sm, const SceneDev& S, const ViewDev& V, const FrameDev& Fr,
+                                            const TriRec* __restrict__ vtris, const int* __restrict__ tri_list,
+                                            int t_beg, int t_end, int X0, int Y0, int X1, int Yb0, int Y1, bool rh,
+                                            uint8_t* status_view) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int base = t_beg; base < t_end; base += STAGE_TRIS) {
+        const int n = min(STAGE_TRIS, t_end - base);
+        __syncthreads();  // previous round fully consumed
+        for (int u = threadIdx.x; u < n * 8; u += RASTER_THREADS) {  // coalesced 16-byte pieces
+            const int t = u >> 3, part = u & 7;
+            const int face = tri_list[base + t];
+            reinterpret_cast<uint4*>(&sm.tri[t])[part] = __ldg(reinterpret_cast<const uint4*>(vtris + face) + part);
+            if (part == 0) sm.face[t] = face;
+        }
+        __syncthreads();
+        for (int t = 0; t < n; ++t) {
+            const TriRec& r = sm.tri[t];
+            const int x0 = max((int)r.bx0, X0), x1 = min((int)r.bx1, X1), y0 = max((int)r.by0, Yb0), y1 = min((int)r.by1, Y1);
+            const int w = x1 - x0, npx = w * (y1 - y0);
+            const int nchunks = (npx + 31) >> 5;
+            const int c0 = (wid - t) & (RASTER_WARPS - 1);
+            if (c0 >= nchunks) continue;
+            const int face = sm.face[t];
+            const int flags = r.flags;
+            double* cc = sm.clip[wid];
+            if (flags & TR_NEEDS_CLIP) {  // lanes 0..23 each evaluate one clip coordinate (4 FMAs)
+                __syncwarp();
+                if (lane < CLIP_DOUBLES) {
+                    const int cam = lane / 12, vtx = (lane % 12) >> 2, k = lane & 3;
+                    const double4 p = S.pos[S.faces[face].v[vtx]];
+                    const double* M = cam ? V.mvp_dbg : V.mvp;
+                    cc[lane] = fma(p.w, M[12 + k], fma(p.z, M[8 + k], fma(p.y, M[4 + k], p.x * M[k])));
+                }
+                __syncwarp();
+            }
+            const bool cov_one = (flags & TR_COV_ONE) != 0;
+            unsigned bits = 0;
+            for (int c = c0; c < nchunks; c += RASTER_WARPS) {
+                const int i = (c << 5) + lane;
+                if (i >= npx) continue;
+                const int yy = i / w, px = x0 + i - yy * w, py = y0 + yy;
+                float bu, bv, bw;
+                if (!tri_pixel_in(r, cc, px, py, bu, bv, bw)) continue;
+                const double b0 = (double)bu, b1 = (double)bv, b2 = (double)bw;
+                const double z = cov_one ? seq3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2])
+                                         : gemv3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2]);
+                bits |= 1;
+                if (!(z == z)) continue;
+                const int p = (py - Y0) * TILE_W + (px - X0);
+                const unsigned long long key = zkey(z);
+                if (PASS == 1) {
+                    if (rh) atomicMin(&sm.z[p], key); else atomicMax(&sm.z[p], key);
+                } else if (key == sm.z[p]) {
+                    atomicMax(&sm.id[p], face);
+                    bits |= 2 | (sm.st[p] == 0 ? 4 : 0);
+                }
+            }
+            if (PASS == 3 && status_view) {
+                bits = __reduce_or_sync(0xffffffffu, bits);
+                if (lane == 0 && bits) {
+                    uint8_t* sp = status_view + face;
+                    unsigned* wp = (unsigned*)((uintptr_t)sp & ~(uintptr_t)3);
+                    atomicOr(wp, bits << (8 * ((uintptr_t)sp & 3)));
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(RASTER_THREADS, 6)
 k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec* __restrict__ tris,
          const QuadRec* __restrict__ quads, int quad_stride, BinDev B, RasterOut O) {
-    __shared__ unsigned long long s_z[TILE_PX];
-    __shared__ int s_id[TILE_PX];
-    __shared__ int s_st[TILE_PX];
+    __shared__ RasterSmem sm;
     const int view = blockIdx.z;
     const ViewDev& V = views[view];
     const int tx = blockIdx.x, ty = blockIdx.y + Fr.tile_row0;
@@ -493,47 +583,42 @@ k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRe
     const int X1 = min(X0 + TILE_W, Fr.W), Y1 = min(min(Y0 + TILE_H, Fr.H), Fr.row_end);
     const int Yb0 = max(Y0, Fr.row_begin);
     const bool rh = V.system == 1;
-    const unsigned long long z_init = zkey(rh ? __longlong_as_double(0x7FF0000000000000ll)
-                                              : __longlong_as_double(0xFFF0000000000000ll));
-    for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) { s_z[i] = z_init; s_id[i] = -1; s_st[i] = 0; }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    constexpr int NW = RASTER_THREADS / 32;
     const int* tri_off = B.tri_off + (size_t)view * (n_tiles + 1);
-    const int* tri_list = B.tri_list + (size_t)view * B.tri_cap;
+    const int* quad_off = B.quad_off + (size_t)view * (n_tiles + 1);
     const int t_beg = tri_off[tile], t_end = tri_off[tile + 1];
-    const TriRec* vtris = tris + (size_t)view * Fr.n_faces;
+    const int q_beg = quad_off[tile], q_end = quad_off[tile + 1];
+    const size_t plane = (size_t)view * Fr.H * Fr.W;
+    const double z_bg = rh ? __longlong_as_double(0x7FF0000000000000ll) : __longlong_as_double(0xFFF0000000000000ll);
 
-    // ---- phase 1: depth.  zbuf = min (RH) / max (LH) of z over covered, unclipped pixels  (triangular.py:96-118) ----
-    for (int t = t_beg + wid; t < t_end; t += NW) {
-        const int face = tri_list[t];
-        const TriRec r = vtris[face];
-        ClipCoords cc;
-        if (r.flags & TR_NEEDS_CLIP) load_clip_coords(S, V, S.faces[face], cc);
-        const int x0 = max((int)r.bx0, X0), x1 = min((int)r.bx1, X1), y0 = max((int)r.by0, Yb0), y1 = min((int)r.by1, Y1);
-        const int w = x1 - x0, n = w * (y1 - y0);
-        const bool cov_one = (r.flags & TR_COV_ONE) != 0;
-        for (int i = lane; i < n; i += 32) {
-            const int yy = i / w, px = x0 + i - yy * w, py = y0 + yy;
-            float bu, bv, bw;
-            if (!tri_pixel_in(r, cc, px, py, bu, bv, bw)) continue;
-            const double b0 = (double)bu, b1 = (double)bv, b2 = (double)bw;
-            const double z = cov_one ? seq3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2])
-                                     : gemv3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2]);
-            if (!(z == z)) continue;
-            const int p = (py - Y0) * TILE_W + (px - X0);
-            if (rh) atomicMin(&s_z[p], zkey(z)); else atomicMax(&s_z[p], zkey(z));
+    if (t_beg == t_end && (q_beg == q_end || !Fr.full_stencil)) {
+        // no face can win here, so the stencil count is never read by the shader: background tile
+        for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) {
+            const int px = X0 + (i & (TILE_W - 1)), py = Y0 + i / TILE_W;
+            if (px < X1 && py >= Yb0 && py < Y1) {
+                const size_t g = plane + (size_t)py * Fr.W + px;
+                O.winner[g] = -1;
+                O.stencil[g] = 0;
+                if (O.z) O.z[g] = z_bg;
+            }
         }
+        return;
     }
+
+    const unsigned long long z_init = zkey(z_bg);
+    for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) { sm.z[i] = z_init; sm.id[i] = -1; sm.st[i] = 0; }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const TriRec* vtris = tris + (size_t)view * Fr.n_faces;
+    const int* tri_list = B.tri_list + (size_t)view * B.tri_cap;
+    uint8_t* status_view = O.status ? O.status + (size_t)view * Fr.n_faces : nullptr;
+
+    raster_tris<1>(sm, S, V, Fr, vtris, tri_list, t_beg, t_end, X0, Y0, X1, Yb0, Y1, rh, status_view);
     __syncthreads();
 
-    // ---- phase 2: stencil.  one warp per quad, one lane per tile row, exact span search  (triangular.py:341-368) ----
+    // ---- stencil: one warp per quad, one lane per tile row, exact span search  (triangular.py:341-368) ----
     {
-        const int* quad_off = B.quad_off + (size_t)view * (n_tiles + 1);
         const int* quad_list = B.quad_list + (size_t)view * B.quad_cap;
-        const int q_beg = quad_off[tile], q_end = quad_off[tile + 1];
         const QuadRec* vquads = quads + (size_t)view * quad_stride;
-        for (int t = q_beg + wid; t < q_end; t += NW) {
+        for (int t = q_beg + wid; t < q_end; t += RASTER_WARPS) {
             const QuadRec& R = vquads[quad_list[t]];
             const int py = Y0 + lane;
             int lo = max((int)R.bx0, X0), hi = min((int)R.bx1, X1) - 1;
@@ -547,26 +632,25 @@ k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRe
                 const double ex = R.x[j] - xi, ey = R.y[j] - yi;
                 if (lo > hi) continue;
                 const double c = ((double)py - yi) * ex;
-                // pred(px) := front ? f > 0 : f < 0, f = (px - xi)*ey - c, monotone in px
+                // pred(px) := front ? f > 0 : f < 0,  f = (px - xi)*ey - c is monotone in px (monotone roundings)
                 auto pred = [&](int px) {
                     const double f = ((double)px - xi) * ey - c;
                     return front ? (f > 0) : (f < 0);
                 };
-                const bool up = front ? (ey > 0) : (ey < 0);  // true set is upward closed in px
+                const bool up = front ? (ey > 0) : (ey < 0);  // the true set is upward closed in px
                 if (ey == 0 || !(ey == ey)) {
                     if (!pred(lo)) hi = lo - 1;
                 } else if (up) {
-                    // smallest px in [lo,hi] with pred true
                     if (!pred(hi)) { hi = lo - 1; }
                     else {
-                        int a = lo, b = hi;  // pred(b) true
+                        int a = lo, b = hi;  // pred(b) holds: find the smallest px with pred
                         while (a < b) { const int m = (a + b) >> 1; if (pred(m)) b = m; else a = m + 1; }
                         lo = b;
                     }
                 } else {
                     if (!pred(lo)) { hi = lo - 1; }
                     else {
-                        int a = lo, b = hi;  // pred(a) true
+                        int a = lo, b = hi;  // pred(a) holds: find the largest px with pred
                         while (a < b) { const int m = (a + b + 1) >> 1; if (pred(m)) a = m; else b = m - 1; }
                         hi = a;
                     }
@@ -578,58 +662,24 @@ k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRe
                 z = linearize_z(z, V);
                 if (!(z == z)) continue;
                 const int p = (py - Y0) * TILE_W + (px - X0);
-                const unsigned long long kz = zkey(z), kb = s_z[p];
-                if (rh ? (kb >= kz) : (kb <= kz)) atomicAdd(&s_st[p], delta);
+                const unsigned long long kz = zkey(z), kb = sm.z[p];
+                if (rh ? (kb >= kz) : (kb <= kz)) atomicAdd(&sm.st[p], delta);
             }
         }
     }
     __syncthreads();
 
-    // ---- phase 3: winner = greatest face index among faces whose z equals the final zbuf  (A.5) ----
-    for (int t = t_beg + wid; t < t_end; t += NW) {
-        const int face = tri_list[t];
-        const TriRec r = vtris[face];
-        ClipCoords cc;
-        if (r.flags & TR_NEEDS_CLIP) load_clip_coords(S, V, S.faces[face], cc);
-        const int x0 = max((int)r.bx0, X0), x1 = min((int)r.bx1, X1), y0 = max((int)r.by0, Yb0), y1 = min((int)r.by1, Y1);
-        const int w = x1 - x0, n = w * (y1 - y0);
-        const bool cov_one = (r.flags & TR_COV_ONE) != 0;
-        unsigned bits = 0;
-        for (int i = lane; i < n; i += 32) {
-            const int yy = i / w, px = x0 + i - yy * w, py = y0 + yy;
-            float bu, bv, bw;
-            if (!tri_pixel_in(r, cc, px, py, bu, bv, bw)) continue;
-            bits |= 1;
-            const double b0 = (double)bu, b1 = (double)bv, b2 = (double)bw;
-            const double z = cov_one ? seq3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2])
-                                     : gemv3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2]);
-            if (!(z == z)) continue;
-            const int p = (py - Y0) * TILE_W + (px - X0);
-            if (zkey(z) == s_z[p]) {
-                atomicMax(&s_id[p], face);
-                bits |= 2 | (s_st[p] == 0 ? 4 : 0);
-            }
-        }
-        if (O.status) {
-            bits = __reduce_or_sync(0xffffffffu, bits);
-            if (lane == 0 && bits) {
-                uint8_t* sp = O.status + (size_t)view * Fr.n_faces + face;
-                unsigned* wp = (unsigned*)((uintptr_t)sp & ~(uintptr_t)3);
-                atomicOr(wp, bits << (8 * ((uintptr_t)sp & 3)));
-            }
-        }
-    }
+    raster_tris<3>(sm, S, V, Fr, vtris, tri_list, t_beg, t_end, X0, Y0, X1, Yb0, Y1, rh, status_view);
     __syncthreads();
 
     // ---- write-back (coalesced rows) ----
-    const size_t plane = (size_t)view * Fr.H * Fr.W;
     for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) {
         const int px = X0 + (i & (TILE_W - 1)), py = Y0 + i / TILE_W;
         if (px < X1 && py >= Yb0 && py < Y1) {
             const size_t g = plane + (size_t)py * Fr.W + px;
-            O.winner[g] = s_id[i];
-            O.stencil[g] = (short)s_st[i];
-            if (O.z) O.z[g] = zkey_decode(s_z[i]);
+            O.winner[g] = sm.id[i];
+            O.stencil[g] = (short)sm.st[i];
+            if (O.z) O.z[g] = zkey_decode(sm.z[i]);
         }
     }
 }
