@@ -149,8 +149,8 @@ __device__ __forceinline__ double linearize_z(double depth, const ViewDev& V) {
 
 // order preserving double -> uint64 key (NaN must be filtered by the caller; -0 is folded onto +0)
 __device__ __forceinline__ unsigned long long zkey(double z) {
-    long long b = __double_as_longlong(z + 0.0);
-    return b < 0 ? ~(unsigned long long)b : ((unsigned long long)b | 0x8000000000000000ull);
+    const long long b = __double_as_longlong(z + 0.0);
+    return (unsigned long long)b ^ ((unsigned long long)(b >> 63) | 0x8000000000000000ull);
 }
 __device__ __forceinline__ double zkey_decode(unsigned long long k) {
     long long b = (k & 0x8000000000000000ull) ? (long long)(k & 0x7FFFFFFFFFFFFFFFull) : (long long)~k;

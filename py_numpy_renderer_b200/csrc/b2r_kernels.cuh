@@ -494,6 +494,7 @@ struct RasterSmem {
     TriRec tri[STAGE_TRIS];          // staged per-tile triangle list                      6 KB
     int face[STAGE_TRIS];
     double clip[RASTER_WARPS][CLIP_DOUBLES];
+    unsigned long long red_min[RASTER_WARPS], red_max[RASTER_WARPS];
 };
 
 // One pass over the tile's triangle list.  PASS 1: zbuf = min (RH) / max (LH) of z over covered, unclipped pixels
@@ -614,16 +615,62 @@ k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRe
     raster_tris<1>(sm, S, V, Fr, vtris, tri_list, t_beg, t_end, X0, Y0, X1, Yb0, Y1, rh, status_view);
     __syncthreads();
 
-    // ---- stencil: one warp per quad, one lane per tile row, exact span search  (triangular.py:341-368) ----
-    {
+    // ---- stencil: one warp per quad  (triangular.py:341-368) ----
+    // Outside debug mode the count is only read under a face, so background pixels are skipped, and a whole
+    // (quad, tile) pair is skipped when the quad lies behind every covered pixel of the tile: the depth of the quad
+    // plane as the reference evaluates it is a composition of monotone roundings in px and py, hence its extremes
+    // over a pixel rectangle are attained exactly at the corners (as long as the linearisation has no pole inside).
+    const bool skip_bg = !Fr.full_stencil;
+    unsigned long long kb_min = ~0ull, kb_max = 0ull;
+    if (skip_bg && q_beg < q_end) {
+        for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) {
+            const unsigned long long k = sm.z[i];
+            if (k != z_init) { kb_min = min(kb_min, k); kb_max = max(kb_max, k); }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            kb_min = min(kb_min, __shfl_xor_sync(0xffffffffu, kb_min, o));
+            kb_max = max(kb_max, __shfl_xor_sync(0xffffffffu, kb_max, o));
+        }
+        if (lane == 0) { sm.red_min[wid] = kb_min; sm.red_max[wid] = kb_max; }
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < RASTER_WARPS; ++w) { kb_min = min(kb_min, sm.red_min[w]); kb_max = max(kb_max, sm.red_max[w]); }
+    }
+    const bool any_cov = kb_min <= kb_max;
+    if (!skip_bg || any_cov) {
         const int* quad_list = B.quad_list + (size_t)view * B.quad_cap;
         const QuadRec* vquads = quads + (size_t)view * quad_stride;
         for (int t = q_beg + wid; t < q_end; t += RASTER_WARPS) {
             const QuadRec& R = vquads[quad_list[t]];
+            const int rx0 = max((int)R.bx0, X0), rx1 = min((int)R.bx1, X1) - 1;
+            const int ry0 = max((int)R.by0, Yb0), ry1 = min((int)R.by1, Y1) - 1;
+            if (rx0 > rx1 || ry0 > ry1) continue;
+            auto quad_depth = [&](int px, int py, double& den) {
+                const double z = -(R.nx * (double)px + R.ny * (double)py + R.D) / R.nz;
+                den = V.zl_sum - z * V.zl_diff;
+                return V.zl_num / den;
+            };
+            if (skip_bg) {  // depth-range rejection against the covered pixels of the tile
+                double den;
+                const double zc = quad_depth((lane & 1) ? rx1 : rx0, (lane & 2) ? ry1 : ry0, den);
+                const int sgn = den > 0 ? 1 : (den < 0 ? 2 : 0);
+                const bool regular = __all_sync(0xffffffffu, sgn != 0 && sgn == __shfl_sync(0xffffffffu, sgn, 0) && zc == zc);
+                if (regular) {
+                    unsigned long long kmin = zkey(zc), kmax = kmin;
+#pragma unroll
+                    for (int o = 1; o <= 2; o <<= 1) {
+                        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+                        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+                    }
+                    if (rh ? (kmin > kb_max) : (kmax < kb_min)) continue;  // fails the z test everywhere it matters
+                }
+            }
+            // exact span of row py = Y0 + lane: every edge function is monotone in px, so each edge cuts the
+            // candidate interval from one side; the cut is located by bisection on the exact predicate
             const int py = Y0 + lane;
-            int lo = max((int)R.bx0, X0), hi = min((int)R.bx1, X1) - 1;
-            const bool row_ok = py >= max((int)R.by0, Yb0) && py < min((int)R.by1, Y1);
-            if (!row_ok) hi = lo - 1;
+            int lo = rx0, hi = rx1;
+            if (py < ry0 || py > ry1) hi = lo - 1;
             const bool front = R.front != 0;
             const int nv = R.n;
             for (int e = 0; e < nv; ++e) {
@@ -632,8 +679,7 @@ k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRe
                 const double ex = R.x[j] - xi, ey = R.y[j] - yi;
                 if (lo > hi) continue;
                 const double c = ((double)py - yi) * ex;
-                // pred(px) := front ? f > 0 : f < 0,  f = (px - xi)*ey - c is monotone in px (monotone roundings)
-                auto pred = [&](int px) {
+                auto pred = [&](int px) {  // front ? f > 0 : f < 0 with f = (px - xi)*ey - c  (triangular.py:305-311)
                     const double f = ((double)px - xi) * ey - c;
                     return front ? (f > 0) : (f < 0);
                 };
@@ -643,27 +689,40 @@ k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRe
                 } else if (up) {
                     if (!pred(hi)) { hi = lo - 1; }
                     else {
-                        int a = lo, b = hi;  // pred(b) holds: find the smallest px with pred
+                        int a = lo, b = hi;  // pred(b) holds: smallest px with pred
                         while (a < b) { const int m = (a + b) >> 1; if (pred(m)) b = m; else a = m + 1; }
                         lo = b;
                     }
                 } else {
                     if (!pred(lo)) { hi = lo - 1; }
                     else {
-                        int a = lo, b = hi;  // pred(a) holds: find the largest px with pred
+                        int a = lo, b = hi;  // pred(a) holds: largest px with pred
                         while (a < b) { const int m = (a + b + 1) >> 1; if (pred(m)) a = m; else b = m - 1; }
                         hi = a;
                     }
                 }
             }
             const int delta = front ? 1 : -1;
-            for (int px = lo; px <= hi; ++px) {
-                double z = -(R.nx * (double)px + R.ny * (double)py + R.D) / R.nz;
-                z = linearize_z(z, V);
-                if (!(z == z)) continue;
-                const int p = (py - Y0) * TILE_W + (px - X0);
-                const unsigned long long kz = zkey(z), kb = sm.z[p];
+            auto do_pixel = [&](int px, int qy) {
+                const int p = (qy - Y0) * TILE_W + (px - X0);
+                const unsigned long long kb = sm.z[p];
+                if (skip_bg && kb == z_init) return;
+                double den;
+                const double z = quad_depth(px, qy, den);
+                if (!(z == z)) return;
+                const unsigned long long kz = zkey(z);
                 if (rh ? (kb >= kz) : (kb <= kz)) atomicAdd(&sm.st[p], delta);
+            };
+            // short spans: each lane walks its own row; long spans: the warp walks the row together
+            constexpr int SHORT = 3;
+            const int len = hi - lo + 1;
+            unsigned long_rows = __ballot_sync(0xffffffffu, len > SHORT);
+            if (len <= SHORT) for (int px = lo; px <= hi; ++px) do_pixel(px, py);
+            while (long_rows) {
+                const int r = __ffs(long_rows) - 1;
+                long_rows &= long_rows - 1;
+                const int px = __shfl_sync(0xffffffffu, lo, r) + lane;
+                if (px <= __shfl_sync(0xffffffffu, hi, r)) do_pixel(px, Y0 + r);
             }
         }
     }

@@ -19,6 +19,9 @@ def gpu_render(scene):
     scene.persist_silhouette = False
     dbg = {}
     rgb = scene.render(debug=dbg)
+    # the production path (no debug planes) takes the stencil shortcuts (background pixels skipped, depth-range
+    # rejection of whole quad/tile pairs): it must produce the very same frame
+    assert np.array_equal(scene.render(), rgb)
     return dict(rgb=rgb, z=dbg['z'], stencil=dbg['stencil'], winner=dbg['winner'], face_status=dbg['face_status'],
                 n_silhouette=dbg['n_silhouette'])
 
