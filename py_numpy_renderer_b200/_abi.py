@@ -169,31 +169,44 @@ class PackedScene:
         return C.byref(self.sky) if self.sky is not None else None
 
 
-def _mat(dst, m):
-    flat = np.asarray(m, dtype=np.float64).ravel()
-    for k in range(flat.size):
-        dst[k] = float(flat[k])
+VIEW_DTYPE = np.dtype([("mvp", "<f8", 16), ("mvp_dbg", "<f8", 16), ("viewport", "<f8", 16), ("planes", "<f8", 24),
+                       ("sky_inv", "<f8", 16), ("cam_pos", "<f8", 3), ("near_", "<f8"), ("far_", "<f8"),
+                       ("system", "<i4"), ("backface_culling", "<i4")], align=True)
+assert VIEW_DTYPE.itemsize == C.sizeof(View)
 
 
-def pack_view(camera, debug_camera, system, with_sky: bool) -> View:
+def _fill_view(rec, camera, debug_camera, system, with_sky):
     """Everything the kernels read from a camera, evaluated with the reference's own expressions
     (core.py:394-429).  `camera.scene` / `debug_camera.scene` must already be bound."""
-    v = View()
-    mvp = camera.MVP  # cached_property like the reference: first use freezes it (Appendix B-3)
-    _mat(v.mvp, mvp)
-    _mat(v.mvp_dbg, debug_camera.MVP)
-    _mat(v.viewport, camera.viewport)
-    _mat(v.planes, camera.frustum_planes)
+    rec["mvp"] = np.asarray(camera.MVP, dtype=np.float64).ravel()  # cached_property like the reference (B-3)
+    rec["mvp_dbg"] = np.asarray(debug_camera.MVP, dtype=np.float64).ravel()
+    rec["viewport"] = np.asarray(camera.viewport, dtype=np.float64).ravel()
+    rec["planes"] = camera.frustum_planes.ravel()
     if with_sky:
         # cube_map.py:94-97: lookat with its translation row zeroed, times the projection, inverted
         look = np.array(camera.lookat, dtype=np.float64, copy=True)
         look[3, :3] = 0
-        _mat(v.sky_inv, np.linalg.inv(look @ camera.projection))
-    _vec3(v.cam_pos, camera.position)
-    v.near_, v.far_ = float(camera.near), float(camera.far)
-    v.system = 1 if system == SYSTEM.RH else -1
-    v.backface_culling = int(bool(camera.backface_culling))
-    return v
+        rec["sky_inv"] = np.linalg.inv(look @ camera.projection).ravel()
+    pos = np.asarray(camera.position, dtype=np.float64).ravel()
+    rec["cam_pos"] = pos if pos.size == 3 else np.repeat(pos, 3)
+    rec["near_"], rec["far_"] = float(camera.near), float(camera.far)
+    rec["system"] = 1 if system == SYSTEM.RH else -1
+    rec["backface_culling"] = int(bool(camera.backface_culling))
+
+
+def pack_views(cameras, debug_cameras, system, with_sky):
+    """-> ctypes array of View (backed by one NumPy record array, filled field-wise)."""
+    n = len(cameras)
+    arr = np.zeros(n, dtype=VIEW_DTYPE)
+    for k in range(n):
+        _fill_view(arr[k], cameras[k], debug_cameras[k], system, with_sky)
+    views = (View * n).from_buffer(arr)
+    views._keep = arr
+    return views
+
+
+def pack_view(camera, debug_camera, system, with_sky: bool) -> View:
+    return pack_views([camera], [debug_camera], system, with_sky)[0]
 
 
 def pack_light(light) -> LightDesc:

@@ -171,7 +171,7 @@ class DeviceScene:
         """Host-side evaluation of the per-view constants (the reference's NumPy camera maths) -> (fp, views)."""
         n = len(cameras)
         fp = pack_frame_params(light, (int(resolution[0]), int(resolution[1])), background, persist_silhouette, band)
-        views = (View * n)(*[pack_view(c, d, system, self.has_sky) for c, d in zip(cameras, debug_cameras)])
+        views = _abi.pack_views(cameras, debug_cameras, system, self.has_sky)
         return fp, views
 
     def render(self, cameras, debug_cameras, light, resolution, system, background, persist_silhouette=False,

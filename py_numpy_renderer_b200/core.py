@@ -171,6 +171,24 @@ class Model:
         return set()
 
 
+_MEMO = {}
+
+
+def _memo(build, *args):
+    """Projection / viewport matrices depend on a handful of scalars shared by every camera of an orbit batch:
+    build once per distinct argument tuple, hand out copies (callers may mutate their matrix like in the reference)."""
+    try:
+        key = (build, *[float(a) if not isinstance(a, tuple) else a for a in args])
+        hit = _MEMO.get(key)
+    except TypeError:
+        return build(*args)
+    if hit is None:
+        if len(_MEMO) > 256:
+            _MEMO.clear()
+        hit = _MEMO[key] = build(*args)
+    return hit.copy()
+
+
 class PositionedObject:
     def __init__(self, position, center=np.array([0, 0, 0])):
         self.scene = None
@@ -207,7 +225,7 @@ class TransformationMatrixMixin:
     def projection(self):
         height, width = self.scene.resolution
         build = perspectives[self.scene.subsystem][self.projection_type][self.scene.system]
-        return build(self.fovy, width / height, self.near, self.far)
+        return _memo(build, self.fovy, width / height, self.near, self.far)
 
     @property
     def rotate(self):
@@ -234,7 +252,7 @@ class TransformationMatrixMixin:
 
     @property
     def viewport(self):
-        return ViewPort(self.scene.resolution, self.far, self.near, x_offset=self.x_offset, y_offset=self.y_offset)
+        return _memo(ViewPort, tuple(self.scene.resolution), self.far, self.near, self.x_offset, self.y_offset)
 
 
 class Camera(PositionedObject, TransformationMatrixMixin):

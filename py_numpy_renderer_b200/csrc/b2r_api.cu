@@ -29,8 +29,14 @@ struct Globals {
     int n_stage = 0;
     const char* stage_name[B2R_MAX_STAGES];
     cudaEvent_t stage_ev[B2R_MAX_STAGES + 1];
-    int* pinned_flags = nullptr;  // overflow read-back
+    int* pinned_flags = nullptr;  // overflow read-back, 2 ints per view
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t chunk_done = nullptr;
+    int host_chunk = 4;           // views per chunk when frames go to host memory (copy/compute overlap)
+    int pending_views = 0;        // asynchronous render whose overflow flags were not checked yet
+    struct b2r_scene* pending_scene = nullptr;
 } g;
+constexpr int MAX_FLAG_VIEWS = 4096;
 
 int fail(const std::string& msg) {
     t_error = msg;
@@ -116,6 +122,8 @@ struct b2r_scene {
     }
 };
 
+static void b2r_scene_grow_lists(struct b2r_scene* sc, int need_tri, int need_quad);
+
 extern "C" {
 
 int b2r_abi_version(void) { return B2R_ABI_VERSION; }
@@ -135,7 +143,10 @@ int b2r_init(int device) {
     g.sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     for (int i = 0; i <= B2R_MAX_STAGES; ++i) CK(cudaEventCreate(&g.stage_ev[i]));
-    CK(cudaMallocHost(&g.pinned_flags, 4096));
+    CK(cudaMallocHost(&g.pinned_flags, sizeof(int) * 2 * MAX_FLAG_VIEWS));
+    CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&g.chunk_done, cudaEventDisableTiming));
+    if (const char* hc = std::getenv("B2R_HOST_CHUNK")) g.host_chunk = std::max(1, std::atoi(hc));
     float lut[2][256];
     for (int i = 0; i < 256; ++i) {  // core.py:96-104: f32(u8/255), f32(u8/255*2-1) with float64 intermediates
         const double t = (double)i / 255;
@@ -153,6 +164,8 @@ int b2r_shutdown(void) {
     if (!g.ready) return 0;
     cudaStreamSynchronize(g.stream);
     cudaStreamDestroy(g.stream);
+    cudaStreamDestroy(g.copy_stream);
+    cudaEventDestroy(g.chunk_done);
     for (int i = 0; i <= B2R_MAX_STAGES; ++i) cudaEventDestroy(g.stage_ev[i]);
     cudaFreeHost(g.pinned_flags);
     g = Globals();
@@ -162,6 +175,17 @@ int b2r_shutdown(void) {
 int b2r_sync(void) {
     if (!g.ready) return fail("b2r_init was not called");
     CK(cudaStreamSynchronize(g.stream));
+    CK(cudaStreamSynchronize(g.copy_stream));
+    if (g.pending_views > 0) {  // an asynchronous render ran since the last check: did its tile lists fit?
+        int need_tri = 0, need_quad = 0;
+        for (int i = 0; i < g.pending_views; ++i) { need_tri = std::max(need_tri, g.pinned_flags[2 * i]); need_quad = std::max(need_quad, g.pinned_flags[2 * i + 1]); }
+        g.pending_views = 0;
+        if (need_tri || need_quad) {
+            b2r_scene_grow_lists(g.pending_scene, need_tri, need_quad);
+            return fail("tile list capacity overflow in an asynchronous render: affected frames show background only; "
+                        "capacity was raised, render again");
+        }
+    }
     return 0;
 }
 void* b2r_stream(void) { return (void*)g.stream; }
@@ -324,7 +348,8 @@ int b2r_scene_create(const b2r_model_desc* models, int32_t n_models, const b2r_t
 
 int b2r_scene_destroy(b2r_scene* sc) {
     if (!sc) return 0;
-    if (g.ready) cudaStreamSynchronize(g.stream);
+    if (g.ready) { cudaStreamSynchronize(g.stream); cudaStreamSynchronize(g.copy_stream); }
+    if (g.pending_scene == sc) { g.pending_scene = nullptr; g.pending_views = 0; }
     sc->pos.release(); sc->uv.release(); sc->nrm.release(); sc->faces.release(); sc->mats.release(); sc->tex.release();
     for (uchar4* d : sc->tex_data) cudaFree(d);
     sc->sky.release(); sc->edge_v.release(); sc->edge_ptr.release(); sc->edge_inc.release(); sc->edge_model.release();
@@ -366,6 +391,14 @@ int b2r_scene_get_silhouette(b2r_scene* sc, int32_t* out_pairs, int32_t* out_mod
     }
     return n;
 }
+
+}  // extern "C"
+static void b2r_scene_grow_lists(b2r_scene* sc, int need_tri, int need_quad) {
+    if (!sc) return;
+    if (need_tri) { sc->tri_cap = need_tri + need_tri / 4; sc->tri_list.release(); }
+    if (need_quad) { sc->quad_cap = need_quad + need_quad / 4; sc->quad_list.release(); }
+}
+extern "C" {
 
 // ---- host-side evaluation of the view constants (same operation order as the reference) ----------------------------
 static void host_vec4_mat4(const double v[4], const double* M, double out[4]) {
@@ -456,10 +489,14 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
     const size_t npx = (size_t)H * W;
     const SceneDev S = sc->dev();
 
-    // views per chunk bounded by a scratch budget
+    // Chunking.  Device-resident output: as many views per launch as the scratch budget allows.  Host output: small
+    // chunks, so that the D2H copy of chunk i (copy stream) overlaps the kernels of chunk i+1 (compute stream).
     const size_t per_view = (size_t)F * sizeof(TriRec) + (size_t)E * sizeof(QuadRec) + npx * 6 + (want_z ? npx * 8 : 0);
     int VB = (int)std::max<size_t>(1, std::min<size_t>(n_views, ((size_t)6 << 30) / std::max<size_t>(per_view, 1)));
     VB = std::min(VB, 64);
+    const bool pipelined = !out_on_device && !dbg && n_views > 1;
+    if (pipelined) VB = std::min(VB, std::max(1, g.host_chunk));
+    if (n_views > MAX_FLAG_VIEWS) return fail("too many views in one call (max 4096)");
     if (sc->tri_cap == 0) sc->tri_cap = std::max(1 << 16, 4 * F + 8 * n_tiles);
     if (sc->quad_cap == 0) sc->quad_cap = std::max(1 << 20, 32 * E);
     sc->tri_cap = std::max(sc->tri_cap, 8 * n_tiles);
@@ -484,25 +521,27 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
     }
     stage_mark("silhouette");
 
-    for (int first = 0; first < n_views; first += VB) {
-        const int nv = std::min(VB, n_views - first);
-        for (int attempt = 0; attempt < 4; ++attempt) {
-            CK(sc->views.reserve(VB));
-            CK(sc->tris.reserve((size_t)VB * F));
-            CK(sc->quads.reserve((size_t)VB * E));
-            CK(sc->tile_counts.reserve((size_t)VB * n_tiles * 2));
-            CK(sc->tile_offs.reserve((size_t)VB * (n_tiles + 1) * 2));
-            CK(sc->tri_list.reserve((size_t)VB * sc->tri_cap));
-            CK(sc->quad_list.reserve((size_t)VB * sc->quad_cap));
-            CK(sc->overflow.reserve((size_t)VB * 2));
-            CK(sc->winner.reserve((size_t)VB * npx));
-            CK(sc->stencil.reserve((size_t)VB * npx));
-            if (want_z) CK(sc->zplane.reserve((size_t)VB * npx));
-            if (want_status) CK(sc->status.reserve((size_t)VB * F + 8));
-            if (!out_on_device) CK(sc->rgb.reserve((size_t)VB * npx * 3));
+    const cudaMemcpyKind kind = out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        CK(sc->views.reserve(VB));
+        CK(sc->tris.reserve((size_t)VB * F));
+        CK(sc->quads.reserve((size_t)VB * E));
+        CK(sc->tile_counts.reserve((size_t)VB * n_tiles * 2));
+        CK(sc->tile_offs.reserve((size_t)VB * (n_tiles + 1) * 2));
+        CK(sc->tri_list.reserve((size_t)VB * sc->tri_cap));
+        CK(sc->quad_list.reserve((size_t)VB * sc->quad_cap));
+        CK(sc->overflow.reserve((size_t)VB * 2));
+        CK(sc->winner.reserve((size_t)VB * npx));
+        CK(sc->stencil.reserve((size_t)VB * npx));
+        if (want_z) CK(sc->zplane.reserve((size_t)VB * npx));
+        if (want_status) CK(sc->status.reserve((size_t)VB * F + 8));
+        if (!out_on_device) CK(sc->rgb.reserve((size_t)n_views * npx * 3));  // one region per view: copies never race
 
+        for (int first = 0; first < n_views; first += VB) {
+            const int nv = std::min(VB, n_views - first);
             std::vector<ViewDev> hv(nv);
             for (int i = 0; i < nv; ++i) make_view(views[first + i], with_sky, hv[i]);
+            // pageable source: the runtime stages it before returning, so `hv` may die at the end of the iteration
             CK(cudaMemcpyAsync(sc->views.p, hv.data(), sizeof(ViewDev) * nv, cudaMemcpyHostToDevice, g.stream));
             CK(cudaMemsetAsync(sc->tile_counts.p, 0, sizeof(int) * (size_t)VB * n_tiles * 2, g.stream));
 
@@ -539,50 +578,52 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
                 ++g.launches;
             }
             stage_mark("raster");
-            uint8_t* rgb_dev = out_on_device ? out_rgb + (size_t)first * npx * 3 : sc->rgb.p;
+            uint8_t* rgb_dev = (out_on_device ? out_rgb : sc->rgb.p) + (size_t)first * npx * 3;
             const int rows = row_end - row_begin;
             k_shade<<<dim3((W + 31) / 32, (rows + 7) / 8, nv), 256, 0, g.stream>>>(S, sc->views.p, Fr, sc->tris.p,
                                                                                sc->winner.p, sc->stencil.p, rgb_dev);
             ++g.launches;
             stage_mark("shade");
             CK(cudaGetLastError());
-            CK(cudaMemcpyAsync(g.pinned_flags, sc->overflow.p, sizeof(int) * 2 * nv, cudaMemcpyDeviceToHost, g.stream));
+            CK(cudaMemcpyAsync(g.pinned_flags + 2 * first, sc->overflow.p, sizeof(int) * 2 * nv, cudaMemcpyDeviceToHost, g.stream));
 
-            if (out_on_device && !dbg) break;  // asynchronous mode: overflow is reported by the next synchronous call
-            CK(cudaStreamSynchronize(g.stream));
-            int need_tri = 0, need_quad = 0;
-            for (int i = 0; i < nv; ++i) { need_tri = std::max(need_tri, g.pinned_flags[2 * i]); need_quad = std::max(need_quad, g.pinned_flags[2 * i + 1]); }
-            if (need_tri || need_quad) {
-                if (attempt == 3) return fail("tile list capacity overflow");
-                if (need_tri) { sc->tri_cap = need_tri + need_tri / 4; sc->tri_list.release(); }
-                if (need_quad) { sc->quad_cap = need_quad + need_quad / 4; sc->quad_list.release(); }
-                continue;
+            if (!out_on_device) {  // frames of this chunk travel on the copy stream while the next chunk renders
+                CK(cudaEventRecord(g.chunk_done, g.stream));
+                CK(cudaStreamWaitEvent(g.copy_stream, g.chunk_done, 0));
+                const size_t band_off = (size_t)(H - row_end) * W * 3, band_bytes = (size_t)(row_end - row_begin) * W * 3;
+                if (band_bytes == npx * 3) {
+                    CK(cudaMemcpyAsync(out_rgb + (size_t)first * npx * 3, rgb_dev, (size_t)nv * npx * 3, kind, g.copy_stream));
+                } else {
+                    for (int i = 0; i < nv; ++i)
+                        CK(cudaMemcpyAsync(out_rgb + (size_t)(first + i) * npx * 3 + band_off, rgb_dev + (size_t)i * npx * 3 + band_off,
+                                           band_bytes, kind, g.copy_stream));
+                }
             }
-            break;
-        }
-        // outputs of this chunk
-        const cudaMemcpyKind kind = out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-        if (!out_on_device) {
-            // only the rendered band is defined; copy whole frames for simplicity when the band is the frame
-            for (int i = 0; i < nv; ++i) {
-                const size_t off = ((size_t)(first + i) * H + (size_t)(H - row_end)) * W * 3;
-                const size_t src = ((size_t)i * H + (size_t)(H - row_end)) * W * 3;
-                CK(cudaMemcpyAsync(out_rgb + off, sc->rgb.p + src, (size_t)(row_end - row_begin) * W * 3, kind, g.stream));
+            if (dbg) {  // debug planes: same stream, so the next chunk cannot overwrite the scratch planes early
+                if (dbg->z) CK(cudaMemcpyAsync(dbg->z + (size_t)first * npx, sc->zplane.p, sizeof(double) * nv * npx, kind, g.stream));
+                if (dbg->stencil) CK(cudaMemcpyAsync(dbg->stencil + (size_t)first * npx, sc->stencil.p, sizeof(short) * nv * npx, kind, g.stream));
+                if (dbg->winner) CK(cudaMemcpyAsync(dbg->winner + (size_t)first * npx, sc->winner.p, sizeof(int) * nv * npx, kind, g.stream));
+                if (dbg->face_status) CK(cudaMemcpyAsync(dbg->face_status + (size_t)first * F, sc->status.p, (size_t)nv * F, kind, g.stream));
+                if (dbg->n_silhouette)
+                    for (int i = 0; i < nv; ++i)
+                        CK(cudaMemcpyAsync(dbg->n_silhouette + (size_t)(first + i) * sc->n_models, sc->counters.p + 1,
+                                           sizeof(int) * sc->n_models, kind, g.stream));
             }
         }
-        if (dbg) {
-            if (dbg->z) CK(cudaMemcpyAsync(dbg->z + (size_t)first * npx, sc->zplane.p, sizeof(double) * nv * npx, kind, g.stream));
-            if (dbg->stencil) CK(cudaMemcpyAsync(dbg->stencil + (size_t)first * npx, sc->stencil.p, sizeof(short) * nv * npx, kind, g.stream));
-            if (dbg->winner) CK(cudaMemcpyAsync(dbg->winner + (size_t)first * npx, sc->winner.p, sizeof(int) * nv * npx, kind, g.stream));
-            if (dbg->face_status) CK(cudaMemcpyAsync(dbg->face_status + (size_t)first * F, sc->status.p, (size_t)nv * F, kind, g.stream));
-            if (dbg->n_silhouette)
-                for (int i = 0; i < nv; ++i)
-                    CK(cudaMemcpyAsync(dbg->n_silhouette + (size_t)(first + i) * sc->n_models, sc->counters.p + 1,
-                                       sizeof(int) * sc->n_models, kind, g.stream));
+        if (out_on_device && !dbg) {  // asynchronous mode: capacity overflow is reported by the next b2r_sync
+            g.pending_views = n_views;
+            g.pending_scene = sc;
+            return 0;
         }
-        if (!out_on_device || dbg) CK(cudaStreamSynchronize(g.stream));
+        CK(cudaStreamSynchronize(g.stream));
+        CK(cudaStreamSynchronize(g.copy_stream));
+        int need_tri = 0, need_quad = 0;
+        for (int i = 0; i < n_views; ++i) { need_tri = std::max(need_tri, g.pinned_flags[2 * i]); need_quad = std::max(need_quad, g.pinned_flags[2 * i + 1]); }
+        if (!need_tri && !need_quad) return 0;
+        if (need_tri) { sc->tri_cap = need_tri + need_tri / 4; sc->tri_list.release(); }
+        if (need_quad) { sc->quad_cap = need_quad + need_quad / 4; sc->quad_list.release(); }
     }
-    return 0;
+    return fail("tile list capacity overflow");
 }
 
 }  // extern "C"

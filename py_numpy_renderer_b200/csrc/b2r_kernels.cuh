@@ -586,8 +586,10 @@ k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRe
     const bool rh = V.system == 1;
     const int* tri_off = B.tri_off + (size_t)view * (n_tiles + 1);
     const int* quad_off = B.quad_off + (size_t)view * (n_tiles + 1);
-    const int t_beg = tri_off[tile], t_end = tri_off[tile + 1];
-    const int q_beg = quad_off[tile], q_end = quad_off[tile + 1];
+    // lists that did not fit (capacity overflow, reported to the host) are treated as empty: never read past them
+    const bool lists_ok = (B.overflow[view * 2] | B.overflow[view * 2 + 1]) == 0;
+    const int t_beg = lists_ok ? tri_off[tile] : 0, t_end = lists_ok ? tri_off[tile + 1] : 0;
+    const int q_beg = lists_ok ? quad_off[tile] : 0, q_end = lists_ok ? quad_off[tile + 1] : 0;
     const size_t plane = (size_t)view * Fr.H * Fr.W;
     const double z_bg = rh ? __longlong_as_double(0x7FF0000000000000ll) : __longlong_as_double(0xFFF0000000000000ll);
 

@@ -141,3 +141,30 @@ def test_depth_test_false_is_fenced():
     m = b2r.Model(np.zeros((3, 4), np.float32), None, None, np.zeros((1, 3, 4), np.int32), depth_test=False)
     with pytest.raises(NotImplementedError):
         _abi.PackedScene([m])
+
+
+def test_fast_look_at_equals_numpy_formulation():
+    """transformation._look_at_basis evaluates the reference's look-at on Python floats; it must be bit-identical
+    to the NumPy expressions of obj/transformation.py:83-98 (restated here) for arbitrary cameras."""
+    rng = np.random.default_rng(5)
+
+    def numpy_rotate(eye, center, up, sign):
+        forward = T.normalize(center - eye).ravel()
+        right = T.normalize(np.cross(up, forward)).ravel()
+        new_up = np.cross(forward, right)
+        rot = np.eye(4)
+        rot[:3, :3] = np.column_stack((right, new_up, sign * forward))
+        return rot
+
+    for k in range(300):
+        eye = rng.standard_normal(3) * rng.choice([0.1, 1, 10, 1000])
+        center = rng.standard_normal(3) if k % 3 else np.array([0, 0, 0])
+        up = np.array([0, 1, 0]) if k % 2 else rng.standard_normal(3)
+        assert np.array_equal(T.look_at_rotate_lh(eye, center, up), numpy_rotate(eye, center, up, -1))
+        assert np.array_equal(T.look_at_rotate_rh(eye, center, up), numpy_rotate(eye, center, up, 1))
+    m = rng.standard_normal((4, 4))
+    planes = np.zeros((6, 4))
+    for i, p in enumerate((m[:, 3] + m[:, 0], m[:, 3] - m[:, 0], m[:, 3] + m[:, 1], m[:, 3] - m[:, 1],
+                           m[:, 3] + m[:, 2], m[:, 3] - m[:, 2])):
+        planes[i] = p / np.linalg.norm(p)
+    assert np.array_equal(T.extract_frustum_planes(m), planes)
