@@ -21,7 +21,7 @@ def nvcc_cmd(extra=()):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
             "-Xcompiler", "-fPIC,-ffp-contract=off,-mfma", "-shared", "-I", os.path.join(ROOT, "include"),
-            *extra, "-o", LIB, SRC]
+            *(["-DB2R_STATS"] if os.environ.get("B2R_STATS") else []), *extra, "-o", LIB, SRC]
 
 
 def build(force=False, verbose=False):

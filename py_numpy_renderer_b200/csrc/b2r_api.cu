@@ -190,6 +190,14 @@ int b2r_sync(void) {
 }
 void* b2r_stream(void) { return (void*)g.stream; }
 int64_t b2r_launch_count(void) { return (int64_t)g.launches; }
+// Work counters of a -DB2R_STATS build (all zero otherwise): copies 16 values, optionally resets them.
+int b2r_debug_stats(unsigned long long* out16, int reset) {
+    if (!g.ready) return fail("b2r_init was not called");
+    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaMemcpyFromSymbol(out16, g_stats, sizeof(unsigned long long) * 16));
+    if (reset) { unsigned long long z[16] = {0}; CK(cudaMemcpyToSymbol(g_stats, z, sizeof(z))); }
+    return 0;
+}
 int b2r_set_stage_timing(int enabled) { g.timing = enabled != 0; return 0; }
 int b2r_last_stage_ms(const char** names, float* ms) {
     for (int i = 0; i < g.n_stage; ++i) {

@@ -19,7 +19,15 @@
 
 namespace b2r {
 
-__constant__ float c_lut[2][256];  // [B2R_TEX_UNORM|B2R_TEX_SNORM][u8] -> the reference's float32 texel
+__constant__ float c_lut[2][256];
+
+// optional work counters (build with -DB2R_STATS; read with b2r_debug_stats) -- never in the production library
+__device__ unsigned long long g_stats[16];
+#ifdef B2R_STATS
+#define B2R_STAT(i, n) atomicAdd(&g_stats[i], (unsigned long long)(n))
+#else
+#define B2R_STAT(i, n) ((void)0)
+#endif  // [B2R_TEX_UNORM|B2R_TEX_SNORM][u8] -> the reference's float32 texel
 
 struct SceneDev {
     const double4* pos;      // (Vtot) world positions, exact promotion of the model's storage
@@ -544,7 +552,9 @@ __device__ __forceinline__ void raster_tris(RasterSmem& sm, const SceneDev& S, c
                 if (i >= npx) continue;
                 const int yy = i / w, px = x0 + i - yy * w, py = y0 + yy;
                 float bu, bv, bw;
+                if (PASS == 1) B2R_STAT(12, 1);
                 if (!tri_pixel_in(r, cc, px, py, bu, bv, bw)) continue;
+                if (PASS == 1) B2R_STAT(13, 1);
                 const double b0 = (double)bu, b1 = (double)bv, b2 = (double)bw;
                 const double z = cov_one ? seq3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2])
                                          : gemv3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2]);
@@ -607,6 +617,7 @@ k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRe
         return;
     }
 
+    if (threadIdx.x == 0) { B2R_STAT(11, 1); B2R_STAT(14, q_end - q_beg); B2R_STAT(15, t_end - t_beg); }
     const unsigned long long z_init = zkey(z_bg);
     for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) { sm.z[i] = z_init; sm.id[i] = -1; sm.st[i] = 0; }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -625,6 +636,7 @@ k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRe
     const bool skip_bg = !Fr.full_stencil;
     unsigned long long kb_min = ~0ull, kb_max = 0ull;
     if (skip_bg && q_beg < q_end) {
+        // depth range of the covered pixels of the tile (keys; empty = min > max)
         for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) {
             const unsigned long long k = sm.z[i];
             if (k != z_init) { kb_min = min(kb_min, k); kb_max = max(kb_max, k); }
@@ -648,12 +660,14 @@ k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRe
             const int rx0 = max((int)R.bx0, X0), rx1 = min((int)R.bx1, X1) - 1;
             const int ry0 = max((int)R.by0, Yb0), ry1 = min((int)R.by1, Y1) - 1;
             if (rx0 > rx1 || ry0 > ry1) continue;
+            if (lane == 0) B2R_STAT(0, 1);
             auto quad_depth = [&](int px, int py, double& den) {
                 const double z = -(R.nx * (double)px + R.ny * (double)py + R.D) / R.nz;
                 den = V.zl_sum - z * V.zl_diff;
                 return V.zl_num / den;
             };
-            if (skip_bg) {  // depth-range rejection against the covered pixels of the tile
+            bool all_pass = false;  // the quad is in front of every covered pixel of the tile: no depth needed per pixel
+            if (skip_bg) {  // depth-range classification against the covered pixels of the tile
                 double den;
                 const double zc = quad_depth((lane & 1) ? rx1 : rx0, (lane & 2) ? ry1 : ry0, den);
                 const int sgn = den > 0 ? 1 : (den < 0 ? 2 : 0);
@@ -665,7 +679,9 @@ k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRe
                         kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
                         kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
                     }
-                    if (rh ? (kmin > kb_max) : (kmax < kb_min)) continue;  // fails the z test everywhere it matters
+                    if (rh ? (kmin > kb_max) : (kmax < kb_min)) { if (lane == 0) B2R_STAT(1, 1); continue; }  // fails everywhere it matters
+                    all_pass = rh ? (kmax <= kb_min) : (kmin >= kb_max);
+                    if (all_pass && lane == 0) B2R_STAT(6, 1);
                 }
             }
             // exact span of row py = Y0 + lane: every edge function is monotone in px, so each edge cuts the
@@ -708,23 +724,29 @@ k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRe
             auto do_pixel = [&](int px, int qy) {
                 const int p = (qy - Y0) * TILE_W + (px - X0);
                 const unsigned long long kb = sm.z[p];
-                if (skip_bg && kb == z_init) return;
+                if (skip_bg && kb == z_init) { B2R_STAT(9, 1); return; }
+                if (all_pass) { atomicAdd(&sm.st[p], delta); return; }
                 double den;
                 const double z = quad_depth(px, qy, den);
+                B2R_STAT(8, 1);
                 if (!(z == z)) return;
                 const unsigned long long kz = zkey(z);
-                if (rh ? (kb >= kz) : (kb <= kz)) atomicAdd(&sm.st[p], delta);
+                if (rh ? (kb >= kz) : (kb <= kz)) { atomicAdd(&sm.st[p], delta); B2R_STAT(10, 1); }
             };
             // short spans: each lane walks its own row; long spans: the warp walks the row together
             constexpr int SHORT = 3;
             const int len = hi - lo + 1;
             unsigned long_rows = __ballot_sync(0xffffffffu, len > SHORT);
+            if (len > 0 && len <= SHORT) B2R_STAT(2, 1);
+            if (len > SHORT) B2R_STAT(3, 1);
             if (len <= SHORT) for (int px = lo; px <= hi; ++px) do_pixel(px, py);
             while (long_rows) {
                 const int r = __ffs(long_rows) - 1;
                 long_rows &= long_rows - 1;
-                const int px = __shfl_sync(0xffffffffu, lo, r) + lane;
-                if (px <= __shfl_sync(0xffffffffu, hi, r)) do_pixel(px, Y0 + r);
+                const int lo_r = __shfl_sync(0xffffffffu, lo, r), hi_r = __shfl_sync(0xffffffffu, hi, r);
+                const int px = lo_r + lane, qy = Y0 + r;
+                if (lane == 0) B2R_STAT(7, 1);
+                if (px <= hi_r) do_pixel(px, qy);
             }
         }
     }
@@ -767,46 +789,13 @@ __device__ __forceinline__ void texel_fetch(const TextureDev& T, const double P[
     out[0] = lut[t.x]; out[1] = lut[t.y]; out[2] = lut[t.z];
 }
 
-// inverse of a 3x3 by LU with partial pivoting + solves against the identity (what np.linalg.inv -> dgesv does)
-__device__ __forceinline__ void inv3(const double A[9], double out[9]) {
-    double a[9];
-    int perm[3] = {0, 1, 2};
-#pragma unroll
-    for (int i = 0; i < 9; ++i) a[i] = A[i];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        int p = k;
-        double best = fabs(a[k * 3 + k]);
-#pragma unroll
-        for (int r = k + 1; r < 3; ++r) if (fabs(a[r * 3 + k]) > best) { best = fabs(a[r * 3 + k]); p = r; }
-        if (p != k) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) { const double t = a[k * 3 + c]; a[k * 3 + c] = a[p * 3 + c]; a[p * 3 + c] = t; }
-            const int t = perm[k]; perm[k] = perm[p]; perm[p] = t;
-        }
-        const double piv = 1.0 / a[k * 3 + k];
-#pragma unroll
-        for (int r = k + 1; r < 3; ++r) {
-            a[r * 3 + k] *= piv;
-#pragma unroll
-            for (int c = k + 1; c < 3; ++c) a[r * 3 + c] -= a[r * 3 + k] * a[k * 3 + c];
-        }
-    }
-#pragma unroll
-    for (int col = 0; col < 3; ++col) {
-        double y[3];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) y[r] = perm[r] == col ? 1.0 : 0.0;
-        y[1] -= a[3] * y[0];
-        y[2] -= a[6] * y[0];
-        y[2] -= a[7] * y[1];
-        y[2] /= a[8];
-        y[1] -= a[5] * y[2];
-        y[1] /= a[4];
-        y[0] -= a[1] * y[1];
-        y[0] -= a[2] * y[2];
-        y[0] /= a[0];
-        out[0 + col] = y[0]; out[3 + col] = y[1]; out[6 + col] = y[2];
+// normalize() for shading vectors: x * rsqrt(|x|^2).  Within an ulp or two of the reference's x / sqrt(.) -- far
+// below what survives the uint8 quantisation (the exact form is kept wherever a comparison depends on it).
+__device__ __forceinline__ void shade_norm3(double v[3]) {
+    const double s = (v[0] * v[0] + v[1] * v[1]) + v[2] * v[2];
+    if (s > 0) {
+        const double r = rsqrt(s);
+        v[0] *= r; v[1] *= r; v[2] *= r;
     }
 }
 
@@ -875,20 +864,19 @@ __device__ void shade_face_pixel(const SceneDev& S, const ViewDev& V, const Ligh
             double n[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) n[k] = seq3(P[0], P[1], P[2], vn[0][k], vn[1][k], vn[2][k]);
-            normalize3(n);
-            double A[9], AI[9];
+            shade_norm3(n);
+            // rows of A (core.py:210-213): r0 = b - a, r1 = c - a (vertex dtype arithmetic), r2 = n
+            double r0[3], r1[3];
             if (fs.flags & FS_VTX_F32) {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    A[k] = (double)__fsub_rn((float)wp[1][k], (float)wp[0][k]);
-                    A[3 + k] = (double)__fsub_rn((float)wp[2][k], (float)wp[0][k]);
+                    r0[k] = (double)__fsub_rn((float)wp[1][k], (float)wp[0][k]);
+                    r1[k] = (double)__fsub_rn((float)wp[2][k], (float)wp[0][k]);
                 }
             } else {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) { A[k] = wp[1][k] - wp[0][k]; A[3 + k] = wp[2][k] - wp[0][k]; }
+                for (int k = 0; k < 3; ++k) { r0[k] = wp[1][k] - wp[0][k]; r1[k] = wp[2][k] - wp[0][k]; }
             }
-            A[6] = n[0]; A[7] = n[1]; A[8] = n[2];
-            inv3(A, AI);
             double du1, du2, dv1, dv2;
             if (fs.flags & FS_UV_F32) {
                 du1 = (double)__fsub_rn((float)uu[1], (float)uu[0]); du2 = (double)__fsub_rn((float)uu[2], (float)uu[0]);
@@ -896,13 +884,19 @@ __device__ void shade_face_pixel(const SceneDev& S, const ViewDev& V, const Ligh
             } else {
                 du1 = uu[1] - uu[0]; du2 = uu[2] - uu[0]; dv1 = vv[1] - vv[0]; dv2 = vv[2] - vv[0];
             }
+            // inv(A) @ (d1, d2, 0) = (d1 * (r1 x n) + d2 * (n x r0)) / det(A); the result is normalised right away
+            // (core.py:221-222), so only the SIGN of the determinant survives: no matrix inverse is formed.
+            const double c1[3] = {r1[1] * n[2] - r1[2] * n[1], r1[2] * n[0] - r1[0] * n[2], r1[0] * n[1] - r1[1] * n[0]};
+            const double c2[3] = {n[1] * r0[2] - n[2] * r0[1], n[2] * r0[0] - n[0] * r0[2], n[0] * r0[1] - n[1] * r0[0]};
+            const double det = (r0[0] * c1[0] + r0[1] * c1[1]) + r0[2] * c1[2];
+            const double sg = det < 0 ? -1.0 : 1.0;
             double ti[3], tj[3];
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
-                ti[q] = gemv3(AI[q * 3], AI[q * 3 + 1], AI[q * 3 + 2], du1, du2, 0.0);
-                tj[q] = gemv3(AI[q * 3], AI[q * 3 + 1], AI[q * 3 + 2], dv1, dv2, 0.0);
+                ti[q] = sg * (du1 * c1[q] + du2 * c2[q]);
+                tj[q] = sg * (dv1 * c1[q] + dv2 * c2[q]);
             }
-            normalize3(ti); normalize3(tj);
+            shade_norm3(ti); shade_norm3(tj);
 #pragma unroll
             for (int q = 0; q < 3; ++q) N[q] = seq3(ti[q], tj[q], n[q], (double)t[0], (double)t[1], (double)t[2]);
         } else {
@@ -934,12 +928,12 @@ __device__ void shade_face_pixel(const SceneDev& S, const ViewDev& V, const Ligh
 #pragma unroll
         for (int k = 0; k < 3; ++k) N[k] = seq3(P[0], P[1], P[2], fn[k], fn[k], fn[k]);
     }
-    normalize3(N);
+    shade_norm3(N);
     double Ld[3];
     if (L.type == B2R_LIGHT_DIRECTIONAL) { Ld[0] = L.direction[0]; Ld[1] = L.direction[1]; Ld[2] = L.direction[2]; }
-    else { Ld[0] = dl[0]; Ld[1] = dl[1]; Ld[2] = dl[2]; normalize3(Ld); }
+    else { Ld[0] = dl[0]; Ld[1] = dl[1]; Ld[2] = dl[2]; shade_norm3(Ld); }
     double Vd[3] = {V.cam_pos[0] - frag[0], V.cam_pos[1] - frag[1], V.cam_pos[2] - frag[2]};
-    normalize3(Vd);
+    shade_norm3(Vd);
     if (L.type == B2R_LIGHT_SPOT) {  // triangular.py:157-161, core.py:497-515
         double x = dot3_plain(L.direction, Ld);
         x = (x - L.spot_cos_outer) / (L.spot_cos_inner - L.spot_cos_outer);
@@ -957,7 +951,7 @@ __device__ void shade_face_pixel(const SceneDev& S, const ViewDev& V, const Ligh
         spec_light[0] = M.Ks255[0]; spec_light[1] = M.Ks255[1]; spec_light[2] = M.Ks255[2];
     }
     double Hd[3] = {Ld[0] + Vd[0], Ld[1] + Vd[1], Ld[2] + Vd[2]};
-    normalize3(Hd);
+    shade_norm3(Hd);
     double nh = dot3_plain(N, Hd);
     nh = nh < 0 ? 0 : nh;
     const double sr = pow_ns(nh, M);
