@@ -367,21 +367,27 @@ __device__ __forceinline__ double edge_fn(double px, double py, double x0, doubl
     return (px - x0) * ey - (py - y0) * ex;
 }
 
-// Can the pixel rectangle [x0,x1] x [y0,y1] (inclusive) contain a pixel inside the polygon?  edge_fn is a
-// composition of monotone roundings, so its extreme over the rectangle is attained, EXACTLY, at a corner.
-__device__ __forceinline__ bool quad_may_touch(const QuadRec& R, int x0, int x1, int y0, int y1) {
+// How does the pixel rectangle [x0,x1] x [y0,y1] (inclusive) meet the polygon?  edge_fn is a composition of monotone
+// roundings, so its extremes over the rectangle are attained, EXACTLY, at corners:
+//   0 = no pixel of the rectangle can be inside,  1 = some may be,  2 = every pixel of the rectangle is inside.
+constexpr int QUAD_FULL_BIT = 1 << 30;  // flag in a tile-list entry: the quad covers every pixel of the tile
+__device__ __forceinline__ int quad_tile_class(const QuadRec& R, int x0, int x1, int y0, int y1) {
+    bool full = true;
     for (int i = 0; i < R.n; ++i) {
         const int j = (i + 1 == R.n) ? 0 : i + 1;
         const double ex = R.x[j] - R.x[i], ey = R.y[j] - R.y[i];
-        if (R.front) {  // need f > 0 somewhere: take the corner maximising f
-            const double f = edge_fn(ey >= 0 ? x1 : x0, ex <= 0 ? y1 : y0, R.x[i], R.y[i], ex, ey);
-            if (!(f > 0)) return false;
-        } else {        // need f < 0 somewhere: corner minimising f
-            const double f = edge_fn(ey >= 0 ? x0 : x1, ex <= 0 ? y0 : y1, R.x[i], R.y[i], ex, ey);
-            if (!(f < 0)) return false;
+        // corner maximising f = (px-xi)*ey - (py-yi)*ex, and the opposite corner minimising it
+        const double fmax = edge_fn(ey >= 0 ? x1 : x0, ex <= 0 ? y1 : y0, R.x[i], R.y[i], ex, ey);
+        const double fmin = edge_fn(ey >= 0 ? x0 : x1, ex <= 0 ? y0 : y1, R.x[i], R.y[i], ex, ey);
+        if (R.front) {  // inside means f > 0
+            if (!(fmax > 0)) return 0;
+            full = full && (fmin > 0);
+        } else {        // inside means f < 0
+            if (!(fmin < 0)) return 0;
+            full = full && (fmax < 0);
         }
     }
-    return true;
+    return full ? 2 : 1;
 }
 
 struct BinDev {
@@ -430,13 +436,19 @@ __global__ void k_bin(FrameDev Fr, const TriRec* __restrict__ tris, const QuadRe
         int* list = Q ? B.quad_list + (size_t)view * B.quad_cap : B.tri_list + (size_t)view * B.tri_cap;
         for (int i = lane; i < nt; i += 32) {
             const int ty = ty0 + i / tw, tx = tx0 + i % tw;
+            int entry = prim;
             if (Q) {
                 const int x0 = max(bx0, tx * TILE_W), x1 = min(bx1, (tx + 1) * TILE_W) - 1;
                 const int y0 = max(by0, ty * TILE_H), y1 = min(by1, (ty + 1) * TILE_H) - 1;
-                if (!quad_may_touch(*Q, x0, x1, y0, y1)) continue;
+                const int cls = quad_tile_class(*Q, x0, x1, y0, y1);
+                if (cls == 0) continue;
+                // "full" only counts when the rectangle is the whole tile (clipped to the screen and the band)
+                if (FILL && cls == 2 && x0 == tx * TILE_W && x1 == min(Fr.W, (tx + 1) * TILE_W) - 1 &&
+                    y0 == max(band_y0, ty * TILE_H) && y1 == min(min(Fr.H, band_y1), (ty + 1) * TILE_H) - 1)
+                    entry |= QUAD_FULL_BIT;
             }
             const int t = (ty - Fr.tile_row0) * Fr.tiles_x + tx;
-            if (FILL) list[off[t] + atomicAdd(count + t, 1)] = prim;
+            if (FILL) list[off[t] + atomicAdd(count + t, 1)] = entry;
             else atomicAdd(count + t, 1);
         }
     }
@@ -503,6 +515,7 @@ struct RasterSmem {
     int face[STAGE_TRIS];
     double clip[RASTER_WARPS][CLIP_DOUBLES];
     unsigned long long red_min[RASTER_WARPS], red_max[RASTER_WARPS];
+    int uniform;
 };
 
 // One pass over the tile's triangle list.  PASS 1: zbuf = min (RH) / max (LH) of z over covered, unclipped pixels
@@ -529,6 +542,7 @@ __device__ __forceinline__ void raster_tris(RasterSmem& sm, const SceneDev& S, c
             const TriRec& r = sm.tri[t];
             const int x0 = max((int)r.bx0, X0), x1 = min((int)r.bx1, X1), y0 = max((int)r.by0, Yb0), y1 = min((int)r.by1, Y1);
             const int w = x1 - x0, npx = w * (y1 - y0);
+            const float rcp_w = 1.0f / (float)w;  // i / w for i < 1024, w <= 32: (i + 0.5) / w is >= 1/64 from an integer
             const int nchunks = (npx + 31) >> 5;
             const int c0 = (wid - t) & (RASTER_WARPS - 1);
             if (c0 >= nchunks) continue;
@@ -550,7 +564,7 @@ __device__ __forceinline__ void raster_tris(RasterSmem& sm, const SceneDev& S, c
             for (int c = c0; c < nchunks; c += RASTER_WARPS) {
                 const int i = (c << 5) + lane;
                 if (i >= npx) continue;
-                const int yy = i / w, px = x0 + i - yy * w, py = y0 + yy;
+                const int yy = __float2int_rd(((float)i + 0.5f) * rcp_w), px = x0 + i - yy * w, py = y0 + yy;
                 float bu, bv, bw;
                 if (PASS == 1) B2R_STAT(12, 1);
                 if (!tri_pixel_in(r, cc, px, py, bu, bv, bw)) continue;
@@ -620,6 +634,7 @@ k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRe
     if (threadIdx.x == 0) { B2R_STAT(11, 1); B2R_STAT(14, q_end - q_beg); B2R_STAT(15, t_end - t_beg); }
     const unsigned long long z_init = zkey(z_bg);
     for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) { sm.z[i] = z_init; sm.id[i] = -1; sm.st[i] = 0; }
+    if (threadIdx.x == 0) sm.uniform = 0;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const TriRec* vtris = tris + (size_t)view * Fr.n_faces;
     const int* tri_list = B.tri_list + (size_t)view * B.tri_cap;
@@ -652,11 +667,14 @@ k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRe
         for (int w = 0; w < RASTER_WARPS; ++w) { kb_min = min(kb_min, sm.red_min[w]); kb_max = max(kb_max, sm.red_max[w]); }
     }
     const bool any_cov = kb_min <= kb_max;
+    int uniform = 0;  // stencil increments that apply to every covered pixel of the tile
     if (!skip_bg || any_cov) {
         const int* quad_list = B.quad_list + (size_t)view * B.quad_cap;
         const QuadRec* vquads = quads + (size_t)view * quad_stride;
         for (int t = q_beg + wid; t < q_end; t += RASTER_WARPS) {
-            const QuadRec& R = vquads[quad_list[t]];
+            const int entry = quad_list[t];
+            const bool full = (entry & QUAD_FULL_BIT) != 0;  // every pixel of the tile is inside the quad
+            const QuadRec& R = vquads[entry & (QUAD_FULL_BIT - 1)];
             const int rx0 = max((int)R.bx0, X0), rx1 = min((int)R.bx1, X1) - 1;
             const int ry0 = max((int)R.by0, Yb0), ry1 = min((int)R.by1, Y1) - 1;
             if (rx0 > rx1 || ry0 > ry1) continue;
@@ -682,6 +700,11 @@ k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRe
                     if (rh ? (kmin > kb_max) : (kmax < kb_min)) { if (lane == 0) B2R_STAT(1, 1); continue; }  // fails everywhere it matters
                     all_pass = rh ? (kmax <= kb_min) : (kmin >= kb_max);
                     if (all_pass && lane == 0) B2R_STAT(6, 1);
+                    if (all_pass && full) {  // one count for every covered pixel of the tile: no per-pixel work at all
+                        uniform += R.front ? 1 : -1;
+                        if (lane == 0) B2R_STAT(4, 1);
+                        continue;
+                    }
                 }
             }
             // exact span of row py = Y0 + lane: every edge function is monotone in px, so each edge cuts the
@@ -690,7 +713,8 @@ k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRe
             int lo = rx0, hi = rx1;
             if (py < ry0 || py > ry1) hi = lo - 1;
             const bool front = R.front != 0;
-            const int nv = R.n;
+            const int nv = full ? 0 : R.n;  // a fully covered tile needs no span search
+            if (full && lane == 0) B2R_STAT(5, 1);
             for (int e = 0; e < nv; ++e) {
                 const int j = (e + 1 == nv) ? 0 : e + 1;
                 const double xi = R.x[e], yi = R.y[e];
@@ -733,24 +757,37 @@ k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRe
                 const unsigned long long kz = zkey(z);
                 if (rh ? (kb >= kz) : (kb <= kz)) { atomicAdd(&sm.st[p], delta); B2R_STAT(10, 1); }
             };
-            // short spans: each lane walks its own row; long spans: the warp walks the row together
-            constexpr int SHORT = 3;
-            const int len = hi - lo + 1;
-            unsigned long_rows = __ballot_sync(0xffffffffu, len > SHORT);
-            if (len > 0 && len <= SHORT) B2R_STAT(2, 1);
-            if (len > SHORT) B2R_STAT(3, 1);
-            if (len <= SHORT) for (int px = lo; px <= hi; ++px) do_pixel(px, py);
-            while (long_rows) {
-                const int r = __ffs(long_rows) - 1;
-                long_rows &= long_rows - 1;
-                const int lo_r = __shfl_sync(0xffffffffu, lo, r), hi_r = __shfl_sync(0xffffffffu, hi, r);
-                const int px = lo_r + lane, qy = Y0 + r;
-                if (lane == 0) B2R_STAT(7, 1);
-                if (px <= hi_r) do_pixel(px, qy);
+            // The spans of the 32 rows are flattened into one dense pixel list and dealt 32 at a time, so every lane
+            // works whatever the shape of the quad: pixel k lies in the row r with start[r] <= k < start[r+1]
+            // (inclusive scan over the lanes, then a 5-step bisection through shuffles).
+            const int len = max(hi - lo + 1, 0);
+            int incl = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (lane == 0) { B2R_STAT(2, 1); B2R_STAT(3, total); }
+            for (int k = lane; k < ((total + 31) & ~31); k += 32) {
+                int r = 0;  // smallest lane with incl[r] > k
+#pragma unroll
+                for (int step = 16; step; step >>= 1) {
+                    const int probe = __shfl_sync(0xffffffffu, incl, r + step - 1);
+                    if (probe <= k) r += step;
+                }
+                const int row_incl = __shfl_sync(0xffffffffu, incl, r), row_len = __shfl_sync(0xffffffffu, len, r);
+                const int row_lo = __shfl_sync(0xffffffffu, lo, r);
+                if (k < total) do_pixel(row_lo + (k - (row_incl - row_len)), Y0 + r);
             }
         }
     }
+    if (skip_bg) {  // fold the tile-uniform increments into the per-pixel counts
+        if (lane == 0 && uniform) atomicAdd(&sm.uniform, uniform);
+    }
     __syncthreads();
+    if (skip_bg && sm.uniform) {
+        const int u = sm.uniform;
+        for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) if (sm.z[i] != z_init) sm.st[i] += u;
+        __syncthreads();
+    }
 
     raster_tris<3>(sm, S, V, Fr, vtris, tri_list, t_beg, t_end, X0, Y0, X1, Yb0, Y1, rh, status_view);
     __syncthreads();
