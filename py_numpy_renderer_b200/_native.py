@@ -17,7 +17,7 @@ from ._abi import (B2R_BG_COLOR, B2R_BG_CUBEMAP, DebugOut, FrameParams, PackedSc
                    pack_frame_params, pack_view)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb2r.so")
+LIB_PATH = os.environ.get("B2R_LIB") or os.path.join(HERE, "libb2r.so")  # B2R_LIB: load a tuning variant
 
 
 class Errors(Flag):

@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-LIB = os.path.join(HERE, "libb2r.so")
+LIB = os.environ.get("B2R_LIB_OUT") or os.path.join(HERE, "libb2r.so")  # B2R_LIB_OUT: tuning variants
 SRC = os.path.join(HERE, "csrc", "b2r_api.cu")
 DEPS = [SRC, os.path.join(HERE, "csrc", "b2r_kernels.cuh"), os.path.join(HERE, "csrc", "b2r_device.cuh"),
         os.path.join(ROOT, "include", "b2r.h")]
@@ -21,7 +21,8 @@ def nvcc_cmd(extra=()):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
             "-Xcompiler", "-fPIC,-ffp-contract=off,-mfma", "-shared", "-I", os.path.join(ROOT, "include"),
-            *(["-DB2R_STATS"] if os.environ.get("B2R_STATS") else []), *extra, "-o", LIB, SRC]
+            *(["-DB2R_STATS"] if os.environ.get("B2R_STATS") else []), *os.environ.get("B2R_NVCC_FLAGS", "").split(),
+            *extra, "-o", LIB, SRC]
 
 
 def build(force=False, verbose=False):

@@ -588,7 +588,7 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
             stage_mark("raster");
             uint8_t* rgb_dev = (out_on_device ? out_rgb : sc->rgb.p) + (size_t)first * npx * 3;
             const int rows = row_end - row_begin;
-            k_shade<<<dim3((W + 31) / 32, (rows + 7) / 8, nv), 256, 0, g.stream>>>(S, sc->views.p, Fr, sc->tris.p,
+            k_shade<<<dim3((W + 31) / 32, (rows + B2R_SHADE_THREADS / 32 - 1) / (B2R_SHADE_THREADS / 32), nv), B2R_SHADE_THREADS, 0, g.stream>>>(S, sc->views.p, Fr, sc->tris.p,
                                                                                sc->winner.p, sc->stencil.p, rgb_dev);
             ++g.launches;
             stage_mark("shade");

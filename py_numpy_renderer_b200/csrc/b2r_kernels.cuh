@@ -595,7 +595,10 @@ __device__ __forceinline__ void raster_tris(RasterSmem& sm, const SceneDev& S, c
     }
 }
 
-__global__ void __launch_bounds__(RASTER_THREADS, 6)
+#ifndef B2R_RASTER_MINB
+#define B2R_RASTER_MINB 8
+#endif
+__global__ void __launch_bounds__(RASTER_THREADS, B2R_RASTER_MINB)
 k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec* __restrict__ tris,
          const QuadRec* __restrict__ quads, int quad_stride, BinDev B, RasterOut O) {
     __shared__ RasterSmem sm;
@@ -1038,7 +1041,13 @@ __device__ __forceinline__ bool skybox_pixel(const SceneDev& S, const ViewDev& V
 
 // One thread per pixel; a warp covers 32 consecutive pixels of one buffer row and packs its 96 output bytes into
 // 24 aligned 32-bit stores.  Output row = H-1-py (core.py:640).
-__global__ void __launch_bounds__(256)
+#ifndef B2R_SHADE_THREADS
+#define B2R_SHADE_THREADS 128
+#endif
+#ifndef B2R_SHADE_MINB
+#define B2R_SHADE_MINB 8
+#endif
+__global__ void __launch_bounds__(B2R_SHADE_THREADS, B2R_SHADE_MINB)
 k_shade(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec* __restrict__ tris,
         const int* __restrict__ winner, const short* __restrict__ stencil, uint8_t* __restrict__ out_rgb) {
     const int view = blockIdx.z;
