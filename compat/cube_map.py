@@ -1,0 +1,5 @@
+import os as _os
+import sys as _sys
+
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
+from py_numpy_renderer_b200.cube_map import CubeMap  # noqa: F401,E402

@@ -1,0 +1,7 @@
+"""`from transformation import scale, translation, rotate` (reference README step 2)."""
+import os as _os
+import sys as _sys
+
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
+from py_numpy_renderer_b200.transformation import *  # noqa: F401,F403,E402
+from py_numpy_renderer_b200.constants import SYSTEM, SUBSYSTEM, PROJECTION_TYPE  # noqa: F401,E402
