@@ -89,6 +89,19 @@ def sync():
     _check(init().b2r_sync())
 
 
+_worker = None
+
+
+def submit(fn, *args, **kw):
+    """Run `fn` on the library's single worker thread -> concurrent.futures.Future.  ctypes drops the GIL inside
+    libb2r, so the caller can evaluate the cameras of the next batch while this one renders and copies."""
+    global _worker
+    if _worker is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _worker = ThreadPoolExecutor(max_workers=1, thread_name_prefix="b2r")
+    return _worker.submit(fn, *args, **kw)
+
+
 def launch_count() -> int:
     return int(init().b2r_launch_count())
 

@@ -393,3 +393,18 @@ class Scene:
         if debug is not None:
             debug.update(info)
         return frames
+
+    def render_batch_async(self, cameras, debug_cameras=None, out=None, band=None):
+        """`render_batch` as a two-stage pipeline: the camera maths of this batch runs here, in the calling
+        thread; rendering + the copy into `out` run on the library's worker thread.  Returns a Future whose
+        `result()` is the frame stack.  Keep one or two batches in flight (each with its own `out` buffer) and the
+        host-side evaluation of batch k+1 overlaps the GPU work of batch k."""
+        from . import _native
+        dev = self._device_scene()
+        cameras = list(cameras)
+        dcams = [self.debug_camera] * len(cameras) if debug_cameras is None else list(debug_cameras)
+        for cam in cameras + dcams:
+            cam.scene = self
+        fp, views = dev.pack(cameras, dcams, self.light, self.resolution, self.system, self._background(),
+                             persist_silhouette=False, band=band)
+        return _native.submit(lambda: dev.render_packed(fp, views, out=out)[0])

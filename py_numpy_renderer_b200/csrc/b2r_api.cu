@@ -32,7 +32,7 @@ struct Globals {
     int* pinned_flags = nullptr;  // overflow read-back, 2 ints per view
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_done = nullptr;
-    int host_chunk = 4;           // views per chunk when frames go to host memory (copy/compute overlap)
+    int host_chunk = 8;           // views per chunk when frames go to host memory (copy/compute overlap)
     int pending_views = 0;        // asynchronous render whose overflow flags were not checked yet
     struct b2r_scene* pending_scene = nullptr;
 } g;
@@ -174,6 +174,7 @@ int b2r_shutdown(void) {
 
 int b2r_sync(void) {
     if (!g.ready) return fail("b2r_init was not called");
+    CK(cudaSetDevice(g.device));
     CK(cudaStreamSynchronize(g.stream));
     CK(cudaStreamSynchronize(g.copy_stream));
     if (g.pending_views > 0) {  // an asynchronous render ran since the last check: did its tile lists fit?
@@ -216,6 +217,7 @@ int b2r_scene_create(const b2r_model_desc* models, int32_t n_models, const b2r_t
                      int32_t n_textures, const b2r_cubemap_desc* skybox, b2r_scene** out_scene) {
     if (!g.ready) return fail("b2r_init was not called");
     if (!out_scene) return fail("out_scene is NULL");
+    CK(cudaSetDevice(g.device));
     b2r_scene* sc = new b2r_scene();
     sc->n_models = n_models;
     size_t nv = 0, nt = 0, nn = 0, nf = 0, nm = 0;
@@ -356,6 +358,7 @@ int b2r_scene_create(const b2r_model_desc* models, int32_t n_models, const b2r_t
 
 int b2r_scene_destroy(b2r_scene* sc) {
     if (!sc) return 0;
+    if (g.ready) cudaSetDevice(g.device);
     if (g.ready) { cudaStreamSynchronize(g.stream); cudaStreamSynchronize(g.copy_stream); }
     if (g.pending_scene == sc) { g.pending_scene = nullptr; g.pending_views = 0; }
     sc->pos.release(); sc->uv.release(); sc->nrm.release(); sc->faces.release(); sc->mats.release(); sc->tex.release();
@@ -463,6 +466,7 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
                const b2r_debug_out* dbg, int32_t out_on_device) {
     if (!g.ready) return fail("b2r_init was not called");
     if (!sc || !fp || !views || n_views <= 0 || !out_rgb) return fail("b2r_render: bad arguments");
+    CK(cudaSetDevice(g.device));  // the current device is per host thread; callers may render from a worker thread
     const int H = fp->height, W = fp->width;
     if (H <= 0 || W <= 0 || H > 32000 || W > 32000) return fail("resolution out of range");
     const int row_begin = std::max(0, fp->row_begin), row_end = std::min(H, fp->row_end <= 0 ? H : fp->row_end);
