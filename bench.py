@@ -12,9 +12,9 @@ A STEP = one camera-orbit batch of `--views` frames of the scene (BASELINE confi
 Multi-GPU: weak scaling, every rank renders its own `--views` frames per step (frames are independent, no
 data-path collective) and ONE NCCL gather per step assembles the uint8 frames on rank 0.
 
-value : device-resident throughput (scene + pre-evaluated view constants in HBM, frames left in HBM), timed per
-        step with CUDA events on the library stream, L2 flushed between steps, MAX over ranks.
-e2e   : through the public API `Scene.render_batch(cameras, out=pinned)`, host camera maths + H2D of the view
+value : device-resident throughput (scene + pre-evaluated view constants in HBM, frames left in HBM): one CUDA-event
+        pair around the K steps, L2 flushed before every step (inside the region), MAX over ranks.
+e2e   : through the public API `Scene.render_batch_async(cameras, out=pinned)`: host camera maths + H2D of the view
         constants + render + D2H of the frames inside the timed region (wall clock, MAX over ranks).
 """
 from __future__ import annotations
@@ -41,8 +41,8 @@ HBM_FALLBACK_GBS = 6650.0
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--views", type=int, default=16, help="frames per step per GPU")
     ap.add_argument("--height", type=int, default=1080)
@@ -94,7 +94,7 @@ def algorithmic_bytes(scene, n_shaded):
 
 
 class ClockSampler(threading.Thread):
-    """SM clock + throttle reasons during the timed region (NVML, 100 ms period)."""
+    """SM clock + throttle reasons during the timed region (NVML, 50 ms period)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -125,7 +125,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
@@ -220,36 +220,53 @@ def main():
         for c in cams + dcams:
             c.scene = scene
         packed_steps.append(dev.pack(cams, dcams, scene.light, scene.resolution, scene.system, bg))
-    frames_dev = torch.empty((B, H, W, 3), dtype=torch.uint8, device=device)
-    counts = [B] * world
+    frames_dev = [torch.empty((B, H, W, 3), dtype=torch.uint8, device=device) for _ in range(2)]
+    gathered = [[torch.empty((B, H, W, 3), dtype=torch.uint8, device=device) for _ in range(world)]
+                for _ in range(2)] if (world > 1 and rank == 0) else [None, None]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
-    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(Wm + K)]
-    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(Wm + K)]
-    stage_ms = {}
-    _native.set_stage_timing(True)
+    cur = torch.cuda.current_stream()
 
-    def one_step(s, timed):
-        fp, views = packed_steps[s]
-        flush.zero_()                                   # evict L2 (256 MiB > 126 MB) -- outside the timed span
-        torch.cuda.synchronize()
-        ev0[s].record(lib_stream)
-        dev.render_packed(fp, views, out=frames_dev)    # asynchronous, frames stay in HBM
-        if world > 1:
-            done = torch.cuda.Event()
-            done.record(lib_stream)
-            torch.cuda.current_stream().wait_event(done)
-            parallel.gather_frames(frames_dev, counts, dst=0)   # the single NCCL gather that assembles the batch
-            ev1[s].record(torch.cuda.current_stream())
-        else:
-            ev1[s].record(lib_stream)
+    def run_steps(first, count, per_step_sync):
+        """`count` steps as a stream pipeline: [L2 flush] -> render (library stream) -> NCCL gather of the step's
+        frames to rank 0 (NCCL stream), the gather of step s overlapping the render of step s+1 (two frame
+        buffers).  Returns elapsed device milliseconds between the first flush and the last gather."""
+        ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        works = [None, None]
+        ev_a.record(cur)
+        for s in range(first, first + count):
+            fp, views = packed_steps[s]
+            slot = s % 2
+            flush.zero_()                                   # evict L2: 256 MiB > 126 MB (its ~45 us ARE timed)
+            if works[slot] is not None:
+                works[slot].wait()                          # frames_dev[slot] was handed to NCCL two steps ago
+                works[slot] = None
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            lib_stream.wait_event(ready)
+            dev.render_packed(fp, views, out=frames_dev[slot])          # asynchronous, frames stay in HBM
+            if world > 1:
+                done = torch.cuda.Event()
+                done.record(lib_stream)
+                cur.wait_event(done)
+                works[slot] = dist.gather(frames_dev[slot], gathered[slot], dst=0, async_op=True)
+            if per_step_sync:
+                torch.cuda.synchronize()
+                _native.sync()
+                for k, v in _native.last_stage_ms().items():
+                    stage_ms[k] = stage_ms.get(k, 0.0) + v
+        for w in works:
+            if w is not None:
+                w.wait()
+        fin = torch.cuda.Event()
+        fin.record(lib_stream)
+        cur.wait_event(fin)
+        ev_b.record(cur)
         torch.cuda.synchronize()
         _native.sync()
-        if timed:
-            for k, v in _native.last_stage_ms().items():
-                stage_ms[k] = stage_ms.get(k, 0.0) + v
+        return ev_a.elapsed_time(ev_b)
 
-    for s in range(Wm):
-        one_step(s, False)
+    stage_ms = {}
+    run_steps(0, Wm, False)                                 # warm-up
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -257,24 +274,25 @@ def main():
     sampler.start()
     launches0 = _native.launch_count()
     wall0 = time.perf_counter()
-    for s in range(Wm, Wm + K):
-        one_step(s, True)
-    torch.cuda.synchronize()
+    dev_ms = run_steps(Wm, K, False)                        # the timed region: exactly K steps
     if world > 1:
         dist.barrier()
     wall = time.perf_counter() - wall0
     launches = _native.launch_count() - launches0
-    _native.set_stage_timing(False)
-    dev_ms = sum(ev0[s].elapsed_time(ev1[s]) for s in range(Wm, Wm + K))
     t = torch.tensor([dev_ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
     value = K * B * world / (dev_ms / 1e3)
+    # per-stage CUDA-event timing (library stream) on a few more steps of the same workload, synchronised per step
+    n_stage_steps = min(K, 5)
+    _native.set_stage_timing(True)
+    run_steps(Wm + K - n_stage_steps, n_stage_steps, True)
+    _native.set_stage_timing(False)
 
     # ---- end to end through the public API: host camera maths + H2D + render + D2H into pinned memory ----
     pinned = [torch.empty((B, H, W, 3), dtype=torch.uint8, pin_memory=True).numpy() for _ in range(2)]
-    e2e_steps = max(3, min(K, 10))
+    e2e_steps = max(3, min(K, 30))
     for s in range(2):
         cams, dcams = step_cameras(1000 + s, rank, world, B)
         scene.render_batch(cams, debug_cameras=dcams, out=pinned[s])
@@ -311,7 +329,7 @@ def main():
     else:
         peak, peak_src = HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
     top = max(stage_ms, key=stage_ms.get) if stage_ms else None
-    stage_avg = {k: v / K for k, v in stage_ms.items()}
+    stage_avg = {k: v / n_stage_steps for k, v in stage_ms.items()}
     roofline = None
     if top:
         achieved = balg["total"] * B / (stage_avg[top] / 1e3) / 1e9
@@ -329,10 +347,11 @@ def main():
             "dtype": "f64", "data": "synthetic" if args.workload == "synthetic" else "reference assets",
             "mpix_per_s": value * H * W / 1e6,
             "config": {"workload": workload, "resolution": [H, W], "frames_per_step_per_gpu": B,
-                       "parallelism": f"frames x{world} (weak), one NCCL gather per step" if world > 1 else "single GPU",
-                       "l2": "flushed between steps (256 MiB memset outside the timed span)",
-                       "timing": "CUDA events on the launching stream per step, summed, MAX over ranks",
-                       "wall_ms_per_step_incl_flush": 1e3 * wall / K},
+                       "parallelism": f"frames x{world} (weak), one NCCL gather per step overlapped with the next render" if world > 1 else "single GPU",
+                       "l2": "flushed before every step (256 MiB memset, inside the timed region)",
+                       "timing": "one CUDA-event pair around the K steps (first flush .. last gather), MAX over ranks; "
+                                 "stage times from a separate per-step-synchronised pass",
+                       "wall_ms_per_step": 1e3 * wall / K},
             "e2e": {"value": e2e_fps, "unit": UNIT,
                     "h2d_bytes_per_step": B * ctypes.sizeof(_abi.View) + ctypes.sizeof(_abi.FrameParams),
                     "d2h_bytes_per_step": B * H * W * 3, "steps": e2e_steps,
