@@ -849,6 +849,17 @@ __device__ __forceinline__ double pow_ns(double x, const MaterialDev& M) {
     return pow(x, M.Ns);
 }
 
+// x ** 0.8 in float32 for the tonemap (core.py:640).  NumPy's float32 power is itself only accurate to about an
+// ulp (SVML), so bit parity is not defined here; this version is within ~2 ulp of the true value at a fifth of the
+// cost of powf: a hardware log2/exp2 estimate polished by one Newton step on y^5 = x^4.
+__device__ __forceinline__ float pow08(float x) {
+    if (!(x > 0.0f)) return 0.0f;
+    const float y = exp2f(0.8f * __log2f(x));
+    const float x2 = x * x, t = x2 * x2;
+    const float y2 = y * y, y5 = y2 * y2 * y;
+    return y * fmaf(0.2f, __fdividef(t, y5), 0.8f);
+}
+
 __device__ __forceinline__ float clip01(double v) { return (float)(v < 0.05 ? 0.05 : (v > 1.0 ? 1.0 : v)); }
 
 // general_shading for one pixel (triangular.py:135-171)
@@ -859,7 +870,12 @@ __device__ void shade_face_pixel(const SceneDev& S, const ViewDev& V, const Ligh
     float bu, bv, bw;
     tri_bary(r, px, py, bu, bv, bw);
     double P[3];
-    persp_bary(r, bu, bv, bw, false, P);
+    {   // Face.screen_perspective (core.py:155-160); one reciprocal instead of three divisions: the result only
+        // feeds shading (<= 1 ulp apart), the clip test in the raster keeps the exact form
+        const double b0 = (double)bu, b1 = (double)bv, b2 = (double)bw;
+        const double inv_w = 1.0 / gemv3(b0, b1, b2, r.d[0], r.d[1], r.d[2]);
+        P[0] = b0 * r.d[0] * inv_w; P[1] = b1 * r.d[1] * inv_w; P[2] = b2 * r.d[2] * inv_w;
+    }
     double uu[3] = {0, 0, 0}, vv[3] = {0, 0, 0};
     if (fs.flags & FS_HAS_UV) {
 #pragma unroll
@@ -1072,7 +1088,7 @@ k_shade(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec
     unsigned packed = 0;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const float v = __fmul_rn(powf(c[k], 0.8f), 255.0f);
+        const float v = __fmul_rn(pow08(c[k]), 255.0f);
         packed |= ((unsigned)(int)v & 0xffu) << (8 * k);
     }
     uint8_t* row = out_rgb + ((size_t)view * Fr.H + (size_t)(Fr.H - 1 - py)) * Fr.W * 3;

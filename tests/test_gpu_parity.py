@@ -187,3 +187,19 @@ def test_empty_and_offscreen_scenes(oracle):
     want = {k: v[0] for k, v in oracle_render(oracle, scene).items()}
     assert_parity(got, want)
     assert np.array_equal(got['face_status'], want['face_status'])
+
+
+def test_c5_one_million_triangles_one_frame(oracle):
+    """BASELINE config 5 at its full mesh size: nu=1000 x nv=500 displaced torus = 1 000 000 triangles, 1080p."""
+    v, uv, n, f = scenes.torus_arrays(1000, 500)
+    cams = scenes.orbit_cameras(1, radius=2.9, start=0.3)
+    dcams = scenes.orbit_cameras(1, radius=2.9, start=0.3, fovy=90, near=0.05, far=20)
+    scene = b2r.Scene(cams[0], scenes.std_light(), debug_camera=dcams[0], resolution=(1080, 1920),
+                      system=b2r.SYSTEM.LH, subsystem=b2r.SUBSYSTEM.OPENGL)
+    scene.verbose = False
+    scene.add_model(b2r.Model(v, uv, n, f))
+    got = gpu_render(scene)
+    want = {k: vv[0] for k, vv in oracle.render_scene(scene, threads=1).items()}
+    assert_parity(got, want)
+    assert np.array_equal(got['face_status'], want['face_status'])
+    assert list(got['n_silhouette']) == list(want['n_silhouette']) and got['n_silhouette'][0] > 10000
