@@ -91,7 +91,7 @@ enum : int {
     TR_BOX_ONE = 4,     // bbox holds exactly one pixel  -> N==1 evaluation order in barycentric()
     TR_COV_ONE = 8,     // exactly one covered & unclipped pixel -> N==1 order for the z interpolation
 };
-struct __align__(16) TriRec {  // 128 B
+struct TriRec {  // 128 B (8-byte aligned on purpose: staged copies in shared memory sit on a 136-byte pitch)
     double ax, ay, v0x, v0y, v1x, v1y;  // screen a, b-a, c-a                          48
     double zl[3];                       // linearised z at the vertices                 24
     double d[3];                        // 1/w at the vertices                          24

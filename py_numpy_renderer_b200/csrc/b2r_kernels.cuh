@@ -505,91 +505,128 @@ struct RasterOut {
 };
 
 constexpr int RASTER_WARPS = RASTER_THREADS / 32;
-constexpr int STAGE_TRIS = 48;  // triangle records staged in shared memory per round (48 x 128 B = 6 KB)
+constexpr int STAGE_TRIS = 32;   // triangle records staged in shared memory per round
+constexpr int STAGE_CLIP = 16;   // of which at most this many need the per-pixel clip test (clip coordinates staged too)
+constexpr int REC_DOUBLES = 17;  // 128-byte record + 8 bytes of padding: consecutive records start on different banks
+static_assert(sizeof(TriRec) == 128, "TriRec layout");
 
 struct RasterSmem {
-    unsigned long long z[TILE_PX];   // order-preserving keys of the float64 z-buffer      8 KB
-    int id[TILE_PX];                 // winner face                                        4 KB
-    int st[TILE_PX];                 // stencil count                                      4 KB
-    TriRec tri[STAGE_TRIS];          // staged per-tile triangle list                      6 KB
+    unsigned long long z[TILE_PX];          // order-preserving keys of the float64 z-buffer      8 KB
+    int id[TILE_PX];                        // winner face                                        4 KB
+    int st[TILE_PX];                        // stencil count                                      4 KB
+    double tri[STAGE_TRIS][REC_DOUBLES];    // staged per-tile triangle list                      4.25 KB
+    double clip[STAGE_CLIP][CLIP_DOUBLES];  // clip coordinates of the staged triangles that need them   3 KB
     int face[STAGE_TRIS];
-    double clip[RASTER_WARPS][CLIP_DOUBLES];
+    int start[STAGE_TRIS + 1];              // exclusive scan of the pixel counts of the staged triangles
+    int geo[STAGE_TRIS];                    // box inside the tile: x0 | y0 << 8 | width << 16
+    signed char clip_slot[STAGE_TRIS];
     unsigned long long red_min[RASTER_WARPS], red_max[RASTER_WARPS];
+    int n_round;
     int uniform;
+    int need_full;                          // the fast winner resolution is not provably right: run the full pass
 };
 
-// One pass over the tile's triangle list.  PASS 1: zbuf = min (RH) / max (LH) of z over covered, unclipped pixels
-// (triangular.py:96-118).  PASS 3: winner = greatest face index whose z equals the final zbuf.
-// Work split: the 32-pixel chunks of triangle t are dealt round-robin to the warps starting at warp t % NW, so both
-// many small triangles and one tile-filling triangle keep every warp busy.
+// One pass over the tile's triangle list.
+//   PASS 1: zbuf = min (RH) / max (LH) of z over covered, unclipped pixels (triangular.py:96-118), remembering the
+//           face that last improved each pixel; an exact tie between two faces raises `need_full`.
+//   PASS 3: winner = greatest face index whose z equals the final zbuf (the reference lets later faces overwrite).
+// Work split: the (triangle, pixel) pairs of a staged round are flattened into one dense list (exclusive scan of the
+// per-triangle pixel counts) and dealt 32 at a time, so a warp is full whether the tile holds a thousand one-pixel
+// triangles or a single triangle covering all of it.
 template <int PASS>
 __device__ __forceinline__ void raster_tris(RasterSmem& sm, const SceneDev& S, const ViewDev& V, const FrameDev& Fr,
                                             const TriRec* __restrict__ vtris, const int* __restrict__ tri_list,
                                             int t_beg, int t_end, int X0, int Y0, int X1, int Yb0, int Y1, bool rh,
                                             uint8_t* status_view) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int base = t_beg; base < t_end; base += STAGE_TRIS) {
-        const int n = min(STAGE_TRIS, t_end - base);
+    int n = 0;
+    for (int base = t_beg; base < t_end; base += n) {
         __syncthreads();  // previous round fully consumed
-        for (int u = threadIdx.x; u < n * 8; u += RASTER_THREADS) {  // coalesced 16-byte pieces
-            const int t = u >> 3, part = u & 7;
-            const int face = tri_list[base + t];
-            reinterpret_cast<uint4*>(&sm.tri[t])[part] = __ldg(reinterpret_cast<const uint4*>(vtris + face) + part);
-            if (part == 0) sm.face[t] = face;
+        if (wid == 0) {   // choose the round: up to 32 triangles, at most STAGE_CLIP of them with a clip test
+            const int cand = min(STAGE_TRIS, t_end - base);
+            const int face = lane < cand ? tri_list[base + lane] : -1;
+            const bool clip = face >= 0 && (vtris[face].flags & TR_NEEDS_CLIP);
+            const unsigned mask = __ballot_sync(0xffffffffu, clip);
+            const int take = __popc(mask) > STAGE_CLIP ? (int)__fns(mask, 0, STAGE_CLIP + 1) : cand;
+            if (lane < take) {
+                sm.face[lane] = face;
+                sm.clip_slot[lane] = clip ? (signed char)__popc(mask & ((1u << lane) - 1)) : (signed char)-1;
+            }
+            if (lane == 0) sm.n_round = take;
         }
         __syncthreads();
-        for (int t = 0; t < n; ++t) {
-            const TriRec& r = sm.tri[t];
-            const int x0 = max((int)r.bx0, X0), x1 = min((int)r.bx1, X1), y0 = max((int)r.by0, Yb0), y1 = min((int)r.by1, Y1);
-            const int w = x1 - x0, npx = w * (y1 - y0);
-            const float rcp_w = 1.0f / (float)w;  // i / w for i < 1024, w <= 32: (i + 0.5) / w is >= 1/64 from an integer
-            const int nchunks = (npx + 31) >> 5;
-            const int c0 = (wid - t) & (RASTER_WARPS - 1);
-            if (c0 >= nchunks) continue;
-            const int face = sm.face[t];
-            const int flags = r.flags;
-            double* cc = sm.clip[wid];
-            if (flags & TR_NEEDS_CLIP) {  // lanes 0..23 each evaluate one clip coordinate (4 FMAs)
-                __syncwarp();
-                if (lane < CLIP_DOUBLES) {
-                    const int cam = lane / 12, vtx = (lane % 12) >> 2, k = lane & 3;
-                    const double4 p = S.pos[S.faces[face].v[vtx]];
-                    const double* M = cam ? V.mvp_dbg : V.mvp;
-                    cc[lane] = fma(p.w, M[12 + k], fma(p.z, M[8 + k], fma(p.y, M[4 + k], p.x * M[k])));
-                }
-                __syncwarp();
+        n = sm.n_round;
+        for (int u = threadIdx.x; u < n * 16; u += RASTER_THREADS) {  // records: coalesced 8-byte pieces
+            const int t = u >> 4, part = u & 15;
+            reinterpret_cast<unsigned long long*>(sm.tri[t])[part] =
+                __ldg(reinterpret_cast<const unsigned long long*>(vtris + sm.face[t]) + part);
+        }
+        for (int u = threadIdx.x; u < n * CLIP_DOUBLES; u += RASTER_THREADS) {  // clip coordinates, 4 FMAs each
+            const int t = u / CLIP_DOUBLES, j = u - t * CLIP_DOUBLES;
+            const int slot = sm.clip_slot[t];
+            if (slot < 0) continue;
+            const int cam = j / 12, vtx = (j % 12) >> 2, k = j & 3;
+            const double4 p = S.pos[S.faces[sm.face[t]].v[vtx]];
+            const double* M = cam ? V.mvp_dbg : V.mvp;
+            sm.clip[slot][j] = fma(p.w, M[12 + k], fma(p.z, M[8 + k], fma(p.y, M[4 + k], p.x * M[k])));
+        }
+        __syncthreads();
+        if (wid == 0) {   // boxes inside the tile and the exclusive scan of their pixel counts
+            int npx = 0;
+            if (lane < n) {
+                const TriRec& r = *reinterpret_cast<const TriRec*>(sm.tri[lane]);
+                const int x0 = max((int)r.bx0, X0), x1 = min((int)r.bx1, X1), y0 = max((int)r.by0, Yb0), y1 = min((int)r.by1, Y1);
+                const int w = max(x1 - x0, 0), h = max(y1 - y0, 0);
+                npx = w * h;
+                sm.geo[lane] = (x0 - X0) | ((y0 - Y0) << 8) | (w << 16);
             }
-            const bool cov_one = (flags & TR_COV_ONE) != 0;
-            unsigned bits = 0;
-            for (int c = c0; c < nchunks; c += RASTER_WARPS) {
-                const int i = (c << 5) + lane;
-                if (i >= npx) continue;
-                const int yy = __float2int_rd(((float)i + 0.5f) * rcp_w), px = x0 + i - yy * w, py = y0 + yy;
-                float bu, bv, bw;
-                if (PASS == 1) B2R_STAT(12, 1);
-                if (!tri_pixel_in(r, cc, px, py, bu, bv, bw)) continue;
-                if (PASS == 1) B2R_STAT(13, 1);
-                const double b0 = (double)bu, b1 = (double)bv, b2 = (double)bw;
-                const double z = cov_one ? seq3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2])
-                                         : gemv3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2]);
-                bits |= 1;
-                if (!(z == z)) continue;
+            int incl = npx;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            sm.start[lane + 1] = incl;
+            if (lane == 0) sm.start[0] = 0;
+        }
+        __syncthreads();
+        const int total = sm.start[n];
+        for (int k0 = wid * 32; k0 < total; k0 += RASTER_THREADS) {
+            const int k = k0 + lane;
+            if (k >= total) continue;
+            int t = 0;  // largest t with start[t] <= k
+#pragma unroll
+            for (int step = 16; step; step >>= 1) if (t + step < n && sm.start[t + step] <= k) t += step;
+            const int i = k - sm.start[t], geo = sm.geo[t];
+            const int w = geo >> 16;
+            // i / w for i < 1024, w <= 32: (i + 0.5) / w stays >= 1/64 away from an integer
+            const int yy = __float2int_rd(((float)i + 0.5f) * (1.0f / (float)w));
+            const int px = X0 + (geo & 0xff) + i - yy * w, py = Y0 + ((geo >> 8) & 0xff) + yy;
+            const TriRec& r = *reinterpret_cast<const TriRec*>(sm.tri[t]);
+            const int slot = sm.clip_slot[t];
+            const double* cc = sm.clip[slot < 0 ? 0 : slot];
+            float bu, bv, bw;
+            if (PASS == 1) B2R_STAT(12, 1);
+            if (!tri_pixel_in(r, cc, px, py, bu, bv, bw)) continue;
+            if (PASS == 1) B2R_STAT(13, 1);
+            const double b0 = (double)bu, b1 = (double)bv, b2 = (double)bw;
+            const double z = (r.flags & TR_COV_ONE) ? seq3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2])
+                                                    : gemv3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2]);
+            unsigned bits = 1;
+            const int face = sm.face[t];
+            if (z == z) {
                 const int p = (py - Y0) * TILE_W + (px - X0);
                 const unsigned long long key = zkey(z);
                 if (PASS == 1) {
-                    if (rh) atomicMin(&sm.z[p], key); else atomicMax(&sm.z[p], key);
+                    const unsigned long long old = rh ? atomicMin(&sm.z[p], key) : atomicMax(&sm.z[p], key);
+                    if (old == key) sm.need_full = 1;                       // exact tie: the greatest face index wins
+                    else if (rh ? (key < old) : (key > old)) sm.id[p] = face;  // last improver (verified afterwards)
                 } else if (key == sm.z[p]) {
                     atomicMax(&sm.id[p], face);
                     bits |= 2 | (sm.st[p] == 0 ? 4 : 0);
                 }
             }
             if (PASS == 3 && status_view) {
-                bits = __reduce_or_sync(0xffffffffu, bits);
-                if (lane == 0 && bits) {
-                    uint8_t* sp = status_view + face;
-                    unsigned* wp = (unsigned*)((uintptr_t)sp & ~(uintptr_t)3);
-                    atomicOr(wp, bits << (8 * ((uintptr_t)sp & 3)));
-                }
+                uint8_t* sp = status_view + face;
+                unsigned* wp = (unsigned*)((uintptr_t)sp & ~(uintptr_t)3);
+                atomicOr(wp, bits << (8 * ((uintptr_t)sp & 3)));
             }
         }
     }
@@ -637,7 +674,7 @@ k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRe
     if (threadIdx.x == 0) { B2R_STAT(11, 1); B2R_STAT(14, q_end - q_beg); B2R_STAT(15, t_end - t_beg); }
     const unsigned long long z_init = zkey(z_bg);
     for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) { sm.z[i] = z_init; sm.id[i] = -1; sm.st[i] = 0; }
-    if (threadIdx.x == 0) sm.uniform = 0;
+    if (threadIdx.x == 0) { sm.uniform = 0; sm.need_full = 0; }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const TriRec* vtris = tris + (size_t)view * Fr.n_faces;
     const int* tri_list = B.tri_list + (size_t)view * B.tri_cap;
@@ -792,8 +829,30 @@ k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRe
         __syncthreads();
     }
 
-    raster_tris<3>(sm, S, V, Fr, vtris, tri_list, t_beg, t_end, X0, Y0, X1, Yb0, Y1, rh, status_view);
+    // ---- winner.  Fast path: the face that last improved a pixel is its winner if its depth is the final zbuf
+    // there and no exact tie was seen in the tile; it is checked by re-evaluating that one face per pixel.  Anything
+    // else (ties, a late store losing a race, status requested) falls back to the full pass over the lists. ----
+    if (!status_view && !sm.need_full) {
+        for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) {
+            const int f = sm.id[i];
+            const unsigned long long kb = sm.z[i];
+            if (f < 0) { if (kb != z_init) sm.need_full = 1; continue; }
+            const TriRec& r = vtris[f];
+            float bu, bv, bw;
+            tri_bary(r, X0 + (i & (TILE_W - 1)), Y0 + i / TILE_W, bu, bv, bw);
+            const double b0 = (double)bu, b1 = (double)bv, b2 = (double)bw;
+            const double z = (r.flags & TR_COV_ONE) ? seq3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2])
+                                                    : gemv3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2]);
+            if (!(z == z) || zkey(z) != kb) sm.need_full = 1;
+        }
+    }
     __syncthreads();
+    if (status_view || sm.need_full) {
+        if (threadIdx.x == 0) B2R_STAT(7, 1);
+        for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) sm.id[i] = -1;
+        raster_tris<3>(sm, S, V, Fr, vtris, tri_list, t_beg, t_end, X0, Y0, X1, Yb0, Y1, rh, status_view);
+        __syncthreads();
+    }
 
     // ---- write-back (coalesced rows) ----
     for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) {
