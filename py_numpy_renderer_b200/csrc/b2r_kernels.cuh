@@ -759,6 +759,12 @@ k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRe
                 const int j = (e + 1 == nv) ? 0 : e + 1;
                 const double xi = R.x[e], yi = R.y[e];
                 const double ex = R.x[j] - xi, ey = R.y[j] - yi;
+                // (warp-uniform) an edge whose worst corner of the rectangle is already inside constrains no row
+                {
+                    const double fworst = front ? edge_fn(ey >= 0 ? rx0 : rx1, ex <= 0 ? ry0 : ry1, xi, yi, ex, ey)
+                                                : edge_fn(ey >= 0 ? rx1 : rx0, ex <= 0 ? ry1 : ry0, xi, yi, ex, ey);
+                    if (front ? (fworst > 0) : (fworst < 0)) continue;
+                }
                 if (lo > hi) continue;
                 const double c = ((double)py - yi) * ex;
                 auto pred = [&](int px) {  // front ? f > 0 : f < 0 with f = (px - xi)*ey - c  (triangular.py:305-311)
@@ -768,20 +774,25 @@ k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRe
                 const bool up = front ? (ey > 0) : (ey < 0);  // the true set is upward closed in px
                 if (ey == 0 || !(ey == ey)) {
                     if (!pred(lo)) hi = lo - 1;
-                } else if (up) {
-                    if (!pred(hi)) { hi = lo - 1; }
-                    else {
-                        int a = lo, b = hi;  // pred(b) holds: smallest px with pred
-                        while (a < b) { const int m = (a + b) >> 1; if (pred(m)) b = m; else a = m + 1; }
-                        lo = b;
-                    }
-                } else {
-                    if (!pred(lo)) { hi = lo - 1; }
-                    else {
-                        int a = lo, b = hi;  // pred(a) holds: largest px with pred
-                        while (a < b) { const int m = (a + b + 1) >> 1; if (pred(m)) a = m; else b = m - 1; }
-                        hi = a;
-                    }
+                    continue;
+                }
+                // The boundary is where f changes sign: px* = xi + c/ey.  Start from that estimate and walk to the
+                // exact first/last pixel satisfying the EXACT predicate (monotone in px): normally zero or one step.
+                const double est = xi + c / ey;
+                if (up) {          // smallest px in [lo,hi] with pred
+                    if (!pred(hi)) { hi = lo - 1; continue; }
+                    int k = est >= (double)hi ? hi : (est <= (double)lo ? lo : (int)ceil(est));  // NaN falls to lo
+                    if (!(est == est)) k = lo;
+                    while (k > lo && pred(k - 1)) --k;
+                    while (!pred(k)) ++k;                 // terminates: pred(hi) holds
+                    lo = k;
+                } else {           // largest px in [lo,hi] with pred
+                    if (!pred(lo)) { hi = lo - 1; continue; }
+                    int k = est >= (double)hi ? hi : (est <= (double)lo ? lo : (int)floor(est));
+                    if (!(est == est)) k = hi;
+                    while (k < hi && pred(k + 1)) ++k;
+                    while (!pred(k)) --k;                 // terminates: pred(lo) holds
+                    hi = k;
                 }
             }
             const int delta = front ? 1 : -1;
