@@ -522,6 +522,7 @@ struct RasterSmem {
     signed char clip_slot[STAGE_TRIS];
     unsigned long long red_min[RASTER_WARPS], red_max[RASTER_WARPS];
     int n_round;
+    int next_quad;
     int uniform;
     int need_full;                          // the fast winner resolution is not provably right: run the full pass
 };
@@ -674,7 +675,7 @@ k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRe
     if (threadIdx.x == 0) { B2R_STAT(11, 1); B2R_STAT(14, q_end - q_beg); B2R_STAT(15, t_end - t_beg); }
     const unsigned long long z_init = zkey(z_bg);
     for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) { sm.z[i] = z_init; sm.id[i] = -1; sm.st[i] = 0; }
-    if (threadIdx.x == 0) { sm.uniform = 0; sm.need_full = 0; }
+    if (threadIdx.x == 0) { sm.uniform = 0; sm.need_full = 0; sm.next_quad = 0; }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const TriRec* vtris = tris + (size_t)view * Fr.n_faces;
     const int* tri_list = B.tri_list + (size_t)view * B.tri_cap;
@@ -711,7 +712,13 @@ k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRe
     if (!skip_bg || any_cov) {
         const int* quad_list = B.quad_list + (size_t)view * B.quad_cap;
         const QuadRec* vquads = quads + (size_t)view * quad_stride;
-        for (int t = q_beg + wid; t < q_end; t += RASTER_WARPS) {
+        // quads are handed out one at a time (their cost differs by orders of magnitude): a warp that finishes a
+        // cheap one grabs the next instead of idling at the barrier
+        for (;;) {
+            int t = 0;
+            if (lane == 0) t = q_beg + atomicAdd(&sm.next_quad, 1);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (t >= q_end) break;
             const int entry = quad_list[t];
             const bool full = (entry & QUAD_FULL_BIT) != 0;  // every pixel of the tile is inside the quad
             const QuadRec& R = vquads[entry & (QUAD_FULL_BIT - 1)];
