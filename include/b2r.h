@@ -156,6 +156,10 @@ int b2r_scene_get_silhouette(b2r_scene* scene, int32_t* out_pairs, int32_t* out_
  * stream (use b2r_sync, or order against `b2r_stream()`). */
 int b2r_render(b2r_scene* scene, const b2r_frame_params* params, const b2r_view* views, int32_t n_views,
                uint8_t* out_rgb, const b2r_debug_out* debug /* nullable */, int32_t out_on_device);
+/* out_on_device == 2: host pointers, but the call returns as soon as everything is enqueued; the frames (and the
+ * capacity check) are complete after b2r_wait(b2r_last_ticket()).  Up to two such calls may be in flight. */
+int64_t b2r_last_ticket(void);
+int b2r_wait(int64_t ticket);
 int b2r_sync(void);
 void* b2r_stream(void); /* the cudaStream_t the library launches on */
 

@@ -44,6 +44,8 @@ _SYMBOLS = {
     "b2r_scene_get_silhouette": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
     "b2r_render": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]),
     "b2r_sync": (C.c_int, []),
+    "b2r_last_ticket": (C.c_int64, []),
+    "b2r_wait": (C.c_int, [C.c_int64]),
     "b2r_stream": (C.c_void_p, []),
     "b2r_launch_count": (C.c_int64, []),
     "b2r_last_stage_ms": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -97,8 +99,12 @@ def submit(fn, *args, **kw):
     libb2r, so the caller can evaluate the cameras of the next batch while this one renders and copies."""
     global _worker
     if _worker is None:
+        import sys
         from concurrent.futures import ThreadPoolExecutor
         _worker = ThreadPoolExecutor(max_workers=1, thread_name_prefix="b2r")
+        # the worker re-acquires the GIL after every library call; with the default 5 ms switch interval it would
+        # wait behind the caller's camera maths for longer than a whole batch takes to render
+        sys.setswitchinterval(min(sys.getswitchinterval(), 2e-4))
     return _worker.submit(fn, *args, **kw)
 
 
@@ -192,7 +198,7 @@ class DeviceScene:
         fp, views = self.pack(cameras, debug_cameras, light, resolution, system, background, persist_silhouette, band)
         return self.render_packed(fp, views, want_debug=want_debug, out=out)
 
-    def render_packed(self, fp, views, want_debug=False, out=None):
+    def render_packed(self, fp, views, want_debug=False, out=None, wait=True):
         """-> (frames, info).  frames: uint8 (n, H, W, 3): a new NumPy array, `out` if it is a NumPy array (filled
         synchronously; pinned memory makes the copy fast), or `out` if it is a CUDA tensor / device pointer
         (written asynchronously on the library stream)."""
@@ -222,12 +228,29 @@ class DeviceScene:
             else:
                 frames = np.zeros((n, H, W, 3), np.uint8) if band is not None else np.empty((n, H, W, 3), np.uint8)
             target = C.c_void_p(frames.ctypes.data)
+        mode = 1 if on_device else (0 if (wait or want_debug) else 2)
         _check(self.lib.b2r_render(self.handle, C.byref(fp), C.cast(views, C.c_void_p), n, target,
-                                   C.byref(dbg) if dbg is not None else None, int(on_device)))
+                                   C.byref(dbg) if dbg is not None else None, mode))
+        if mode == 2:
+            info['ticket'] = int(self.lib.b2r_last_ticket())
+            info['keep'] = (fp, views)
         if want_debug:
             info['face_status'] = info['face_status'][:, :self.packed.total_faces]
             info['n_silhouette'] = info['n_silhouette'][:, :self.packed.n_models]
         return frames, info
+
+
+class PendingFrames:
+    """Frames of an asynchronous host render: `result()` blocks (GIL released) until they are in `out`."""
+
+    def __init__(self, lib, ticket, frames, keep):
+        self.lib, self.ticket, self.frames, self.keep = lib, ticket, frames, keep
+
+    def result(self):
+        if self.ticket is not None:
+            _check(self.lib.b2r_wait(self.ticket))
+            self.ticket = self.keep = None
+        return self.frames
 
 
 def status_report(models, face_status):

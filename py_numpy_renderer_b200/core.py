@@ -395,16 +395,20 @@ class Scene:
         return frames
 
     def render_batch_async(self, cameras, debug_cameras=None, out=None, band=None):
-        """`render_batch` as a two-stage pipeline: the camera maths of this batch runs here, in the calling
-        thread; rendering + the copy into `out` run on the library's worker thread.  Returns a Future whose
-        `result()` is the frame stack.  Keep one or two batches in flight (each with its own `out` buffer) and the
-        host-side evaluation of batch k+1 overlaps the GPU work of batch k."""
+        """`render_batch` without the final wait: the camera maths runs here, the kernels and the device-to-host
+        copies are only ENQUEUED (library streams), and the call returns a handle whose `result()` blocks until the
+        frames are in `out` (a pinned NumPy array the caller must leave alone until then).  Keep two batches in
+        flight, each with its own `out`, and the host work of batch k+1 and the PCIe transfer of batch k overlap the
+        rendering of batch k+1."""
         from . import _native
         dev = self._device_scene()
         cameras = list(cameras)
         dcams = [self.debug_camera] * len(cameras) if debug_cameras is None else list(debug_cameras)
         for cam in cameras + dcams:
             cam.scene = self
+        if out is None:
+            out = np.empty((len(cameras), int(self.resolution[0]), int(self.resolution[1]), 3), np.uint8)
         fp, views = dev.pack(cameras, dcams, self.light, self.resolution, self.system, self._background(),
                              persist_silhouette=False, band=band)
-        return _native.submit(lambda: dev.render_packed(fp, views, out=out)[0])
+        frames, info = dev.render_packed(fp, views, out=out, wait=False)
+        return _native.PendingFrames(dev.lib, info.get('ticket'), frames, info.get('keep'))

@@ -32,8 +32,26 @@ struct Globals {
     int* pinned_flags = nullptr;  // overflow read-back, 2 ints per view
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_done = nullptr;
-    int host_chunk = 8;           // views per chunk when frames go to host memory (copy/compute overlap)
+    static constexpr int N_AUX = 3;   // sub-chunks of one batch render concurrently: the long tail of a raster launch
+    cudaStream_t aux[N_AUX] = {};     // (a few very heavy tiles) is filled by the next sub-chunk's work
+    cudaEvent_t aux_done[16] = {};
+    cudaEvent_t setup_done = nullptr;
+    int host_chunk = 2;           // views per sub-chunk when frames go to host memory (copy/compute overlap)
+    int dev_chunk = 8;            // views per sub-chunk when frames stay on the device (overlap of raster tails)
+    int async_chunk = 8;          // views per sub-chunk of a host-asynchronous call
+    int aux_host = 2, aux_dev = 3;  // how many auxiliary streams the sub-chunks rotate over
+    // pinned staging ring for the per-view constants: a pageable source would make cudaMemcpyAsync synchronise the
+    // stream, i.e. serialise the host with the previous chunk / previous asynchronous call
+    struct Staging { ViewDev* host = nullptr; size_t cap = 0; cudaEvent_t done = nullptr; bool used = false; } stage[4];
+    unsigned stage_next = 0;
+    // host-asynchronous renders (out_on_device == 2): ticket t uses slot t % 4 for its events and overflow flags
+    long long ticket = 0;
+    cudaEvent_t ticket_copy[4] = {}, ticket_compute[4] = {};
+    int ticket_views[4] = {};
+    struct b2r_scene* ticket_scene[4] = {};
+    long long rgb_last_ticket[2] = {-1, -1};  // which ticket last copied out of rgb[slot]
     int pending_views = 0;        // asynchronous render whose overflow flags were not checked yet
+    int* pending_flags = nullptr;
     struct b2r_scene* pending_scene = nullptr;
 } g;
 constexpr int MAX_FLAG_VIEWS = 4096;
@@ -109,7 +127,7 @@ struct b2r_scene {
     DevBuf<short> stencil;
     DevBuf<double> zplane;
     DevBuf<uint8_t> status;
-    DevBuf<uint8_t> rgb;
+    DevBuf<uint8_t> rgb[2];  // device staging of host-bound frames, alternating so that copies of call t overlap call t+1
     int tri_cap = 0, quad_cap = 0;
     int views_cap = 0;
 
@@ -143,10 +161,21 @@ int b2r_init(int device) {
     g.sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     for (int i = 0; i <= B2R_MAX_STAGES; ++i) CK(cudaEventCreate(&g.stage_ev[i]));
-    CK(cudaMallocHost(&g.pinned_flags, sizeof(int) * 2 * MAX_FLAG_VIEWS));
+    CK(cudaMallocHost(&g.pinned_flags, sizeof(int) * 2 * MAX_FLAG_VIEWS * 4));
+    for (int i = 0; i < 4; ++i) {
+        CK(cudaEventCreateWithFlags(&g.ticket_copy[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&g.ticket_compute[i], cudaEventDisableTiming));
+    }
     CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&g.chunk_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&g.setup_done, cudaEventDisableTiming));
+    for (int i = 0; i < Globals::N_AUX; ++i) CK(cudaStreamCreateWithFlags(&g.aux[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 16; ++i) CK(cudaEventCreateWithFlags(&g.aux_done[i], cudaEventDisableTiming));
     if (const char* hc = std::getenv("B2R_HOST_CHUNK")) g.host_chunk = std::max(1, std::atoi(hc));
+    if (const char* dc = std::getenv("B2R_DEV_CHUNK")) g.dev_chunk = std::max(1, std::atoi(dc));
+    if (const char* ac = std::getenv("B2R_ASYNC_CHUNK")) g.async_chunk = std::max(1, std::atoi(ac));
+    if (const char* a = std::getenv("B2R_AUX_HOST")) g.aux_host = std::min(Globals::N_AUX, std::max(1, std::atoi(a)));
+    if (const char* a = std::getenv("B2R_AUX_DEV")) g.aux_dev = std::min(Globals::N_AUX, std::max(1, std::atoi(a)));
     float lut[2][256];
     for (int i = 0; i < 256; ++i) {  // core.py:96-104: f32(u8/255), f32(u8/255*2-1) with float64 intermediates
         const double t = (double)i / 255;
@@ -179,13 +208,33 @@ int b2r_sync(void) {
     CK(cudaStreamSynchronize(g.copy_stream));
     if (g.pending_views > 0) {  // an asynchronous render ran since the last check: did its tile lists fit?
         int need_tri = 0, need_quad = 0;
-        for (int i = 0; i < g.pending_views; ++i) { need_tri = std::max(need_tri, g.pinned_flags[2 * i]); need_quad = std::max(need_quad, g.pinned_flags[2 * i + 1]); }
+        for (int i = 0; i < g.pending_views; ++i) { need_tri = std::max(need_tri, g.pending_flags[2 * i]); need_quad = std::max(need_quad, g.pending_flags[2 * i + 1]); }
         g.pending_views = 0;
         if (need_tri || need_quad) {
             b2r_scene_grow_lists(g.pending_scene, need_tri, need_quad);
             return fail("tile list capacity overflow in an asynchronous render: affected frames show background only; "
                         "capacity was raised, render again");
         }
+    }
+    return 0;
+}
+int64_t b2r_last_ticket(void) { return (int64_t)g.ticket; }
+int b2r_wait(int64_t ticket) {
+    if (!g.ready) return fail("b2r_init was not called");
+    if (ticket <= 0 || ticket > g.ticket) return fail("b2r_wait: unknown ticket");
+    if (g.ticket - ticket >= 4) return 0;  // long gone: its slot has been reused, so it was complete
+    CK(cudaSetDevice(g.device));
+    const int tslot = (int)(ticket & 3);
+    CK(cudaEventSynchronize(g.ticket_copy[tslot]));
+    CK(cudaEventSynchronize(g.ticket_compute[tslot]));
+    const int* flags = g.pinned_flags + (size_t)tslot * 2 * MAX_FLAG_VIEWS;
+    int need_tri = 0, need_quad = 0;
+    for (int i = 0; i < g.ticket_views[tslot]; ++i) { need_tri = std::max(need_tri, flags[2 * i]); need_quad = std::max(need_quad, flags[2 * i + 1]); }
+    g.ticket_views[tslot] = 0;
+    if (need_tri || need_quad) {
+        b2r_scene_grow_lists(g.ticket_scene[tslot], need_tri, need_quad);
+        return fail("tile list capacity overflow in an asynchronous render: affected frames show background only; "
+                    "capacity was raised, render again");
     }
     return 0;
 }
@@ -361,13 +410,14 @@ int b2r_scene_destroy(b2r_scene* sc) {
     if (g.ready) cudaSetDevice(g.device);
     if (g.ready) { cudaStreamSynchronize(g.stream); cudaStreamSynchronize(g.copy_stream); }
     if (g.pending_scene == sc) { g.pending_scene = nullptr; g.pending_views = 0; }
+    for (int i = 0; i < 4; ++i) if (g.ticket_scene[i] == sc) { g.ticket_scene[i] = nullptr; g.ticket_views[i] = 0; }
     sc->pos.release(); sc->uv.release(); sc->nrm.release(); sc->faces.release(); sc->mats.release(); sc->tex.release();
     for (uchar4* d : sc->tex_data) cudaFree(d);
     sc->sky.release(); sc->edge_v.release(); sc->edge_ptr.release(); sc->edge_inc.release(); sc->edge_model.release();
     sc->sil_state.release(); sc->facing.release(); sc->sil.release(); sc->counters.release(); sc->views.release();
     sc->tris.release(); sc->quads.release(); sc->tile_counts.release(); sc->tile_offs.release(); sc->tri_list.release();
     sc->quad_list.release(); sc->overflow.release(); sc->winner.release(); sc->stencil.release(); sc->zplane.release();
-    sc->status.release(); sc->rgb.release();
+    sc->status.release(); sc->rgb[0].release(); sc->rgb[1].release();
     delete sc;
     return 0;
 }
@@ -506,8 +556,12 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
     const size_t per_view = (size_t)F * sizeof(TriRec) + (size_t)E * sizeof(QuadRec) + npx * 6 + (want_z ? npx * 8 : 0);
     int VB = (int)std::max<size_t>(1, std::min<size_t>(n_views, ((size_t)6 << 30) / std::max<size_t>(per_view, 1)));
     VB = std::min(VB, 64);
-    const bool pipelined = !out_on_device && !dbg && n_views > 1;
-    if (pipelined) VB = std::min(VB, std::max(1, g.host_chunk));
+    const bool host_out = out_on_device != 1;
+    const bool host_async = out_on_device == 2 && !dbg;
+    const long long ticket = ++g.ticket;
+    const int tslot = (int)(ticket & 3), rslot = (int)(ticket & 1);
+    int* const flags = g.pinned_flags + (size_t)tslot * 2 * MAX_FLAG_VIEWS;
+    const bool pipelined = host_out && !dbg && n_views > 1;
     if (n_views > MAX_FLAG_VIEWS) return fail("too many views in one call (max 4096)");
     if (sc->tri_cap == 0) sc->tri_cap = std::max(1 << 16, 4 * F + 8 * n_tiles);
     if (sc->quad_cap == 0) sc->quad_cap = std::max(1 << 20, 32 * E);
@@ -533,9 +587,28 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
     }
     stage_mark("silhouette");
 
-    const cudaMemcpyKind kind = out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    // ---- per-view constants: evaluated once, staged in pinned memory, one asynchronous upload for the whole call ----
+    {
+        Globals::Staging& st = g.stage[g.stage_next++ % 4];
+        if (!st.done) CK(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
+        if (st.used) CK(cudaEventSynchronize(st.done));  // the upload that last used this slot has left host memory
+        if (st.cap < (size_t)n_views) {
+            if (st.host) cudaFreeHost(st.host);
+            st.host = nullptr; st.cap = 0;
+            CK(cudaMallocHost(&st.host, sizeof(ViewDev) * (size_t)std::max(n_views, 64)));
+            st.cap = (size_t)std::max(n_views, 64);
+        }
+        for (int i = 0; i < n_views; ++i) make_view(views[i], with_sky, st.host[i]);
+        CK(sc->views.reserve(n_views));
+        CK(cudaMemcpyAsync(sc->views.p, st.host, sizeof(ViewDev) * (size_t)n_views, cudaMemcpyHostToDevice, g.stream));
+        CK(cudaEventRecord(st.done, g.stream));
+        st.used = true;
+    }
+
+    const cudaMemcpyKind kind = !host_out ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (host_out && g.rgb_last_ticket[rslot] >= 0 && g.ticket - g.rgb_last_ticket[rslot] < 4)
+        CK(cudaStreamWaitEvent(g.stream, g.ticket_copy[g.rgb_last_ticket[rslot] & 3], 0));  // its frames have left rgb[rslot]
     for (int attempt = 0; attempt < 4; ++attempt) {
-        CK(sc->views.reserve(VB));
         CK(sc->tris.reserve((size_t)VB * F));
         CK(sc->quads.reserve((size_t)VB * E));
         CK(sc->tile_counts.reserve((size_t)VB * n_tiles * 2));
@@ -547,14 +620,11 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
         CK(sc->stencil.reserve((size_t)VB * npx));
         if (want_z) CK(sc->zplane.reserve((size_t)VB * npx));
         if (want_status) CK(sc->status.reserve((size_t)VB * F + 8));
-        if (!out_on_device) CK(sc->rgb.reserve((size_t)n_views * npx * 3));  // one region per view: copies never race
+        if (host_out) CK(sc->rgb[rslot].reserve((size_t)n_views * npx * 3));  // one region per view: copies never race
 
         for (int first = 0; first < n_views; first += VB) {
             const int nv = std::min(VB, n_views - first);
-            std::vector<ViewDev> hv(nv);
-            for (int i = 0; i < nv; ++i) make_view(views[first + i], with_sky, hv[i]);
-            // pageable source: the runtime stages it before returning, so `hv` may die at the end of the iteration
-            CK(cudaMemcpyAsync(sc->views.p, hv.data(), sizeof(ViewDev) * nv, cudaMemcpyHostToDevice, g.stream));
+            const ViewDev* dviews = sc->views.p + first;
             CK(cudaMemsetAsync(sc->tile_counts.p, 0, sizeof(int) * (size_t)VB * n_tiles * 2, g.stream));
 
             BinDev B;
@@ -565,12 +635,12 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
             uint8_t* status = want_status ? sc->status.p : nullptr;
 
             if (F > 0) {
-                k_tri_setup<<<dim3((F + 127) / 128, nv), 128, 0, g.stream>>>(S, sc->views.p, Fr, sc->tris.p, status);
+                k_tri_setup<<<dim3((F + 127) / 128, nv), 128, 0, g.stream>>>(S, dviews, Fr, sc->tris.p, status);
                 ++g.launches;
             }
             stage_mark("tri_setup");
             const int quad_blocks = std::max(1, std::min((sc->n_edges + 63) / 64, g.sm_count * 4));
-            k_quad_setup<<<dim3(quad_blocks, nv), 64, 0, g.stream>>>(sc->sil.p, sc->counters.p, sc->views.p, Fr, sc->quads.p, E);
+            k_quad_setup<<<dim3(quad_blocks, nv), 64, 0, g.stream>>>(sc->sil.p, sc->counters.p, dviews, Fr, sc->quads.p, E);
             ++g.launches;
             stage_mark("quad_setup");
             const int bin_blocks = g.sm_count * 8;
@@ -581,36 +651,54 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
             stage_mark("bin");
             RasterOut O;
             O.winner = sc->winner.p; O.stencil = sc->stencil.p; O.z = want_z ? sc->zplane.p : nullptr; O.status = status;
-            k_raster<<<dim3(Fr.tiles_x, Fr.tiles_y, nv), RASTER_THREADS, 0, g.stream>>>(S, sc->views.p, Fr, sc->tris.p,
-                                                                                     sc->quads.p, E, B, O);
-            ++g.launches;
+            uint8_t* rgb_dev = (!host_out ? out_rgb : sc->rgb[rslot].p) + (size_t)first * npx * 3;
+            const int rows = row_end - row_begin;
+            // raster + shade (+ copy) in sub-chunks: set-up and binning above ran once for the whole batch, so a
+            // sub-chunk costs two launches.  Sub-chunks are independent (per-view planes, read-only lists): they go
+            // round-robin to a few auxiliary streams so that the tail of one raster launch overlaps the next, and
+            // their frames leave over PCIe (copy stream) while later sub-chunks render.
+            // host-asynchronous calls overlap their copies with the NEXT call, so they keep whole-batch launches
+            const int want_sub = !host_out ? g.dev_chunk : (host_async ? g.async_chunk : g.host_chunk);
+            const int sub = (g.timing || dbg || nv <= want_sub) ? nv : std::max(1, want_sub);
+            const bool multi = sub < nv;
+            if (multi) CK(cudaEventRecord(g.setup_done, g.stream));
+            int n_sub = 0;
+            for (int v0 = 0; v0 < nv; v0 += sub, ++n_sub) {
+                const int sv = std::min(sub, nv - v0);
+                cudaStream_t st = multi ? g.aux[n_sub % (!host_out ? g.aux_dev : g.aux_host)] : g.stream;
+                if (multi) CK(cudaStreamWaitEvent(st, g.setup_done, 0));
+                k_raster<<<dim3(Fr.tiles_x, Fr.tiles_y, sv), RASTER_THREADS, 0, st>>>(S, dviews, Fr, sc->tris.p,
+                                                                                   sc->quads.p, E, B, O, v0);
+                ++g.launches;
+                stage_mark("raster");
+                k_shade<<<dim3((W + 31) / 32, (rows + B2R_SHADE_THREADS / 32 - 1) / (B2R_SHADE_THREADS / 32), sv),
+                          B2R_SHADE_THREADS, 0, st>>>(S, dviews, Fr, sc->tris.p, sc->winner.p, sc->stencil.p, rgb_dev, v0);
+                ++g.launches;
+                stage_mark("shade");
+                cudaEvent_t done = g.aux_done[n_sub % 16];
+                if (multi || host_out) CK(cudaEventRecord(done, st));
+                if (multi) CK(cudaStreamWaitEvent(g.stream, done, 0));  // the batch is complete on the main stream
+                if (host_out) {  // these frames travel on the copy stream while the next sub-chunk renders
+                    CK(cudaStreamWaitEvent(g.copy_stream, done, 0));
+                    const size_t band_off = (size_t)(H - row_end) * W * 3, band_bytes = (size_t)(row_end - row_begin) * W * 3;
+                    uint8_t* src = rgb_dev + (size_t)v0 * npx * 3;
+                    uint8_t* dst = out_rgb + (size_t)(first + v0) * npx * 3;
+                    if (band_bytes == npx * 3) {
+                        CK(cudaMemcpyAsync(dst, src, (size_t)sv * npx * 3, kind, g.copy_stream));
+                    } else {
+                        for (int i = 0; i < sv; ++i)
+                            CK(cudaMemcpyAsync(dst + (size_t)i * npx * 3 + band_off, src + (size_t)i * npx * 3 + band_off,
+                                               band_bytes, kind, g.copy_stream));
+                    }
+                }
+            }
             if (want_status) {
                 const size_t ns = (size_t)nv * F;
                 k_status_resolve<<<(unsigned)((ns + 255) / 256), 256, 0, g.stream>>>(status, ns);
                 ++g.launches;
             }
-            stage_mark("raster");
-            uint8_t* rgb_dev = (out_on_device ? out_rgb : sc->rgb.p) + (size_t)first * npx * 3;
-            const int rows = row_end - row_begin;
-            k_shade<<<dim3((W + 31) / 32, (rows + B2R_SHADE_THREADS / 32 - 1) / (B2R_SHADE_THREADS / 32), nv), B2R_SHADE_THREADS, 0, g.stream>>>(S, sc->views.p, Fr, sc->tris.p,
-                                                                               sc->winner.p, sc->stencil.p, rgb_dev);
-            ++g.launches;
-            stage_mark("shade");
             CK(cudaGetLastError());
-            CK(cudaMemcpyAsync(g.pinned_flags + 2 * first, sc->overflow.p, sizeof(int) * 2 * nv, cudaMemcpyDeviceToHost, g.stream));
-
-            if (!out_on_device) {  // frames of this chunk travel on the copy stream while the next chunk renders
-                CK(cudaEventRecord(g.chunk_done, g.stream));
-                CK(cudaStreamWaitEvent(g.copy_stream, g.chunk_done, 0));
-                const size_t band_off = (size_t)(H - row_end) * W * 3, band_bytes = (size_t)(row_end - row_begin) * W * 3;
-                if (band_bytes == npx * 3) {
-                    CK(cudaMemcpyAsync(out_rgb + (size_t)first * npx * 3, rgb_dev, (size_t)nv * npx * 3, kind, g.copy_stream));
-                } else {
-                    for (int i = 0; i < nv; ++i)
-                        CK(cudaMemcpyAsync(out_rgb + (size_t)(first + i) * npx * 3 + band_off, rgb_dev + (size_t)i * npx * 3 + band_off,
-                                           band_bytes, kind, g.copy_stream));
-                }
-            }
+            CK(cudaMemcpyAsync(flags + 2 * first, sc->overflow.p, sizeof(int) * 2 * nv, cudaMemcpyDeviceToHost, g.stream));
             if (dbg) {  // debug planes: same stream, so the next chunk cannot overwrite the scratch planes early
                 if (dbg->z) CK(cudaMemcpyAsync(dbg->z + (size_t)first * npx, sc->zplane.p, sizeof(double) * nv * npx, kind, g.stream));
                 if (dbg->stencil) CK(cudaMemcpyAsync(dbg->stencil + (size_t)first * npx, sc->stencil.p, sizeof(short) * nv * npx, kind, g.stream));
@@ -622,15 +710,26 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
                                            sizeof(int) * sc->n_models, kind, g.stream));
             }
         }
-        if (out_on_device && !dbg) {  // asynchronous mode: capacity overflow is reported by the next b2r_sync
+        if (host_out) {
+            CK(cudaEventRecord(g.ticket_copy[tslot], g.copy_stream));
+            g.rgb_last_ticket[rslot] = ticket;
+        }
+        if (host_async) {  // frames are on their way: b2r_wait(ticket) blocks until they (and the overflow flags) landed
+            CK(cudaEventRecord(g.ticket_compute[tslot], g.stream));
+            g.ticket_views[tslot] = n_views;
+            g.ticket_scene[tslot] = sc;
+            return 0;
+        }
+        if (!host_out && !dbg) {  // asynchronous mode: capacity overflow is reported by the next b2r_sync
             g.pending_views = n_views;
             g.pending_scene = sc;
+            g.pending_flags = flags;
             return 0;
         }
         CK(cudaStreamSynchronize(g.stream));
         CK(cudaStreamSynchronize(g.copy_stream));
         int need_tri = 0, need_quad = 0;
-        for (int i = 0; i < n_views; ++i) { need_tri = std::max(need_tri, g.pinned_flags[2 * i]); need_quad = std::max(need_quad, g.pinned_flags[2 * i + 1]); }
+        for (int i = 0; i < n_views; ++i) { need_tri = std::max(need_tri, flags[2 * i]); need_quad = std::max(need_quad, flags[2 * i + 1]); }
         if (!need_tri && !need_quad) return 0;
         if (need_tri) { sc->tri_cap = need_tri + need_tri / 4; sc->tri_list.release(); }
         if (need_quad) { sc->quad_cap = need_quad + need_quad / 4; sc->quad_list.release(); }

@@ -638,9 +638,9 @@ __device__ __forceinline__ void raster_tris(RasterSmem& sm, const SceneDev& S, c
 #endif
 __global__ void __launch_bounds__(RASTER_THREADS, B2R_RASTER_MINB)
 k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec* __restrict__ tris,
-         const QuadRec* __restrict__ quads, int quad_stride, BinDev B, RasterOut O) {
+         const QuadRec* __restrict__ quads, int quad_stride, BinDev B, RasterOut O, int view0) {
     __shared__ RasterSmem sm;
-    const int view = blockIdx.z;
+    const int view = blockIdx.z + view0;  // view0: first view of this sub-chunk within the set-up batch
     const ViewDev& V = views[view];
     const int tx = blockIdx.x, ty = blockIdx.y + Fr.tile_row0;
     const int n_tiles = Fr.tiles_x * Fr.tiles_y;
@@ -1142,8 +1142,8 @@ __device__ __forceinline__ bool skybox_pixel(const SceneDev& S, const ViewDev& V
 #endif
 __global__ void __launch_bounds__(B2R_SHADE_THREADS, B2R_SHADE_MINB)
 k_shade(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec* __restrict__ tris,
-        const int* __restrict__ winner, const short* __restrict__ stencil, uint8_t* __restrict__ out_rgb) {
-    const int view = blockIdx.z;
+        const int* __restrict__ winner, const short* __restrict__ stencil, uint8_t* __restrict__ out_rgb, int view0) {
+    const int view = blockIdx.z + view0;
     const ViewDev& V = views[view];
     const int lane = threadIdx.x & 31;
     const int px = blockIdx.x * 32 + lane;
