@@ -140,3 +140,109 @@ def orbit_cameras(n, radius=3.0, height=1.5, start=0.0, fovy=60, near=0.1, far=1
         cams.append(b2r.Camera((radius * np.sin(t), height, radius * np.cos(t)), center=np.array((0, 0, 0)),
                                fovy=fovy, near=near, far=far, backface_culling=True))
     return cams
+
+
+# ---- seeded random scenes (fuzzing the parity of oracle / CUDA / reference) ------------------------------------
+def random_scene_spec(seed):
+    """A small random scene as plain data: meshes (closed blobs + loose triangles), textures, camera, light."""
+    rng = np.random.default_rng(seed)
+    spec = dict(seed=seed, models=[])
+    n_models = int(rng.integers(1, 4))
+    for mi in range(n_models):
+        kind = rng.choice(['torus', 'soup', 'plane'])
+        if kind == 'torus':
+            nu, nv = int(rng.integers(5, 14)), int(rng.integers(4, 10))
+            v, uv, n, f = torus_arrays(nu, nv, R=float(rng.uniform(0.4, 0.9)), r0=float(rng.uniform(0.15, 0.35)),
+                                       amp=float(rng.uniform(0, 0.08)), fu=3, fv=2)
+        elif kind == 'plane':
+            s = float(rng.uniform(1, 4))
+            v = (FLOOR_V * np.array([s / 2, 1, s / 2, 1], np.float32)).astype(np.float32)
+            uv, n, f = FLOOR_UV.copy(), FLOOR_N.copy(), FLOOR_F.copy()
+        else:
+            nt = int(rng.integers(3, 40))
+            v = np.concatenate([rng.uniform(-1.2, 1.2, (nt * 3, 3)), np.ones((nt * 3, 1))], 1).astype(np.float32)
+            uv = np.concatenate([rng.uniform(0, 1, (nt * 3, 2)), np.zeros((nt * 3, 1))], 1).astype(np.float32)
+            n = rng.standard_normal((nt * 3, 3)).astype(np.float32)
+            n /= np.linalg.norm(n, axis=1, keepdims=True)
+            f = np.zeros((nt, 3, 4), np.int32)
+            f[..., 0] = f[..., 1] = f[..., 2] = np.arange(nt * 3).reshape(nt, 3)
+            if nt > 4:
+                f[1, 2, 0] = f[1, 1, 0]                      # a degenerate face (repeated vertex)
+        offset = rng.uniform(-0.6, 0.6, 3) * (mi > 0)
+        transform = None
+        if rng.random() < 0.5:                               # float64 vertices through an `@` chain
+            transform = dict(scale=float(rng.uniform(0.6, 1.3)), translation=offset.tolist(),
+                             rotate=rng.uniform(-40, 40, 3).tolist())
+        else:
+            v = v.copy()
+            v[:, :3] += offset.astype(np.float32)
+        tex = {}
+        if rng.random() < 0.6:
+            tex['map_Kd'] = dict(texels=procedural_texture(32, int(rng.integers(1 << 30))), signed=False, tangent=False)
+        r = rng.random()
+        if r < 0.35:
+            tex['norm'] = dict(texels=procedural_texture(32, int(rng.integers(1 << 30)), 'normal'), signed=True, tangent=True)
+        elif r < 0.5:
+            tex['norm'] = dict(texels=procedural_texture(16, int(rng.integers(1 << 30)), 'normal'), signed=True, tangent=False)
+        if rng.random() < 0.3:
+            tex['map_Ks'] = dict(texels=procedural_texture(16, int(rng.integers(1 << 30))), signed=False, tangent=False)
+        spec['models'].append(dict(v=v, uv=uv, n=n if rng.random() < 0.85 or 'norm' in tex else None, f=f,
+                                   transform=transform, tex=tex, clip=bool(rng.random() < 0.85),
+                                   Ns=float(rng.choice([8, 32, 64, 12.5]))))
+    ang = rng.uniform(0, 2 * np.pi)
+    rad = rng.uniform(1.8, 4.0)
+    pos = (float(rad * np.sin(ang)), float(rng.uniform(0.3, 2.5)), float(rad * np.cos(ang)))
+    fovy = float(rng.uniform(40, 80))
+    near, far = float(rng.uniform(0.05, 0.5)), float(rng.uniform(6, 15))
+    spec['camera'] = dict(position=pos, center=rng.uniform(-0.3, 0.3, 3).tolist(), fovy=fovy, near=near, far=far,
+                          backface_culling=bool(rng.random() < 0.7))
+    # the debug frustum contains the camera frustum, so the reference's frustum overlay (core.py:638) draws nothing
+    spec['debug_camera'] = dict(spec['camera'], fovy=fovy + 30, near=near / 2, far=far * 2)
+    spec['light'] = dict(position=rng.uniform(-3, 3, 3).round(2).tolist(),
+                         light_type=str(rng.choice(['POINT_LIGHTNING', 'SPOT_LIGHTNING', 'DIRECTIONAL_LIGHTNING'])),
+                         center=rng.uniform(-0.5, 0.5, 3).round(2).tolist(), ambient_strength=float(rng.uniform(0, 0.3)),
+                         linear=float(rng.uniform(0.001, 0.2)), quadratic=float(rng.uniform(0.0005, 0.1)),
+                         specular_strength=float(rng.uniform(0.05, 0.6)), color=rng.uniform(0.5, 1, 3).round(2).tolist())
+    spec['light']['position'][1] = abs(spec['light']['position'][1]) + 1.0
+    combos = [('LH', 'OPENGL'), ('RH', 'OPENGL'), ('LH', 'DIRECTX'), ('RH', 'DIRECTX')]
+    spec['system'], spec['subsystem'] = combos[int(rng.integers(4))]
+    spec['resolution'] = (int(rng.integers(20, 120)), int(rng.integers(20, 160)))
+    spec['skymap'] = rng.uniform(0, 1, 3).round(3).tolist() if rng.random() < 0.5 else None
+    return spec
+
+
+def build_random_scene(spec, api=None, texture_factory=None):
+    """Instantiate `spec` through an API namespace: this package (default) or the booted reference."""
+    api = api or b2r
+    own = api is b2r
+    models = []
+    for m in spec['models']:
+        model = api.Model(m['v'].copy(), m['uv'].copy(), None if m['n'] is None else m['n'].copy(), m['f'].copy(),
+                          clip=m['clip'])
+        mat = model.materials['default']
+        object.__setattr__(mat, 'Ns', m['Ns'])
+        for attr, t in m['tex'].items():
+            if own:
+                setattr(mat, attr, Texture(t['texels'], signed=t['signed'], tangent=t['tangent']))
+            else:
+                object.__setattr__(mat, attr, texture_factory(t))
+        if m['transform'] is not None:
+            tr = m['transform']
+            model = model @ api.scale(tr['scale']) @ api.translation(tuple(tr['translation'])) @ api.rotate_xyz(tuple(tr['rotate']))
+        models.append(model)
+
+    def cam(kw):
+        kw = dict(kw)
+        return api.Camera(tuple(kw.pop('position')), center=np.array(kw.pop('center')), **kw)
+    lk = dict(spec['light'])
+    light = api.Light(tuple(lk.pop('position')), light_type=getattr(api.Lightning, lk.pop('light_type')),
+                      center=tuple(lk.pop('center')), color=tuple(lk.pop('color')), **lk)
+    scene = api.Scene(cam(spec['camera']), light, debug_camera=cam(spec['debug_camera']),
+                      resolution=tuple(spec['resolution']), system=getattr(api.SYSTEM, spec['system']),
+                      subsystem=getattr(api.SUBSYSTEM, spec['subsystem']), skymap=spec['skymap'])
+    if own:
+        scene.verbose = False
+        scene.persist_silhouette = False
+    for model in models:
+        scene.add_model(model)
+    return scene
