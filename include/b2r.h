@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B2R_ABI_VERSION 1
+#define B2R_ABI_VERSION 2
 #define B2R_MAX_POLY 12 /* a quad clipped by 6 planes has at most 10 vertices */
 
 /* Light kinds: obj/lightning.py:4-7 */
@@ -128,6 +128,8 @@ typedef struct b2r_debug_out {
     int32_t* winner;     /* global face index that coloured the pixel, -1 = background */
     uint8_t* face_status;/* n_views * total_faces: B2R_FACE_* of pass 3 (core.py:624-636) */
     int32_t* n_silhouette; /* n_views * n_models: silhouette edges extruded for that view */
+    float* frame_f32;    /* n_views*height*width*3: the float32 frame BEFORE flip and tonemap (core.py:588, buffer rows);
+                            what the frustum overlay of core.py:638 is drawn on (py_numpy_renderer_b200/overlay.py) */
 } b2r_debug_out;
 
 typedef struct b2r_scene b2r_scene;

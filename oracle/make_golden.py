@@ -183,6 +183,18 @@ def fixtures(ref):
                debug_camera=cam_kwargs((0.0, 1.5, 2.9), fovy=90, near=0.05, far=20, backface_culling=True),
                light=LIGHT, skymap=[0.1, 0.2, 0.3],
                models=lambda: [ref.Model(*torus_arrays(96, 48)), floor(ref)])
+    # debug cameras whose frustum does NOT contain the camera frustum: the model is cut by the second clip test
+    # (triangular.py:83-87) and the frustum overlay (core.py:638, frustums.py:46-103) draws its red lines
+    yield dict(name='g10_overlay_top_camera', resolution=(240, 320), system='LH', subsystem='OPENGL', camera=CAM,
+               debug_camera=cam_kwargs((0, 3, 0.01), fovy=80, near=1, far=3, backface_culling=True), light=LIGHT,
+               models=lambda: [diablo(ref, False), floor(ref)])
+    yield dict(name='g11_overlay_inner_frustum', resolution=(200, 260), system='RH', subsystem='DIRECTX',
+               camera=cam_kwargs((2.5, 2.0, 4.0), fovy=50, near=0.5, far=20, backface_culling=True),
+               debug_camera=cam_kwargs((1.0, 2.5, 3.0), fovy=35, near=1.5, far=5.5, backface_culling=True),
+               light=dict(position=[3, 4, 2], light_type='POINT_LIGHTNING', ambient_strength=0.2, linear=0.02,
+                          quadratic=0.002),
+               models=lambda: [ref.Model.load_model(cube_path(5)) @ T.scale(0.5) @ T.rotate_xyz((20, 30, 10)),
+                               floor(ref)])
     yield dict(name='g9_diablo_transformed', resolution=(180, 240), system='LH', subsystem='OPENGL', camera=CAM,
                debug_camera=DCAM, light=dict(LIGHT, position=[-1.5, 2.5, 2.0]),
                models=lambda: [diablo(ref, True, 8) @ T.scale(0.8) @ T.translation((0.1, 0.0, -0.2))

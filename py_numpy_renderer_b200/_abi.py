@@ -13,7 +13,7 @@ from .constants import SYSTEM
 from .lightning import Lightning
 from .materials import Texture
 
-B2R_ABI_VERSION = 1
+B2R_ABI_VERSION = 2
 B2R_F32, B2R_F64 = 0, 1
 B2R_TEX_UNORM, B2R_TEX_SNORM = 0, 1
 B2R_BG_COLOR, B2R_BG_CUBEMAP = 0, 1
@@ -64,7 +64,7 @@ class FrameParams(C.Structure):
 
 class DebugOut(C.Structure):
     _fields_ = [("z", C.c_void_p), ("stencil", C.c_void_p), ("winner", C.c_void_p), ("face_status", C.c_void_p),
-                ("n_silhouette", C.c_void_p)]
+                ("n_silhouette", C.c_void_p), ("frame_f32", C.c_void_p)]
 
 
 def _real(arr, what):

@@ -216,8 +216,10 @@ class DeviceScene:
             if want_debug != 'status':  # full planes
                 info.update(z=np.empty((n, H, W), np.float64), stencil=np.empty((n, H, W), np.int16),
                             winner=np.empty((n, H, W), np.int32))
+            if want_debug == 'overlay':
+                info.update(frame_f32=np.empty((n, H, W, 3), np.float32))
             dbg = DebugOut(*[info[k].ctypes.data if k in info else None
-                             for k in ('z', 'stencil', 'winner', 'face_status', 'n_silhouette')])
+                             for k in ('z', 'stencil', 'winner', 'face_status', 'n_silhouette', 'frame_f32')])
         if on_device:
             target, frames = _dev_ptr(out), out
         else:

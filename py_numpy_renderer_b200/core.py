@@ -359,11 +359,13 @@ class Scene:
         """`Scene.render()` (core.py:587-640): uint8 (*resolution, 3), rows flipped, `** 0.8 * 255` tonemap.
 
         `debug`, if a dict, receives the z / stencil / winner planes and per-face status of this frame."""
-        from . import _native
+        from . import _native, overlay
         dev = self._device_scene()
+        self.camera.scene = self.debug_camera.scene = self
+        lines = overlay.segments(self.camera, self.debug_camera)  # frustum overlay of core.py:638; [] = nothing drawn
+        mode = 'overlay' if lines else (True if debug is not None else ('status' if self.verbose else False))
         frames, info = dev.render([self.camera], [self.debug_camera], self.light, self.resolution, self.system,
-                                  self._background(), persist_silhouette=self.persist_silhouette,
-                                  want_debug=True if debug is not None else ('status' if self.verbose else False))
+                                  self._background(), persist_silhouette=self.persist_silhouette, want_debug=mode)
         if isinstance(self.skybox, CubeMap):
             # fill_frame_from_skybox zeroes the translation row of the *cached* camera.lookat in place
             # (cube_map.py:94-96, Appendix B-3); keep the side effect for callers that look at it afterwards.
@@ -371,9 +373,14 @@ class Scene:
         if self.verbose:
             for line in _native.status_report(self.models, info['face_status'][0]):
                 print(line)
+        frame = frames[0]
+        if lines:  # rare path: the debug frustum pokes into the view -- replay the reference's line pass on the host
+            canvas = overlay.apply(info['frame_f32'][0], info['z'][0], self.camera, self.debug_camera,
+                                   1 if self.system == SYSTEM.RH else -1, lines)
+            frame = overlay.tonemap(canvas)
         if debug is not None:
             debug.update({k: v[0] for k, v in info.items()})
-        return frames[0]
+        return frame
 
     def render_batch(self, cameras, debug_cameras=None, debug=None, out=None, band=None):
         """Extension: one frame per camera in `cameras` with this scene's models / light /

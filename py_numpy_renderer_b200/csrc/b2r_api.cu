@@ -126,6 +126,7 @@ struct b2r_scene {
     DevBuf<int> winner;
     DevBuf<short> stencil;
     DevBuf<double> zplane;
+    DevBuf<float> frame_f32;
     DevBuf<uint8_t> status;
     DevBuf<uint8_t> rgb[2];  // device staging of host-bound frames, alternating so that copies of call t overlap call t+1
     int tri_cap = 0, quad_cap = 0;
@@ -417,7 +418,7 @@ int b2r_scene_destroy(b2r_scene* sc) {
     sc->sil_state.release(); sc->facing.release(); sc->sil.release(); sc->counters.release(); sc->views.release();
     sc->tris.release(); sc->quads.release(); sc->tile_counts.release(); sc->tile_offs.release(); sc->tri_list.release();
     sc->quad_list.release(); sc->overflow.release(); sc->winner.release(); sc->stencil.release(); sc->zplane.release();
-    sc->status.release(); sc->rgb[0].release(); sc->rgb[1].release();
+    sc->status.release(); sc->frame_f32.release(); sc->rgb[0].release(); sc->rgb[1].release();
     delete sc;
     return 0;
 }
@@ -525,6 +526,7 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
     if (with_sky && sc->sky_size == 0) return fail("cubemap background requested but the scene has no skybox");
     const bool want_status = dbg && dbg->face_status;
     const bool want_z = dbg && dbg->z;
+    const bool want_f32 = dbg && dbg->frame_f32;
 
     FrameDev Fr;
     std::memset(&Fr, 0, sizeof(Fr));
@@ -619,6 +621,7 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
         CK(sc->winner.reserve((size_t)VB * npx));
         CK(sc->stencil.reserve((size_t)VB * npx));
         if (want_z) CK(sc->zplane.reserve((size_t)VB * npx));
+        if (want_f32) CK(sc->frame_f32.reserve((size_t)VB * npx * 3));
         if (want_status) CK(sc->status.reserve((size_t)VB * F + 8));
         if (host_out) CK(sc->rgb[rslot].reserve((size_t)n_views * npx * 3));  // one region per view: copies never race
 
@@ -672,7 +675,8 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
                 ++g.launches;
                 stage_mark("raster");
                 k_shade<<<dim3((W + 31) / 32, (rows + B2R_SHADE_THREADS / 32 - 1) / (B2R_SHADE_THREADS / 32), sv),
-                          B2R_SHADE_THREADS, 0, st>>>(S, dviews, Fr, sc->tris.p, sc->winner.p, sc->stencil.p, rgb_dev, v0);
+                          B2R_SHADE_THREADS, 0, st>>>(S, dviews, Fr, sc->tris.p, sc->winner.p, sc->stencil.p, rgb_dev, v0,
+                                                      want_f32 ? sc->frame_f32.p : nullptr);
                 ++g.launches;
                 stage_mark("shade");
                 cudaEvent_t done = g.aux_done[n_sub % 16];
@@ -701,6 +705,7 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
             CK(cudaMemcpyAsync(flags + 2 * first, sc->overflow.p, sizeof(int) * 2 * nv, cudaMemcpyDeviceToHost, g.stream));
             if (dbg) {  // debug planes: same stream, so the next chunk cannot overwrite the scratch planes early
                 if (dbg->z) CK(cudaMemcpyAsync(dbg->z + (size_t)first * npx, sc->zplane.p, sizeof(double) * nv * npx, kind, g.stream));
+                if (dbg->frame_f32) CK(cudaMemcpyAsync(dbg->frame_f32 + (size_t)first * npx * 3, sc->frame_f32.p, sizeof(float) * nv * npx * 3, kind, g.stream));
                 if (dbg->stencil) CK(cudaMemcpyAsync(dbg->stencil + (size_t)first * npx, sc->stencil.p, sizeof(short) * nv * npx, kind, g.stream));
                 if (dbg->winner) CK(cudaMemcpyAsync(dbg->winner + (size_t)first * npx, sc->winner.p, sizeof(int) * nv * npx, kind, g.stream));
                 if (dbg->face_status) CK(cudaMemcpyAsync(dbg->face_status + (size_t)first * F, sc->status.p, (size_t)nv * F, kind, g.stream));

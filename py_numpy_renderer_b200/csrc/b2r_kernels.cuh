@@ -1142,7 +1142,8 @@ __device__ __forceinline__ bool skybox_pixel(const SceneDev& S, const ViewDev& V
 #endif
 __global__ void __launch_bounds__(B2R_SHADE_THREADS, B2R_SHADE_MINB)
 k_shade(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec* __restrict__ tris,
-        const int* __restrict__ winner, const short* __restrict__ stencil, uint8_t* __restrict__ out_rgb, int view0) {
+        const int* __restrict__ winner, const short* __restrict__ stencil, uint8_t* __restrict__ out_rgb, int view0,
+        float* __restrict__ out_f32) {
     const int view = blockIdx.z + view0;
     const ViewDev& V = views[view];
     const int lane = threadIdx.x & 31;
@@ -1160,6 +1161,10 @@ k_shade(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec
         } else {
             c[0] = Fr.background[0]; c[1] = Fr.background[1]; c[2] = Fr.background[2];
         }
+    }
+    if (out_f32 && px < Fr.W) {  // debug plane: the float frame of core.py:588, buffer row order
+        float* o = out_f32 + (((size_t)view * Fr.H + py) * Fr.W + px) * 3;
+        o[0] = c[0]; o[1] = c[1]; o[2] = c[2];
     }
     // (frame ** 0.8 * 255).astype(uint8) in float32
     unsigned packed = 0;

@@ -89,3 +89,17 @@ def compare_planes(got, exp, label=""):
     rep['rgb_max'] = int(d.max())
     rep['pixels'] = int(d.size)
     return rep
+
+
+def oracle_frame(oracle, scene):
+    """Oracle render of `scene` (one view) + the host-side frustum overlay of core.py:638 when it draws anything --
+    i.e. what `Scene.render()` of the reference returns, as dict(rgb, z, stencil, winner, face_status, n_silhouette)."""
+    from py_numpy_renderer_b200 import overlay, SYSTEM
+    got = oracle.render_scene(scene, extra=True)
+    scene.camera.scene = scene.debug_camera.scene = scene
+    lines = overlay.segments(scene.camera, scene.debug_camera)
+    if lines:
+        frame = overlay.apply(got['frame_f32'], got['z'], scene.camera, scene.debug_camera,
+                              1 if scene.system == SYSTEM.RH else -1, lines)
+        got['rgb'] = overlay.tonemap(frame)
+    return got

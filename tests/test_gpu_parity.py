@@ -48,7 +48,7 @@ def test_fixture_vs_reference_and_oracle(name, oracle):
     scene, exp, meta = gu.load(name)
     got = gpu_render(scene)
     assert_parity(got, exp)                                   # vs the unmodified Python reference
-    want = {k: v[0] for k, v in oracle_render(oracle, scene).items()}
+    want = gu.oracle_frame(oracle, scene)                     # oracle (+ host overlay pass where it applies)
     assert_parity(got, want)                                  # vs the oracle
     assert np.array_equal(got['face_status'], want['face_status'])
     assert list(got['n_silhouette']) == meta['n_silhouette']

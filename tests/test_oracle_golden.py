@@ -11,7 +11,7 @@ NAMES = gu.fixture_names()
 
 
 def test_fixtures_present():
-    assert len(NAMES) >= 11
+    assert len(NAMES) >= 13
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -28,7 +28,7 @@ def test_host_matrices_equal_reference(name):
 @pytest.mark.parametrize("name", NAMES)
 def test_oracle_matches_reference(name, oracle):
     scene, exp, meta = gu.load(name)
-    got = oracle.render_scene(scene, extra=True)
+    got = gu.oracle_frame(oracle, scene)   # + the host-side frustum overlay when the debug frustum is visible
     rep = gu.compare_planes(got, exp)
     assert rep['z_mismatch'] == 0, rep          # float64 z-buffer, bit exact
     assert rep['stencil_mismatch'] == 0, rep    # shadow-volume counts, exact
