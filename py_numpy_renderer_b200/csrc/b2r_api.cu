@@ -563,7 +563,6 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
     const long long ticket = ++g.ticket;
     const int tslot = (int)(ticket & 3), rslot = (int)(ticket & 1);
     int* const flags = g.pinned_flags + (size_t)tslot * 2 * MAX_FLAG_VIEWS;
-    const bool pipelined = host_out && !dbg && n_views > 1;
     if (n_views > MAX_FLAG_VIEWS) return fail("too many views in one call (max 4096)");
     if (sc->tri_cap == 0) sc->tri_cap = std::max(1 << 16, 4 * F + 8 * n_tiles);
     if (sc->quad_cap == 0) sc->quad_cap = std::max(1 << 20, 32 * E);

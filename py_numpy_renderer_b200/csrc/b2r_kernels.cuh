@@ -402,6 +402,10 @@ struct BinDev {
 };
 
 // One warp per primitive slot: lanes stride over the tiles of the primitive's box.
+// Triangles: one THREAD per face; a box touching at most BIN_SMALL tiles is binned by its own thread, bigger ones
+// (screen-filling triangles) are handed to the whole warp through a ballot queue, lanes striding over the tiles.
+// Shadow quads: one WARP per quad (long slivers crossing many tiles, each with the exact per-tile classification).
+constexpr int BIN_SMALL = 4;
 template <bool FILL>
 __global__ void k_bin(FrameDev Fr, const TriRec* __restrict__ tris, const QuadRec* __restrict__ quads,
                       const int* __restrict__ sil_count, int quad_stride, BinDev B) {
@@ -411,45 +415,72 @@ __global__ void k_bin(FrameDev Fr, const TriRec* __restrict__ tris, const QuadRe
     const int n_quads = *sil_count;
     const int band_y0 = Fr.row_begin, band_y1 = Fr.row_end;
     if (FILL && (B.overflow[view * 2] | B.overflow[view * 2 + 1])) return;
-    const int total_warps = (gridDim.x * blockDim.x) >> 5;
-    for (int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; slot < Fr.n_faces + n_quads; slot += total_warps) {
-        int bx0, bx1, by0, by1;
-        const QuadRec* Q = nullptr;
-        int prim;
+    const int stride = gridDim.x * blockDim.x;
+    int* const tri_count = B.tri_count + (size_t)view * n_tiles;
+    int* const quad_count = B.quad_count + (size_t)view * n_tiles;
+    const int* const tri_off = B.tri_off + (size_t)view * (n_tiles + 1);
+    const int* const quad_off = B.quad_off + (size_t)view * (n_tiles + 1);
+    int* const tri_list = B.tri_list + (size_t)view * B.tri_cap;
+    int* const quad_list = B.quad_list + (size_t)view * B.quad_cap;
+    for (int base = blockIdx.x * blockDim.x + threadIdx.x - lane; base < Fr.n_faces; base += stride) {
+        const int slot = base + lane;
+        int bx0 = 0, bx1 = 0, by0 = 0, by1 = 0;
+        bool valid = false;
         if (slot < Fr.n_faces) {
             const TriRec& r = tris[(size_t)view * Fr.n_faces + slot];
-            if (!(r.flags & TR_VALID)) continue;
-            bx0 = r.bx0; bx1 = r.bx1; by0 = r.by0; by1 = r.by1;
-            prim = slot;
-        } else {
-            prim = slot - Fr.n_faces;
-            Q = quads + (size_t)view * quad_stride + prim;
-            if (Q->n == 0) continue;
-            bx0 = Q->bx0; bx1 = Q->bx1; by0 = Q->by0; by1 = Q->by1;
+            if (r.flags & TR_VALID) { valid = true; bx0 = r.bx0; bx1 = r.bx1; by0 = r.by0; by1 = r.by1; }
         }
         by0 = max(by0, band_y0); by1 = min(by1, band_y1);
+        valid = valid && by0 < by1 && bx0 < bx1;
+        int tx0 = 0, ty0 = 0, tw = 1, nt = 0;
+        if (valid) {
+            tx0 = bx0 / TILE_W; ty0 = by0 / TILE_H;
+            tw = (bx1 - 1) / TILE_W - tx0 + 1;
+            nt = tw * ((by1 - 1) / TILE_H - ty0 + 1);
+        }
+        const bool small = valid && nt <= BIN_SMALL;
+        if (small) {
+            for (int i = 0; i < nt; ++i) {
+                const int t = (ty0 + i / tw - Fr.tile_row0) * Fr.tiles_x + tx0 + i % tw;
+                if (FILL) tri_list[tri_off[t] + atomicAdd(tri_count + t, 1)] = slot;
+                else atomicAdd(tri_count + t, 1);
+            }
+        }
+        unsigned queue = __ballot_sync(0xffffffffu, valid && !small);
+        while (queue) {
+            const int src = __ffs(queue) - 1;
+            queue &= queue - 1;
+            const int s_tx0 = __shfl_sync(0xffffffffu, tx0, src), s_ty0 = __shfl_sync(0xffffffffu, ty0, src);
+            const int s_tw = __shfl_sync(0xffffffffu, tw, src), s_nt = __shfl_sync(0xffffffffu, nt, src);
+            for (int i = lane; i < s_nt; i += 32) {
+                const int t = (s_ty0 + i / s_tw - Fr.tile_row0) * Fr.tiles_x + s_tx0 + i % s_tw;
+                if (FILL) tri_list[tri_off[t] + atomicAdd(tri_count + t, 1)] = base + src;
+                else atomicAdd(tri_count + t, 1);
+            }
+        }
+    }
+    const int total_warps = stride >> 5;
+    for (int prim = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; prim < n_quads; prim += total_warps) {
+        const QuadRec* Q = quads + (size_t)view * quad_stride + prim;
+        if (Q->n == 0) continue;
+        const int bx0 = Q->bx0, bx1 = Q->bx1, by0 = max((int)Q->by0, band_y0), by1 = min((int)Q->by1, band_y1);
         if (by0 >= by1 || bx0 >= bx1) continue;
-        const int tx0 = bx0 / TILE_W, tx1 = (bx1 - 1) / TILE_W, ty0 = by0 / TILE_H, ty1 = (by1 - 1) / TILE_H;
-        const int tw = tx1 - tx0 + 1, nt = tw * (ty1 - ty0 + 1);
-        int* count = (Q ? B.quad_count : B.tri_count) + (size_t)view * n_tiles;
-        const int* off = (Q ? B.quad_off : B.tri_off) + (size_t)view * (n_tiles + 1);
-        int* list = Q ? B.quad_list + (size_t)view * B.quad_cap : B.tri_list + (size_t)view * B.tri_cap;
+        const int tx0 = bx0 / TILE_W, ty0 = by0 / TILE_H;
+        const int tw = (bx1 - 1) / TILE_W - tx0 + 1, nt = tw * ((by1 - 1) / TILE_H - ty0 + 1);
         for (int i = lane; i < nt; i += 32) {
             const int ty = ty0 + i / tw, tx = tx0 + i % tw;
+            const int x0 = max(bx0, tx * TILE_W), x1 = min(bx1, (tx + 1) * TILE_W) - 1;
+            const int y0 = max(by0, ty * TILE_H), y1 = min(by1, (ty + 1) * TILE_H) - 1;
+            const int cls = quad_tile_class(*Q, x0, x1, y0, y1);
+            if (cls == 0) continue;
             int entry = prim;
-            if (Q) {
-                const int x0 = max(bx0, tx * TILE_W), x1 = min(bx1, (tx + 1) * TILE_W) - 1;
-                const int y0 = max(by0, ty * TILE_H), y1 = min(by1, (ty + 1) * TILE_H) - 1;
-                const int cls = quad_tile_class(*Q, x0, x1, y0, y1);
-                if (cls == 0) continue;
-                // "full" only counts when the rectangle is the whole tile (clipped to the screen and the band)
-                if (FILL && cls == 2 && x0 == tx * TILE_W && x1 == min(Fr.W, (tx + 1) * TILE_W) - 1 &&
-                    y0 == max(band_y0, ty * TILE_H) && y1 == min(min(Fr.H, band_y1), (ty + 1) * TILE_H) - 1)
-                    entry |= QUAD_FULL_BIT;
-            }
+            // "full" only counts when the rectangle is the whole tile (clipped to the screen and the band)
+            if (FILL && cls == 2 && x0 == tx * TILE_W && x1 == min(Fr.W, (tx + 1) * TILE_W) - 1 &&
+                y0 == max(band_y0, ty * TILE_H) && y1 == min(min(Fr.H, band_y1), (ty + 1) * TILE_H) - 1)
+                entry |= QUAD_FULL_BIT;
             const int t = (ty - Fr.tile_row0) * Fr.tiles_x + tx;
-            if (FILL) list[off[t] + atomicAdd(count + t, 1)] = entry;
-            else atomicAdd(count + t, 1);
+            if (FILL) quad_list[quad_off[t] + atomicAdd(quad_count + t, 1)] = entry;
+            else atomicAdd(quad_count + t, 1);
         }
     }
 }
