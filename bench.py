@@ -36,6 +36,7 @@ import numpy as np  # noqa: E402
 METRIC = "frames_per_s_1080p_shadow_volumes"
 UNIT = "frames/s"
 HBM_FALLBACK_GBS = 6650.0
+ORBIT_RADIUS = 3.0
 
 
 def parse_args():
@@ -47,7 +48,9 @@ def parse_args():
     ap.add_argument("--views", type=int, default=16, help="frames per step per GPU")
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--width", type=int, default=1920)
-    ap.add_argument("--workload", default="synthetic", choices=["synthetic", "diablo"])
+    ap.add_argument("--workload", default="synthetic", choices=["synthetic", "diablo", "torus1m"],
+                    help="synthetic = BASELINE config 3 stand-in (headline); diablo = the real assets if staged; "
+                         "torus1m = BASELINE config 5 (1M-triangle displaced torus, camera orbit)")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU sample (default: by core count)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -61,6 +64,15 @@ def build_scene(args):
         if assets is None:
             raise SystemExit("--workload diablo needs the reference assets (baseline/_ref/assets)")
         return scenes.kat2(assets, res), "diablo3_pose(5022 tris, diffuse+tangent nm 1024^2) + floor(600^2), point light, shadow volumes"
+    if args.workload == "torus1m":
+        import py_numpy_renderer_b200 as b2r
+        v, uv, n, f = scenes.torus_arrays(1000, 500)
+        cam, dcam = scenes.std_cameras()
+        sc = b2r.Scene(cam, scenes.std_light(), debug_camera=dcam, resolution=res, system=b2r.SYSTEM.LH,
+                       subsystem=b2r.SUBSYSTEM.OPENGL)
+        sc.verbose = False
+        sc.add_model(b2r.Model(v, uv, n, f))
+        return sc, "synthetic 1M-triangle displaced torus (nu=1000, nv=500), camera orbit radius 2.9, shadow volumes"
     return scenes.c3_synthetic(res), ("synthetic diablo3-class figure (5000 tris, diffuse+tangent normal map 1024^2) "
                                       "+ floor (2 tris, 600^2 diffuse), point light, shadow volumes")
 
@@ -70,8 +82,8 @@ def step_cameras(step, rank, world, views):
     camera frustum."""
     import scenes
     start = 2 * np.pi * ((step * world + rank) * 0.6180339887498949 % 1.0)
-    return (scenes.orbit_cameras(views, start=start),
-            scenes.orbit_cameras(views, start=start, fovy=90, near=0.05, far=20))
+    return (scenes.orbit_cameras(views, radius=ORBIT_RADIUS, start=start),
+            scenes.orbit_cameras(views, radius=ORBIT_RADIUS, start=start, fovy=90, near=0.05, far=20))
 
 
 def algorithmic_bytes(scene, n_shaded):
@@ -200,6 +212,9 @@ def main():
     device = torch.device("cuda", local)
 
     scene, workload = build_scene(args)
+    if args.workload == "torus1m":
+        global ORBIT_RADIUS
+        ORBIT_RADIUS = 2.9
     H, W = scene.resolution
     B, K, Wm = args.views, args.steps, args.warmup
     dev = scene._device_scene()

@@ -203,3 +203,26 @@ def test_c5_one_million_triangles_one_frame(oracle):
     assert_parity(got, want)
     assert np.array_equal(got['face_status'], want['face_status'])
     assert list(got['n_silhouette']) == list(want['n_silhouette']) and got['n_silhouette'][0] > 10000
+
+
+@pytest.mark.parametrize("projection", ["PERSPECTIVE", "ORTHOGRAPHIC"])
+def test_c4_skybox_4k(projection, oracle):
+    """BASELINE config 4 at its full frame size: 2160x3840 with a cubemap skybox (procedural 256^2 faces), perspective
+    and orthographic cameras.  At 4K the integer dot products of the skybox barycentrics exceed 2^24, so the float32
+    rounding of `np.float32(int64)` (transformation.py:19-23 via cube_map.py:88) is exercised for real."""
+    faces = np.stack([scenes.procedural_texture(256, 50 + k) for k in range(6)])
+    v, uv, n, f = scenes.torus_arrays(60, 30, R=0.6, r0=0.25)
+    kw = dict(fovy=60, near=0.1, far=10, backface_culling=True)
+    dkw = dict(fovy=90, near=0.05, far=20, backface_culling=True)
+    if projection == "ORTHOGRAPHIC":
+        kw['projection_type'] = dkw['projection_type'] = b2r.PROJECTION_TYPE.ORTHOGRAPHIC
+    cam = b2r.Camera((0.3, 0.5, 1.5), center=np.array((0, 0, -2)), **kw)
+    dcam = b2r.Camera((0.3, 0.5, 1.5), center=np.array((0, 0, -2)), **dkw)
+    scene = b2r.Scene(cam, scenes.std_light(), debug_camera=dcam, resolution=(2160, 3840), system=b2r.SYSTEM.LH,
+                      subsystem=b2r.SUBSYSTEM.OPENGL, skymap=gu.SkyFromTexels(faces))
+    scene.verbose = False
+    scene.add_model(b2r.Model(v, uv, n, f) @ b2r.translation((0, 0, -2.)))
+    got = gpu_render(scene)
+    want = gu.oracle_frame(oracle, scene)
+    assert_parity(got, want)
+    assert len(np.unique(got['rgb'].reshape(-1, 3), axis=0)) > 1000     # the skybox really is sampled
