@@ -129,8 +129,7 @@ struct b2r_scene {
     DevBuf<float> frame_f32;
     DevBuf<uint8_t> status;
     DevBuf<uint8_t> rgb[2];  // device staging of host-bound frames, alternating so that copies of call t overlap call t+1
-    int tri_cap = 0, quad_cap = 0;
-    int views_cap = 0;
+    int tri_cap = 0, quad_cap = 0;  // per-view capacity of the tile lists (grown after an overflow)
 
     SceneDev dev() const {
         SceneDev S;

@@ -1,25 +1,28 @@
 // b2r_kernels.cuh -- the sm_100a kernels of the frame pipeline (one translation unit with b2r_api.cu).
 //
 // Stage map (reference call sites in parentheses):
-//   k_facing        per face        light-facing flag                      (triangular.py:294-295)
-//   k_silhouette    per edge        parity of facing incident faces, extrusion to a world quad
+//   k_facing        per face         light-facing flag, arithmetic in the vertex dtype      (triangular.py:294-295)
+//   k_silhouette    per edge         replay of the set toggles in face order, extrusion to a world quad
 //                                                                          (triangular.py:296-302, core.py:610-621)
-//   k_tri_setup     per face x view vertex transform, cull, bbox, f32 bary constants, N==1 flags
+//   k_tri_setup     per face x view  vertex transform, cull, box, f32 barycentric constants, N==1 flags
 //                                                                          (triangular.py:36-78)
-//   k_quad_setup    per quad x view Sutherland-Hodgman clip, projection, plane, bbox
+//   k_quad_setup    per quad x view  Sutherland-Hodgman clip, projection, plane, box
 //                                                                          (plane_intersection.py:59-86, triangular.py:319-340)
-//   k_bin<FILL>     per primitive   tile lists (count / fill), exact conservative tile test for quads
-//   k_scan          per view        exclusive scan of tile counts
-//   k_raster        per tile        z (64-bit keyed smem atomics) -> stencil spans -> winner id
+//   k_bin<FILL>     per primitive    tile lists (count / fill): thread per face, warp per quad with the exact
+//                                    corner classification of every (quad, tile) pair
+//   k_scan          per view         exclusive scan of the tile counts
+//   k_raster        per 32x32 tile   (1) depth: staged triangle lists, dense (triangle,pixel) dealing, 64-bit keyed
+//                                    smem atomics  (2) stencil: depth-range classification, exact row spans, dense
+//                                    pixel dealing  (3) winner: verified last-improver, full pass only on ties
 //                                                                          (triangular.py:78-118, 341-368)
-//   k_shade         per pixel       Phong + textures + tangent normal maps + skybox + tonemap
+//   k_shade         per pixel        Phong + textures + tangent normal maps + skybox + tonemap, warp-packed stores
 //                                                                          (triangular.py:135-171, core.py:138-228,640; cube_map.py:63-101)
 #pragma once
 #include "b2r_device.cuh"
 
 namespace b2r {
 
-__constant__ float c_lut[2][256];
+__constant__ float c_lut[2][256];  // [B2R_TEX_UNORM | B2R_TEX_SNORM][u8] -> the reference's float32 texel
 
 // optional work counters (build with -DB2R_STATS; read with b2r_debug_stats) -- never in the production library
 __device__ unsigned long long g_stats[16];
@@ -27,7 +30,7 @@ __device__ unsigned long long g_stats[16];
 #define B2R_STAT(i, n) atomicAdd(&g_stats[i], (unsigned long long)(n))
 #else
 #define B2R_STAT(i, n) ((void)0)
-#endif  // [B2R_TEX_UNORM|B2R_TEX_SNORM][u8] -> the reference's float32 texel
+#endif
 
 struct SceneDev {
     const double4* pos;      // (Vtot) world positions, exact promotion of the model's storage
