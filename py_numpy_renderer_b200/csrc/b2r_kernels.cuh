@@ -746,48 +746,70 @@ k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRe
     if (!skip_bg || any_cov) {
         const int* quad_list = B.quad_list + (size_t)view * B.quad_cap;
         const QuadRec* vquads = quads + (size_t)view * quad_stride;
-        // quads are handed out one at a time (their cost differs by orders of magnitude): a warp that finishes a
-        // cheap one grabs the next instead of idling at the barrier
+        // (quad, tile) pairs are handed out dynamically, eight at a time (their cost differs by orders of magnitude: a
+        // warp that finishes cheap ones grabs more instead of idling at the barrier).  The eight pairs are classified
+        // together -- lane -> pair lane/4, rectangle corner lane%4 -- so a rejected pair costs a few instructions;
+        // the survivors are then processed one after the other by the whole warp.
         for (;;) {
-            int t = 0;
-            if (lane == 0) t = q_beg + atomicAdd(&sm.next_quad, 1);
-            t = __shfl_sync(0xffffffffu, t, 0);
-            if (t >= q_end) break;
-            const int entry = quad_list[t];
+            int t0 = 0;
+            if (lane == 0) t0 = q_beg + atomicAdd(&sm.next_quad, 8);
+            t0 = __shfl_sync(0xffffffffu, t0, 0);
+            if (t0 >= q_end) break;
+            const int tg = t0 + (lane >> 2);
+            int g_entry = 0, g_state = 0;  // 0 skip, 1 process, 2 process and every covered pixel passes the z test
+            double g_z = 0.0;
+            int g_code = 3;                // sign class of the linearisation denominator at this corner, 3 = irregular
+            if (tg < q_end) {
+                g_entry = quad_list[tg];
+                const QuadRec& G = vquads[g_entry & (QUAD_FULL_BIT - 1)];
+                const int gx0 = max((int)G.bx0, X0), gx1 = min((int)G.bx1, X1) - 1;
+                const int gy0 = max((int)G.by0, Yb0), gy1 = min((int)G.by1, Y1) - 1;
+                if (gx0 <= gx1 && gy0 <= gy1) {
+                    g_state = 1;
+                    if (skip_bg) {  // depth of the quad plane at one corner of the rectangle, as the reference rounds it
+                        const int cx = (lane & 1) ? gx1 : gx0, cy = (lane & 2) ? gy1 : gy0;
+                        const double z = -(G.nx * (double)cx + G.ny * (double)cy + G.D) / G.nz;
+                        const double den = V.zl_sum - z * V.zl_diff;
+                        g_z = V.zl_num / den;
+                        g_code = (g_z == g_z) ? (den > 0 ? 1 : (den < 0 ? 2 : 3)) : 3;
+                    }
+                }
+            }
+            if (skip_bg) {  // reduce over the four corners of each pair (lanes 4g .. 4g+3)
+                unsigned long long kmin = zkey(g_z), kmax = kmin;
+#pragma unroll
+                for (int o = 1; o <= 2; o <<= 1) {
+                    const int other = __shfl_xor_sync(0xffffffffu, g_code, o);
+                    g_code = (g_code == other) ? g_code : 3;
+                    kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+                    kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+                }
+                if (g_state && g_code != 3) {  // no pole inside: the corner depths bound the depth over the rectangle
+                    if (rh ? (kmin > kb_max) : (kmax < kb_min)) g_state = 0;         // fails everywhere it matters
+                    else if (rh ? (kmax <= kb_min) : (kmin >= kb_max)) g_state = 2;  // passes on every covered pixel
+                }
+            }
+            if ((lane & 3) == 0 && tg < q_end) { B2R_STAT(0, 1); if (g_state == 0) B2R_STAT(1, 1); if (g_state == 2) B2R_STAT(6, 1); }
+            unsigned todo = __ballot_sync(0xffffffffu, (lane & 3) == 0 && g_state != 0);
+            while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int entry = __shfl_sync(0xffffffffu, g_entry, src);
+            const bool all_pass = __shfl_sync(0xffffffffu, g_state, src) == 2;
             const bool full = (entry & QUAD_FULL_BIT) != 0;  // every pixel of the tile is inside the quad
             const QuadRec& R = vquads[entry & (QUAD_FULL_BIT - 1)];
             const int rx0 = max((int)R.bx0, X0), rx1 = min((int)R.bx1, X1) - 1;
             const int ry0 = max((int)R.by0, Yb0), ry1 = min((int)R.by1, Y1) - 1;
-            if (rx0 > rx1 || ry0 > ry1) continue;
-            if (lane == 0) B2R_STAT(0, 1);
+            if (all_pass && full) {  // one count for every covered pixel of the tile: no per-pixel work at all
+                uniform += R.front ? 1 : -1;
+                if (lane == 0) B2R_STAT(4, 1);
+                continue;
+            }
             auto quad_depth = [&](int px, int py, double& den) {
                 const double z = -(R.nx * (double)px + R.ny * (double)py + R.D) / R.nz;
                 den = V.zl_sum - z * V.zl_diff;
                 return V.zl_num / den;
             };
-            bool all_pass = false;  // the quad is in front of every covered pixel of the tile: no depth needed per pixel
-            if (skip_bg) {  // depth-range classification against the covered pixels of the tile
-                double den;
-                const double zc = quad_depth((lane & 1) ? rx1 : rx0, (lane & 2) ? ry1 : ry0, den);
-                const int sgn = den > 0 ? 1 : (den < 0 ? 2 : 0);
-                const bool regular = __all_sync(0xffffffffu, sgn != 0 && sgn == __shfl_sync(0xffffffffu, sgn, 0) && zc == zc);
-                if (regular) {
-                    unsigned long long kmin = zkey(zc), kmax = kmin;
-#pragma unroll
-                    for (int o = 1; o <= 2; o <<= 1) {
-                        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
-                        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
-                    }
-                    if (rh ? (kmin > kb_max) : (kmax < kb_min)) { if (lane == 0) B2R_STAT(1, 1); continue; }  // fails everywhere it matters
-                    all_pass = rh ? (kmax <= kb_min) : (kmin >= kb_max);
-                    if (all_pass && lane == 0) B2R_STAT(6, 1);
-                    if (all_pass && full) {  // one count for every covered pixel of the tile: no per-pixel work at all
-                        uniform += R.front ? 1 : -1;
-                        if (lane == 0) B2R_STAT(4, 1);
-                        continue;
-                    }
-                }
-            }
             // exact span of row py = Y0 + lane: every edge function is monotone in px, so each edge cuts the
             // candidate interval from one side; the cut is located by bisection on the exact predicate
             const int py = Y0 + lane;
@@ -869,6 +891,7 @@ k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRe
                 const int row_lo = __shfl_sync(0xffffffffu, lo, r);
                 if (k < total) do_pixel(row_lo + (k - (row_incl - row_len)), Y0 + r);
             }
+            }  // survivors of this batch
         }
     }
     if (skip_bg) {  // fold the tile-uniform increments into the per-pixel counts
