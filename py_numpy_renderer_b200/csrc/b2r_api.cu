@@ -104,6 +104,7 @@ struct b2r_scene {
     DevBuf<double2> uv;
     DevBuf<double> nrm;
     DevBuf<FaceStatic> faces;
+    DevBuf<ShadeStatic> shade;
     DevBuf<MaterialDev> mats;
     DevBuf<TextureDev> tex;
     std::vector<uchar4*> tex_data;
@@ -133,7 +134,7 @@ struct b2r_scene {
 
     SceneDev dev() const {
         SceneDev S;
-        S.pos = pos.p; S.uv = uv.p; S.nrm = nrm.p; S.faces = faces.p; S.mats = mats.p; S.tex = tex.p; S.sky = sky.p;
+        S.pos = pos.p; S.uv = uv.p; S.nrm = nrm.p; S.faces = faces.p; S.shade = shade.p; S.mats = mats.p; S.tex = tex.p; S.sky = sky.p;
         S.edge_v = edge_v.p; S.edge_ptr = edge_ptr.p; S.edge_inc = edge_inc.p;
         S.n_faces = n_faces; S.n_edges = n_edges;
         return S;
@@ -369,7 +370,22 @@ int b2r_scene_create(const b2r_model_desc* models, int32_t n_models, const b2r_t
         if (e_ != cudaSuccess) { std::string m_ = cudaGetErrorString(e_); b2r_scene_destroy(sc); return fail("upload " #buf ": " + m_); } \
         sc->static_bytes += (vec).size() * sizeof((vec)[0]);                                                  \
     } while (0)
-    UP(pos, pos); UP(uv, uv); UP(nrm, nrm); UP(faces, faces); UP(mats, mats);
+    // per-face shading records: the three index levels resolved once
+    std::vector<ShadeStatic> shade(nf);
+    for (size_t f = 0; f < nf; ++f) {
+        const FaceStatic& F = faces[f];
+        ShadeStatic& R = shade[f];
+        std::memset(&R, 0, sizeof(R));
+        for (int c = 0; c < 3; ++c) {
+            const double4 p = pos[F.v[c]];
+            R.wp[c][0] = p.x; R.wp[c][1] = p.y; R.wp[c][2] = p.z;
+            if (F.flags & FS_HAS_UV) { R.uu[c] = uv[F.t[c]].x; R.vv[c] = uv[F.t[c]].y; }
+            if (F.flags & FS_HAS_NORMALS) for (int k = 0; k < 3; ++k) R.vn[c][k] = nrm[(size_t)F.n[c] * 3 + k];
+        }
+        R.material = F.material;
+        R.flags = F.flags;
+    }
+    UP(pos, pos); UP(uv, uv); UP(nrm, nrm); UP(faces, faces); UP(shade, shade); UP(mats, mats);
     UP(edge_v, edge_v); UP(edge_ptr, edge_ptr); UP(edge_inc, edge_inc); UP(edge_model, edge_model);
     // textures: uint8 RGB -> RGBX so that one texel is one aligned 32-bit load
     std::vector<TextureDev> tex(std::max(1, n_textures));
@@ -411,7 +427,7 @@ int b2r_scene_destroy(b2r_scene* sc) {
     if (g.ready) { cudaStreamSynchronize(g.stream); cudaStreamSynchronize(g.copy_stream); }
     if (g.pending_scene == sc) { g.pending_scene = nullptr; g.pending_views = 0; }
     for (int i = 0; i < 4; ++i) if (g.ticket_scene[i] == sc) { g.ticket_scene[i] = nullptr; g.ticket_views[i] = 0; }
-    sc->pos.release(); sc->uv.release(); sc->nrm.release(); sc->faces.release(); sc->mats.release(); sc->tex.release();
+    sc->pos.release(); sc->uv.release(); sc->nrm.release(); sc->faces.release(); sc->shade.release(); sc->mats.release(); sc->tex.release();
     for (uchar4* d : sc->tex_data) cudaFree(d);
     sc->sky.release(); sc->edge_v.release(); sc->edge_ptr.release(); sc->edge_inc.release(); sc->edge_model.release();
     sc->sil_state.release(); sc->facing.release(); sc->sil.release(); sc->counters.release(); sc->views.release();

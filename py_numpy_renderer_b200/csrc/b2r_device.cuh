@@ -33,6 +33,16 @@ struct FaceStatic {  // 48 B, indices are GLOBAL (scene-level concatenated array
     int model;
 };
 
+// Everything the shader needs about a face in ONE record (scene lifetime), so that a pixel goes winner -> record
+// instead of winner -> indices -> positions / uv / normals (one dependent gather level less).
+struct ShadeStatic {  // 208 B
+    double wp[3][3];      // world xyz of the three corners
+    double uu[3], vv[3];  // u and v of the three corners
+    double vn[3][3];      // vertex normals
+    int material;
+    int flags;            // FS_*
+};
+
 struct MaterialDev {
     double Kd[3];
     double Ks255[3];  // Ks * 255 (core.py:152)

@@ -37,6 +37,7 @@ struct SceneDev {
     const double2* uv;       // (Ttot) u, v
     const double* nrm;       // (Ntot,3)
     const FaceStatic* faces; // (F)
+    const ShadeStatic* shade; // (F) gathered per-face shading inputs
     const MaterialDev* mats;
     const TextureDev* tex;
     const uchar4* sky;       // (6,S,S) RGBX
@@ -999,7 +1000,7 @@ __device__ __forceinline__ float clip01(double v) { return (float)(v < 0.05 ? 0.
 // general_shading for one pixel (triangular.py:135-171)
 __device__ void shade_face_pixel(const SceneDev& S, const ViewDev& V, const LightDev& L, const TriRec& r, int face,
                                  int px, int py, bool lit, float out[3]) {
-    const FaceStatic fs = S.faces[face];
+    const ShadeStatic& fs = S.shade[face];
     const MaterialDev& M = S.mats[fs.material];
     float bu, bv, bw;
     tri_bary(r, px, py, bu, bv, bw);
@@ -1010,11 +1011,8 @@ __device__ void shade_face_pixel(const SceneDev& S, const ViewDev& V, const Ligh
         const double inv_w = 1.0 / gemv3(b0, b1, b2, r.d[0], r.d[1], r.d[2]);
         P[0] = b0 * r.d[0] * inv_w; P[1] = b1 * r.d[1] * inv_w; P[2] = b2 * r.d[2] * inv_w;
     }
-    double uu[3] = {0, 0, 0}, vv[3] = {0, 0, 0};
-    if (fs.flags & FS_HAS_UV) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) { const double2 t = S.uv[fs.t[c]]; uu[c] = t.x; vv[c] = t.y; }
-    }
+    const double* uu = fs.uu;
+    const double* vv = fs.vv;
     double albedo[3];
     if (M.map_Kd >= 0) {
         float t[3];
@@ -1023,9 +1021,7 @@ __device__ void shade_face_pixel(const SceneDev& S, const ViewDev& V, const Ligh
     } else {
         albedo[0] = M.Kd[0]; albedo[1] = M.Kd[1]; albedo[2] = M.Kd[2];
     }
-    double wp[3][3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) { const double4 p = S.pos[fs.v[c]]; wp[c][0] = p.x; wp[c][1] = p.y; wp[c][2] = p.z; }
+    const double (*wp)[3] = fs.wp;
     double frag[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) frag[k] = seq3(P[0], P[1], P[2], wp[0][k], wp[1][k], wp[2][k]);
@@ -1038,13 +1034,7 @@ __device__ void shade_face_pixel(const SceneDev& S, const ViewDev& V, const Ligh
         return;
     }
     // Face.get_normals (core.py:175-189)
-    double vn[3][3];
-    if (fs.flags & FS_HAS_NORMALS) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-#pragma unroll
-            for (int k = 0; k < 3; ++k) vn[c][k] = S.nrm[(size_t)fs.n[c] * 3 + k];
-    }
+    const double (*vn)[3] = fs.vn;
     double N[3];
     if (M.norm >= 0) {
         const TextureDev& T = S.tex[M.norm];
