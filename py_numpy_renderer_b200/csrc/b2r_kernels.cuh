@@ -539,6 +539,34 @@ struct RasterOut {
     uint8_t* status;    // optional (views, F)
 };
 
+// Can any pixel of the rectangle [x0,x1] x [y0,y1] (inclusive) pass the float32 coverage test of `tri_bary`?
+// The computed barycentrics are, up to float32 rounding, affine functions of the pixel: b_i = t_i(p) + eps_i with
+//   t_v = (d11*D20 - d01*D21)*inv,  t_w = (d00*D21 - d01*D20)*inv,  t_u = 1 - t_v - t_w   (real arithmetic on the
+// float32 constants of the record, D2k = (p-a).v_k) and |eps| bounded by the operation-by-operation error analysis
+// below (4 roundings at 2^-24 each, generously doubled).  An affine function attains its extremes over a rectangle
+// at the corners, so if some t_i stays below -E_i at all four corners, b_i < 0 for every pixel: nothing is covered.
+// Only used for big boxes (one screen-filling triangle against the tiles on the far side of its edges).
+constexpr int BIG_BOX_PX = 256;
+__device__ __forceinline__ bool tri_misses_rect(const TriRec& r, int x0, int x1, int y0, int y1) {
+    const double d00 = r.d00, d01 = r.d01, d11 = r.d11, inv = r.inv;
+    const double u32 = 5.9604644775390625e-8;  // 2^-24
+    double tmax[3] = {-1e300, -1e300, -1e300}, amax_v = 0, amax_w = 0, gv = 0, gw = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const double v2x = (double)((c & 1) ? x1 : x0) - r.ax, v2y = (double)((c & 2) ? y1 : y0) - r.ay;
+        const double D20 = v2x * r.v0x + v2y * r.v0y, D21 = v2x * r.v1x + v2y * r.v1y;
+        const double tv = (d11 * D20 - d01 * D21) * inv, tw = (d00 * D21 - d01 * D20) * inv, tu = 1.0 - tv - tw;
+        if (!(tv == tv) || !(tw == tw)) return false;
+        tmax[0] = fmax(tmax[0], tu); tmax[1] = fmax(tmax[1], tv); tmax[2] = fmax(tmax[2], tw);
+        amax_v = fmax(amax_v, fabs(tv)); amax_w = fmax(amax_w, fabs(tw));
+        gv = fmax(gv, (fabs(d11 * D20) + fabs(d01 * D21)) * fabs(inv));
+        gw = fmax(gw, (fabs(d00 * D21) + fabs(d01 * D20)) * fabs(inv));
+    }
+    const double Ev = 8.0 * u32 * (gv + amax_v) + 1e-30, Ew = 8.0 * u32 * (gw + amax_w) + 1e-30;
+    const double Eu = Ev + Ew + 8.0 * u32 * (1.0 + amax_v + amax_w);
+    return tmax[0] < -Eu || tmax[1] < -Ev || tmax[2] < -Ew;
+}
+
 constexpr int RASTER_WARPS = RASTER_THREADS / 32;
 constexpr int STAGE_TRIS = 32;   // triangle records staged in shared memory per round
 constexpr int STAGE_CLIP = 16;   // of which at most this many need the per-pixel clip test (clip coordinates staged too)
@@ -614,6 +642,7 @@ __device__ __forceinline__ void raster_tris(RasterSmem& sm, const SceneDev& S, c
                 const int x0 = max((int)r.bx0, X0), x1 = min((int)r.bx1, X1), y0 = max((int)r.by0, Yb0), y1 = min((int)r.by1, Y1);
                 const int w = max(x1 - x0, 0), h = max(y1 - y0, 0);
                 npx = w * h;
+                if (npx >= BIG_BOX_PX && tri_misses_rect(r, x0, x1 - 1, y0, y1 - 1)) npx = 0;  // provably no covered pixel
                 sm.geo[lane] = (x0 - X0) | ((y0 - Y0) << 8) | (w << 16);
             }
             int incl = npx;
