@@ -1214,7 +1214,7 @@ __device__ __forceinline__ bool skybox_pixel(const SceneDev& S, const ViewDev& V
 #define B2R_SHADE_THREADS 128
 #endif
 #ifndef B2R_SHADE_MINB
-#define B2R_SHADE_MINB 8
+#define B2R_SHADE_MINB 10
 #endif
 __global__ void __launch_bounds__(B2R_SHADE_THREADS, B2R_SHADE_MINB)
 k_shade(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec* __restrict__ tris,
