@@ -226,3 +226,17 @@ def test_c4_skybox_4k(projection, oracle):
     want = gu.oracle_frame(oracle, scene)
     assert_parity(got, want)
     assert len(np.unique(got['rgb'].reshape(-1, 3), axis=0)) > 1000     # the skybox really is sampled
+
+
+@pytest.mark.parametrize("name", ["g2_diablo_floor_point", "g7_cube_mtl_rh_directx"])
+def test_verbose_render_prints_the_reference_log(name, capsys):
+    """core.py:624-636 prints three lines per model (total / rendered / discarded-by-reason); with `verbose` on, the
+    same text comes out, produced from the per-face status bytes of the device."""
+    scene, exp, meta = gu.load(name)
+    scene.verbose = True
+    scene.persist_silhouette = False
+    capsys.readouterr()
+    rgb = scene.render()
+    out = capsys.readouterr().out
+    assert out == meta['log']
+    assert np.array_equal(rgb, exp['rgb'])
