@@ -174,6 +174,19 @@ int64_t b2r_launch_count(void);
 int b2r_last_stage_ms(const char** names, float* ms);
 int b2r_set_stage_timing(int enabled);
 
+/* ---- native OBJ tokenizer (host only) ---------------------------------------------------------
+ * The arrays `Model.load_model` builds (core.py:257-318): vertices float32 (V,4), uv float32 (T,3), normals float32
+ * (N,3), faces int32 (F,3,4) = [v, vt, vn, material slot] fan-triangulated and 0-based (-1 = absent), the `usemtl`
+ * names in slot order ('\n'-separated, slot 0 = "default") and the `mtllib` file names ('\n'-separated).
+ * All buffers are malloc'ed by the library and released by b2r_obj_free. */
+typedef struct b2r_obj {
+    float* vertices; float* uv; float* normals; int32_t* faces;
+    char* slot_names; char* mtllibs;
+    int32_t n_vertices, n_uv, n_normals, n_faces;
+} b2r_obj;
+int b2r_obj_load(const char* path, b2r_obj* out);
+void b2r_obj_free(b2r_obj* obj);
+
 #ifdef __cplusplus
 }
 #endif

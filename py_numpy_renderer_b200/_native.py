@@ -50,7 +50,41 @@ _SYMBOLS = {
     "b2r_launch_count": (C.c_int64, []),
     "b2r_last_stage_ms": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b2r_set_stage_timing": (C.c_int, [C.c_int]),
+    "b2r_obj_load": (C.c_int, [C.c_char_p, C.c_void_p]),
+    "b2r_obj_free": (None, [C.c_void_p]),
 }
+
+
+class ObjArrays(C.Structure):
+    """`b2r_obj` of include/b2r.h: what the native OBJ tokenizer hands back."""
+    _fields_ = [("vertices", C.POINTER(C.c_float)), ("uv", C.POINTER(C.c_float)), ("normals", C.POINTER(C.c_float)),
+                ("faces", C.POINTER(C.c_int32)), ("slot_names", C.c_char_p), ("mtllibs", C.c_char_p),
+                ("n_vertices", C.c_int32), ("n_uv", C.c_int32), ("n_normals", C.c_int32), ("n_faces", C.c_int32)]
+
+
+def load_obj(path):
+    """Native OBJ tokenizer (host code in libb2r.so, no GPU involved) -> (vertices, uv, normals, faces, slot names,
+    mtllib names) with the dtypes / shapes of the reference's loader (core.py:311-315)."""
+    lib = load_library()
+    o = ObjArrays()
+    rc = lib.b2r_obj_load(os.fsencode(path), C.byref(o))
+    if rc != 0:
+        raise FileNotFoundError(path) if rc == 2 else RuntimeError(f"b2r_obj_load({path!r}) failed ({rc})")
+    try:
+        def take(ptr, n, width, dtype):
+            return np.ctypeslib.as_array(ptr, shape=(n, width)).astype(dtype, copy=True) if n else None
+        vertices = take(o.vertices, o.n_vertices, 4, np.float32)
+        uv = take(o.uv, o.n_uv, 3, np.float32)
+        normals = take(o.normals, o.n_normals, 3, np.float32)
+        faces = (np.ctypeslib.as_array(o.faces, shape=(o.n_faces, 3, 4)).astype(np.int32, copy=True)
+                 if o.n_faces else np.zeros((0, 3, 4), np.int32))
+        slots = o.slot_names.decode().split("\n")[:-1]
+        libs = o.mtllibs.decode().split("\n")[:-1]
+    finally:
+        lib.b2r_obj_free(C.byref(o))
+    if vertices is None:
+        vertices = np.zeros((0, 4), np.float32)
+    return vertices, uv, normals, faces, slots, libs
 
 
 def load_library():

@@ -13,7 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.environ.get("B2R_LIB_OUT") or os.path.join(HERE, "libb2r.so")  # B2R_LIB_OUT: tuning variants
 SRC = os.path.join(HERE, "csrc", "b2r_api.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "b2r_kernels.cuh"), os.path.join(HERE, "csrc", "b2r_device.cuh"),
+SRC_HOST = os.path.join(HERE, "csrc", "b2r_obj.cpp")
+DEPS = [SRC, SRC_HOST, os.path.join(HERE, "csrc", "b2r_kernels.cuh"), os.path.join(HERE, "csrc", "b2r_device.cuh"),
         os.path.join(ROOT, "include", "b2r.h")]
 
 
@@ -22,7 +23,7 @@ def nvcc_cmd(extra=()):
     return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
             "-Xcompiler", "-fPIC,-ffp-contract=off,-mfma", "-shared", "-I", os.path.join(ROOT, "include"),
             *(["-DB2R_STATS"] if os.environ.get("B2R_STATS") else []), *os.environ.get("B2R_NVCC_FLAGS", "").split(),
-            *extra, "-o", LIB, SRC]
+            *extra, "-o", LIB, SRC, SRC_HOST]
 
 
 def build(force=False, verbose=False):

@@ -79,9 +79,24 @@ class Model:
 
     # -- reference API -----------------------------------------------------------------------------------------
     @classmethod
-    def load_model(cls, name, shadowing=True):
+    def load_model(cls, name, shadowing=True, native=None):
         """Wavefront OBJ (+MTL) loader producing the arrays of core.py:257-318: vertices f32 (V,4) with w=1,
-        uv f32 (T,3), normals f32 (N,3), faces int32 (F,3,4) = [v, vt, vn, material slot], 0-based, -1 = absent."""
+        uv f32 (T,3), normals f32 (N,3), faces int32 (F,3,4) = [v, vt, vn, material slot], 0-based, -1 = absent.
+
+        `native`: True = the C++ tokenizer of libb2r.so (~50x faster on million-triangle files,
+        identical arrays), False = the pure-Python parser below, None = native when the library is built."""
+        if native is None:
+            from . import _native
+            native = os.path.exists(_native.LIB_PATH)
+        if native:
+            from . import _native
+            vertices, uv, normals, faces, slot_names, libs = _native.load_obj(name)
+            materials = {'default': Material()}
+            for lib in libs:
+                path = os.path.join(os.path.dirname(name), lib)
+                if os.path.exists(path):
+                    materials |= cls.parse_mtl(path)
+            return Model(vertices, uv, normals, faces, shadowing, materials=materials, material_group=slot_names)
         verts, uvs, norms, faces = [], [], [], []
         slot_names = ['default']
         current = 'default'

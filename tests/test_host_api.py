@@ -168,3 +168,48 @@ def test_fast_look_at_equals_numpy_formulation():
                            m[:, 3] + m[:, 2], m[:, 3] - m[:, 2])):
         planes[i] = p / np.linalg.norm(p)
     assert np.array_equal(T.extract_frustum_planes(m), planes)
+
+
+def _same_model(a, b):
+    assert a.vertices.dtype == b.vertices.dtype and np.array_equal(a.vertices, b.vertices)
+    for x, y in ((a.uv, b.uv), (a.normals, b.normals)):
+        assert (x is None) == (y is None) and (x is None or (x.dtype == y.dtype and np.array_equal(x, y)))
+    assert a._faces.dtype == b._faces.dtype == np.int32 and np.array_equal(a._faces, b._faces)
+    assert a.material_group == b.material_group and sorted(a.materials) == sorted(b.materials)
+
+
+def test_native_obj_tokenizer_equals_python_parser(obj_file, tmp_path):
+    """the C++ tokenizer must hand back exactly the arrays of the Python (= reference) parser."""
+    _same_model(b2r.Model.load_model(obj_file, native=True), b2r.Model.load_model(obj_file, native=False))
+    rng = np.random.default_rng(3)
+    lines = ["# random mesh", "o thing"]
+    nv = 60
+    for _ in range(nv):
+        lines.append("v " + " ".join(f"{x:.7g}" for x in rng.standard_normal(3) * rng.choice([1e-3, 1, 1e3])))
+    for _ in range(40):
+        lines.append("vt " + " ".join(f"{x:.6f}" for x in rng.random(rng.choice([2, 3]))) if False else
+                     "vt " + " ".join(f"{x:.6f}" for x in rng.random(2)))
+    for _ in range(30):
+        lines.append("vn " + " ".join(repr(float(x)) for x in rng.standard_normal(3)))
+    for k in range(50):
+        if k % 17 == 0:
+            lines.append(f"usemtl mat{k % 3}")
+        n = int(rng.integers(3, 6))
+        corners = []
+        for _ in range(n):
+            a, b_, c = rng.integers(1, nv + 1), rng.integers(1, 41), rng.integers(1, 31)
+            corners.append(rng.choice([f"{a}/{b_}/{c}", f"{a}//{c}", f"{a}/{b_}/{c}"]))
+        lines.append("f " + "  ".join(corners))
+    path = tmp_path / "rand.obj"
+    path.write_text("\n".join(lines) + "\n")
+    _same_model(b2r.Model.load_model(str(path), native=True), b2r.Model.load_model(str(path), native=False))
+    with pytest.raises(FileNotFoundError):
+        b2r.Model.load_model(str(tmp_path / "missing.obj"), native=True)
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/obj/diablo3_pose/diablo3_pose.obj"), reason="asset not present")
+def test_native_obj_tokenizer_on_diablo():
+    p = "/root/reference/obj/diablo3_pose/diablo3_pose.obj"
+    a, b = b2r.Model.load_model(p, native=True), b2r.Model.load_model(p, native=False)
+    _same_model(a, b)
+    assert a._faces.shape == (5022, 3, 4) and a.vertices.shape == (2519, 4)
