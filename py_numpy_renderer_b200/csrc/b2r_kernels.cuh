@@ -889,28 +889,18 @@ k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRe
                 }
             }
             const int delta = front ? 1 : -1;
-            auto do_pixel = [&](int px, int qy) {
-                const int p = (qy - Y0) * TILE_W + (px - X0);
-                const unsigned long long kb = sm.z[p];
-                if (skip_bg && kb == z_init) { B2R_STAT(9, 1); return; }
-                if (all_pass) { atomicAdd(&sm.st[p], delta); return; }
-                double den;
-                const double z = quad_depth(px, qy, den);
-                B2R_STAT(8, 1);
-                if (!(z == z)) return;
-                const unsigned long long kz = zkey(z);
-                if (rh ? (kb >= kz) : (kb <= kz)) { atomicAdd(&sm.st[p], delta); B2R_STAT(10, 1); }
-            };
-            // The spans of the 32 rows are flattened into one dense pixel list and dealt 32 at a time, so every lane
+            // The spans of the 32 rows are flattened into one dense pixel list and dealt to the lanes, so every lane
             // works whatever the shape of the quad: pixel k lies in the row r with start[r] <= k < start[r+1]
-            // (inclusive scan over the lanes, then a 5-step bisection through shuffles).
+            // (inclusive scan over the lanes, then a 5-step bisection through shuffles).  Two pixels per lane and
+            // iteration, written as straight-line code: their depth evaluations (two dependent float64 divisions
+            // each) are independent and overlap in the pipeline.
             const int len = max(hi - lo + 1, 0);
             int incl = len;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
             const int total = __shfl_sync(0xffffffffu, incl, 31);
             if (lane == 0) { B2R_STAT(2, 1); B2R_STAT(3, total); }
-            for (int k = lane; k < ((total + 31) & ~31); k += 32) {
+            auto locate = [&](int k, int& px, int& qy) {  // every lane takes part in the shuffles
                 int r = 0;  // smallest lane with incl[r] > k
 #pragma unroll
                 for (int step = 16; step; step >>= 1) {
@@ -918,8 +908,26 @@ k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRe
                     if (probe <= k) r += step;
                 }
                 const int row_incl = __shfl_sync(0xffffffffu, incl, r), row_len = __shfl_sync(0xffffffffu, len, r);
-                const int row_lo = __shfl_sync(0xffffffffu, lo, r);
-                if (k < total) do_pixel(row_lo + (k - (row_incl - row_len)), Y0 + r);
+                px = __shfl_sync(0xffffffffu, lo, r) + (k - (row_incl - row_len));
+                qy = Y0 + r;
+            };
+            for (int k = lane; k < ((total + 63) & ~63); k += 64) {
+                int pxa, qya, pxb, qyb;
+                locate(k, pxa, qya);
+                locate(k + 32, pxb, qyb);
+                const bool va = k < total, vb = k + 32 < total;
+                const int pa = va ? (qya - Y0) * TILE_W + (pxa - X0) : 0, pb = vb ? (qyb - Y0) * TILE_W + (pxb - X0) : 0;
+                const unsigned long long kba = sm.z[pa], kbb = sm.z[pb];
+                bool hit_a = va && !(skip_bg && kba == z_init), hit_b = vb && !(skip_bg && kbb == z_init);
+                if (!all_pass) {
+                    double dena, denb;
+                    const double za = quad_depth(pxa, qya, dena), zb = quad_depth(pxb, qyb, denb);
+                    const unsigned long long kza = zkey(za), kzb = zkey(zb);
+                    hit_a = hit_a && za == za && (rh ? (kba >= kza) : (kba <= kza));
+                    hit_b = hit_b && zb == zb && (rh ? (kbb >= kzb) : (kbb <= kzb));
+                }
+                if (hit_a) atomicAdd(&sm.st[pa], delta);
+                if (hit_b) atomicAdd(&sm.st[pb], delta);
             }
             }  // survivors of this batch
         }
