@@ -119,7 +119,7 @@ struct b2r_scene {
     // per-render scratch (grown on demand)
     DevBuf<uint8_t> facing;
     DevBuf<SilEdge> sil;
-    DevBuf<int> counters;  // [0] silhouette count, [1..n_models] per-model counts
+    DevBuf<int> counters;  // [0] silhouette count, [1..n_models] per-model counts, [1+n_models] tonemapped background
     DevBuf<ViewDev> views;
     DevBuf<TriRec> tris;
     DevBuf<QuadRec> quads;
@@ -589,8 +589,11 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
     // ---- light-dependent, view-independent: facing flags and silhouette quads ----
     CK(sc->facing.reserve(F + 4));
     CK(sc->sil.reserve(E));
-    CK(sc->counters.reserve(1 + sc->n_models));
-    CK(cudaMemsetAsync(sc->counters.p, 0, sizeof(int) * (1 + sc->n_models), g.stream));
+    CK(sc->counters.reserve(2 + sc->n_models));
+    CK(cudaMemsetAsync(sc->counters.p, 0, sizeof(int) * (2 + sc->n_models), g.stream));
+    const unsigned* bg_packed = reinterpret_cast<const unsigned*>(sc->counters.p + 1 + sc->n_models);
+    k_frame_consts<<<1, 32, 0, g.stream>>>(Fr, reinterpret_cast<unsigned*>(sc->counters.p + 1 + sc->n_models));
+    ++g.launches;
     if (F > 0) {
         k_facing<<<(F + 255) / 256, 256, 0, g.stream>>>(S, Fr.light, sc->facing.p);
         ++g.launches;
@@ -690,7 +693,7 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
                 stage_mark("raster");
                 k_shade<<<dim3((W + 31) / 32, (rows + B2R_SHADE_THREADS / 32 - 1) / (B2R_SHADE_THREADS / 32), sv),
                           B2R_SHADE_THREADS, 0, st>>>(S, dviews, Fr, sc->tris.p, sc->winner.p, sc->stencil.p, rgb_dev, v0,
-                                                      want_f32 ? sc->frame_f32.p : nullptr);
+                                                      want_f32 ? sc->frame_f32.p : nullptr, bg_packed);
                 ++g.launches;
                 stage_mark("shade");
                 cudaEvent_t done = g.aux_done[n_sub % 16];

@@ -1032,6 +1032,23 @@ __device__ __forceinline__ float pow08(float x) {
     return y * fmaf(0.2f, __fdividef(t, y5), 0.8f);
 }
 
+// (c ** 0.8 * 255).astype(uint8) of one pixel, R | G << 8 | B << 16  (core.py:640)
+__device__ __forceinline__ unsigned tonemap_pack(const float c[3]) {
+    unsigned packed = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float v = __fmul_rn(pow08(c[k]), 255.0f);
+        packed |= ((unsigned)(int)v & 0xffu) << (8 * k);
+    }
+    return packed;
+}
+
+// Per-call constants evaluated once on the device with the functions the pixel kernels use: the tonemapped
+// constant background (core.py:588 `np.full(..., background)` through core.py:640).
+__global__ void k_frame_consts(FrameDev Fr, unsigned* __restrict__ bg_packed) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *bg_packed = tonemap_pack(Fr.background);
+}
+
 __device__ __forceinline__ float clip01(double v) { return (float)(v < 0.05 ? 0.05 : (v > 1.0 ? 1.0 : v)); }
 
 // general_shading for one pixel (triangular.py:135-171)
@@ -1227,7 +1244,7 @@ __device__ __forceinline__ bool skybox_pixel(const SceneDev& S, const ViewDev& V
 __global__ void __launch_bounds__(B2R_SHADE_THREADS, B2R_SHADE_MINB)
 k_shade(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec* __restrict__ tris,
         const int* __restrict__ winner, const short* __restrict__ stencil, uint8_t* __restrict__ out_rgb, int view0,
-        float* __restrict__ out_f32) {
+        float* __restrict__ out_f32, const unsigned* __restrict__ bg_packed) {
     const int view = blockIdx.z + view0;
     const ViewDev& V = views[view];
     const int lane = threadIdx.x & 31;
@@ -1235,6 +1252,7 @@ k_shade(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec
     const int py = Fr.row_begin + blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (py >= Fr.row_end) return;  // whole warp
     float c[3] = {0.f, 0.f, 0.f};
+    bool const_bg = false;
     if (px < Fr.W) {
         const size_t g = (size_t)view * Fr.H * Fr.W + (size_t)py * Fr.W + px;
         const int face = winner[g];
@@ -1244,31 +1262,23 @@ k_shade(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec
             skybox_pixel(S, V, Fr.sky_size, px, py, c);
         } else {
             c[0] = Fr.background[0]; c[1] = Fr.background[1]; c[2] = Fr.background[2];
+            const_bg = true;
         }
     }
     if (out_f32 && px < Fr.W) {  // debug plane: the float frame of core.py:588, buffer row order
         float* o = out_f32 + (((size_t)view * Fr.H + py) * Fr.W + px) * 3;
         o[0] = c[0]; o[1] = c[1]; o[2] = c[2];
     }
-    // (frame ** 0.8 * 255).astype(uint8) in float32
-    unsigned packed = 0;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const float v = __fmul_rn(pow08(c[k]), 255.0f);
-        packed |= ((unsigned)(int)v & 0xffu) << (8 * k);
-    }
+    // (frame ** 0.8 * 255).astype(uint8) in float32; the constant background was tonemapped once by k_frame_consts
+    const unsigned packed = const_bg ? __ldg(bg_packed) : tonemap_pack(c);
     uint8_t* row = out_rgb + ((size_t)view * Fr.H + (size_t)(Fr.H - 1 - py)) * Fr.W * 3;
     const int x_base = blockIdx.x * 32;
     if (x_base + 32 <= Fr.W && (((size_t)Fr.W * 3) & 3) == 0) {
-        // lane j < 24 assembles bytes 4j..4j+3 of the warp's 96-byte run
-        unsigned word = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int byte = 4 * lane + b;           // may exceed 95 for lanes >= 24 (ignored)
-            const int src = (byte / 3) & 31, ch = byte % 3;
-            const unsigned v = __shfl_sync(0xffffffffu, packed, src);
-            word |= ((v >> (8 * ch)) & 0xffu) << (8 * b);
-        }
+        // lane j < 24 assembles bytes 4j..4j+3 of the warp's 96-byte run: they belong to the pixels k = 4j/3 and
+        // k+1, whose 24-bit values overlap the word at a shift of 8*(j%3) bits
+        const int k = (4 * lane) / 3, s = 8 * (lane - 3 * (lane / 3));
+        const unsigned a = __shfl_sync(0xffffffffu, packed, k & 31), b = __shfl_sync(0xffffffffu, packed, (k + 1) & 31);
+        const unsigned word = (a >> s) | (b << (24 - s));
         if (lane < 24) reinterpret_cast<unsigned*>(row + (size_t)x_base * 3)[lane] = word;
     } else if (px < Fr.W) {
         row[(size_t)px * 3 + 0] = (uint8_t)(packed & 0xff);

@@ -9,9 +9,9 @@ lib = _native.init(0)
 scene = scenes.c3_synthetic((1080, 1920))
 out = torch.empty((views, 1080, 1920, 3), dtype=torch.uint8, device="cuda:0")
 buf = (ctypes.c_ulonglong * 16)()
-names = ["pairs", "pairs_rejected_tile_range", "short_rows", "long_rows", "long_rows_bg_only", "long_rows_all_fail",
-         "long_rows_all_pass", "long_rows_mixed", "pixel_evals", "pixel_bg_skips", "stencil_updates", "tiles_active",
-         "tri_pixel_tests", "tri_pixel_covered", "quad_list_entries", "tri_list_entries"]
+names = ["quad_tile_pairs", "pairs_rejected_by_depth_range", "pairs_with_pixel_work", "stencil_pixel_items",
+         "pairs_uniform_counter", "pairs_full_no_span_search", "pairs_all_pass", "tiles_full_winner_pass", "-", "-", "-",
+         "tiles", "tri_pixel_tests", "tri_pixel_covered", "quad_list_entries", "tri_list_entries"]
 for it in range(2):
     cams = scenes.orbit_cameras(views, start=0.37 * it)
     dcams = scenes.orbit_cameras(views, start=0.37 * it, fovy=90, near=0.05, far=20)
