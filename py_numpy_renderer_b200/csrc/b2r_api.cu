@@ -40,6 +40,7 @@ struct Globals {
     int dev_chunk = 8;            // views per sub-chunk when frames stay on the device (overlap of raster tails)
     int async_chunk = 8;          // views per sub-chunk of a host-asynchronous call
     int aux_host = 2, aux_dev = 3;  // how many auxiliary streams the sub-chunks rotate over
+    int bin_blocks = 0, bin_share = 64;  // k_bin grid (0 = 2 per SM) and the most warps that share one quad
     // pinned staging ring for the per-view constants: a pageable source would make cudaMemcpyAsync synchronise the
     // stream, i.e. serialise the host with the previous chunk / previous asynchronous call
     struct Staging { ViewDev* host = nullptr; size_t cap = 0; cudaEvent_t done = nullptr; bool used = false; } stage[4];
@@ -176,6 +177,8 @@ int b2r_init(int device) {
     if (const char* dc = std::getenv("B2R_DEV_CHUNK")) g.dev_chunk = std::max(1, std::atoi(dc));
     if (const char* ac = std::getenv("B2R_ASYNC_CHUNK")) g.async_chunk = std::max(1, std::atoi(ac));
     if (const char* a = std::getenv("B2R_AUX_HOST")) g.aux_host = std::min(Globals::N_AUX, std::max(1, std::atoi(a)));
+    if (const char* a = std::getenv("B2R_BIN_BLOCKS")) g.bin_blocks = std::max(1, std::atoi(a));
+    if (const char* a = std::getenv("B2R_BIN_SHARE")) g.bin_share = std::max(1, std::atoi(a));
     if (const char* a = std::getenv("B2R_AUX_DEV")) g.aux_dev = std::min(Globals::N_AUX, std::max(1, std::atoi(a)));
     float lut[2][256];
     for (int i = 0; i < 256; ++i) {  // core.py:96-104: f32(u8/255), f32(u8/255*2-1) with float64 intermediates
@@ -652,6 +655,7 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
             B.tri_off = sc->tile_offs.p; B.quad_off = sc->tile_offs.p + (size_t)VB * (n_tiles + 1);
             B.tri_list = sc->tri_list.p; B.quad_list = sc->quad_list.p;
             B.tri_cap = sc->tri_cap; B.quad_cap = sc->quad_cap; B.overflow = sc->overflow.p;
+            B.share_cap = g.bin_share;
             uint8_t* status = want_status ? sc->status.p : nullptr;
 
             if (F > 0) {
@@ -663,7 +667,7 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
             k_quad_setup<<<dim3(quad_blocks, nv), 64, 0, g.stream>>>(sc->sil.p, sc->counters.p, dviews, Fr, sc->quads.p, E);
             ++g.launches;
             stage_mark("quad_setup");
-            const int bin_blocks = g.sm_count * 8;
+            const int bin_blocks = g.bin_blocks ? g.bin_blocks : g.sm_count * 2;
             k_bin<false><<<dim3(bin_blocks, nv), 256, 0, g.stream>>>(Fr, sc->tris.p, sc->quads.p, sc->counters.p, E, B);
             k_scan<<<dim3(nv, 2), 1024, 0, g.stream>>>(Fr, B);
             k_bin<true><<<dim3(bin_blocks, nv), 256, 0, g.stream>>>(Fr, sc->tris.p, sc->quads.p, sc->counters.p, E, B);

@@ -403,6 +403,7 @@ struct BinDev {
     int* quad_list;   // (views, quad_cap)
     int tri_cap, quad_cap;
     int* overflow;    // (views, 2) required sizes when a list does not fit
+    int share_cap;    // most warps that split the tiles of one quad
 };
 
 // One warp per primitive slot: lanes stride over the tiles of the primitive's box.
@@ -410,6 +411,7 @@ struct BinDev {
 // (screen-filling triangles) are handed to the whole warp through a ballot queue, lanes striding over the tiles.
 // Shadow quads: one WARP per quad (long slivers crossing many tiles, each with the exact per-tile classification).
 constexpr int BIN_SMALL = 4;
+constexpr int BIN_SUPER = 4;  // quads: tiles are classified in blocks of BIN_SUPER x BIN_SUPER first
 template <bool FILL>
 __global__ void k_bin(FrameDev Fr, const TriRec* __restrict__ tris, const QuadRec* __restrict__ quads,
                       const int* __restrict__ sil_count, int quad_stride, BinDev B) {
@@ -463,28 +465,63 @@ __global__ void k_bin(FrameDev Fr, const TriRec* __restrict__ tris, const QuadRe
             }
         }
     }
+    // A quad whose box spans the screen has thousands of tiles to classify, each a chain of dependent float64
+    // operations: the grid's warps are split evenly over the quads (`share` warps each, striding over the tiles of
+    // the box) so the launch is not as long as the biggest quad.
     const int total_warps = stride >> 5;
-    for (int prim = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; prim < n_quads; prim += total_warps) {
+    const int share = max(1, min(B.share_cap, total_warps / max(n_quads, 1)));
+    const int warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int part = warp_id % share;
+    for (int prim = warp_id / share; prim < n_quads; prim += total_warps / share) {
         const QuadRec* Q = quads + (size_t)view * quad_stride + prim;
         if (Q->n == 0) continue;
         const int bx0 = Q->bx0, bx1 = Q->bx1, by0 = max((int)Q->by0, band_y0), by1 = min((int)Q->by1, band_y1);
         if (by0 >= by1 || bx0 >= bx1) continue;
-        const int tx0 = bx0 / TILE_W, ty0 = by0 / TILE_H;
-        const int tw = (bx1 - 1) / TILE_W - tx0 + 1, nt = tw * ((by1 - 1) / TILE_H - ty0 + 1);
-        for (int i = lane; i < nt; i += 32) {
-            const int ty = ty0 + i / tw, tx = tx0 + i % tw;
-            const int x0 = max(bx0, tx * TILE_W), x1 = min(bx1, (tx + 1) * TILE_W) - 1;
-            const int y0 = max(by0, ty * TILE_H), y1 = min(by1, (ty + 1) * TILE_H) - 1;
-            const int cls = quad_tile_class(*Q, x0, x1, y0, y1);
-            if (cls == 0) continue;
-            int entry = prim;
-            // "full" only counts when the rectangle is the whole tile (clipped to the screen and the band)
-            if (FILL && cls == 2 && x0 == tx * TILE_W && x1 == min(Fr.W, (tx + 1) * TILE_W) - 1 &&
-                y0 == max(band_y0, ty * TILE_H) && y1 == min(min(Fr.H, band_y1), (ty + 1) * TILE_H) - 1)
-                entry |= QUAD_FULL_BIT;
-            const int t = (ty - Fr.tile_row0) * Fr.tiles_x + tx;
-            if (FILL) quad_list[quad_off[t] + atomicAdd(quad_count + t, 1)] = entry;
-            else atomicAdd(quad_count + t, 1);
+        // Two levels.  The box of a shadow quad (a long diagonal sliver) holds ~20x more tiles than the quad touches,
+        // so blocks of BIN_SUPER x BIN_SUPER tiles are classified first with the same exact corner test: a rejected
+        // block rejects its tiles, a block that is inside everywhere makes its tiles "full" without further tests
+        // (both follow from the monotonicity argument above, the block's rectangle containing the tiles').
+        const int tx0 = bx0 / TILE_W, ty0 = by0 / TILE_H, tx1 = (bx1 - 1) / TILE_W + 1, ty1 = (by1 - 1) / TILE_H + 1;
+        const int sx0 = tx0 / BIN_SUPER, sy0 = ty0 / BIN_SUPER;
+        const int sw = (tx1 - 1) / BIN_SUPER - sx0 + 1, ns = sw * ((ty1 - 1) / BIN_SUPER - sy0 + 1);
+        for (int sb = part * 32; sb < ns; sb += 32 * share) {
+            const int si = sb + lane;
+            int s_cls = 0, stx = 0, sty = 0;
+            if (si < ns) {
+                sty = sy0 + si / sw; stx = sx0 + si % sw;
+                const int ta = max(tx0, stx * BIN_SUPER), tb = min(tx1, (stx + 1) * BIN_SUPER);
+                const int tc = max(ty0, sty * BIN_SUPER), td = min(ty1, (sty + 1) * BIN_SUPER);
+                s_cls = quad_tile_class(*Q, max(bx0, ta * TILE_W), min(bx1, tb * TILE_W) - 1,
+                                        max(by0, tc * TILE_H), min(by1, td * TILE_H) - 1);
+            }
+            unsigned alive = __ballot_sync(0xffffffffu, s_cls != 0);
+            constexpr int PER = BIN_SUPER * BIN_SUPER, GROUPS = 32 / PER;  // surviving blocks expanded per iteration
+            while (alive) {   // warp-uniform: the next GROUPS surviving blocks, PER lanes each
+                int src = -1;
+#pragma unroll
+                for (int gidx = 0; gidx < GROUPS; ++gidx) {
+                    const int bit = alive ? __ffs(alive) - 1 : -1;
+                    alive &= alive - 1;
+                    if (lane / PER == gidx) src = bit;
+                }
+                const int sub = lane % PER;
+                const int b_cls = __shfl_sync(0xffffffffu, s_cls, src & 31);
+                const int tx = __shfl_sync(0xffffffffu, stx, src & 31) * BIN_SUPER + sub % BIN_SUPER;
+                const int ty = __shfl_sync(0xffffffffu, sty, src & 31) * BIN_SUPER + sub / BIN_SUPER;
+                if (src < 0 || tx < tx0 || tx >= tx1 || ty < ty0 || ty >= ty1) continue;
+                const int x0 = max(bx0, tx * TILE_W), x1 = min(bx1, (tx + 1) * TILE_W) - 1;
+                const int y0 = max(by0, ty * TILE_H), y1 = min(by1, (ty + 1) * TILE_H) - 1;
+                const int cls = b_cls == 2 ? 2 : quad_tile_class(*Q, x0, x1, y0, y1);
+                if (cls == 0) continue;
+                int entry = prim;
+                // "full" only counts when the rectangle is the whole tile (clipped to the screen and the band)
+                if (FILL && cls == 2 && x0 == tx * TILE_W && x1 == min(Fr.W, (tx + 1) * TILE_W) - 1 &&
+                    y0 == max(band_y0, ty * TILE_H) && y1 == min(min(Fr.H, band_y1), (ty + 1) * TILE_H) - 1)
+                    entry |= QUAD_FULL_BIT;
+                const int t = (ty - Fr.tile_row0) * Fr.tiles_x + tx;
+                if (FILL) quad_list[quad_off[t] + atomicAdd(quad_count + t, 1)] = entry;
+                else atomicAdd(quad_count + t, 1);
+            }
         }
     }
 }
@@ -1026,7 +1063,9 @@ __device__ __forceinline__ double pow_ns(double x, const MaterialDev& M) {
 // cost of powf: a hardware log2/exp2 estimate polished by one Newton step on y^5 = x^4.
 __device__ __forceinline__ float pow08(float x) {
     if (!(x > 0.0f)) return 0.0f;
-    const float y = exp2f(0.8f * __log2f(x));
+    float lg, y;  // bare MUFU.LG2 / MUFU.EX2: frame values are 0 or normal floats in (2^-126, 1]
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(0.8f * lg));
     const float x2 = x * x, t = x2 * x2;
     const float y2 = y * y, y5 = y2 * y2 * y;
     return y * fmaf(0.2f, __fdividef(t, y5), 0.8f);
