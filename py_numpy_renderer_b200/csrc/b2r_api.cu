@@ -36,6 +36,8 @@ struct Globals {
     cudaStream_t aux[N_AUX] = {};     // (a few very heavy tiles) is filled by the next sub-chunk's work
     cudaEvent_t aux_done[16] = {};
     cudaEvent_t setup_done = nullptr;
+    cudaStream_t fork_stream = nullptr;  // k_tri_setup runs here, next to the facing -> silhouette -> quad chain
+    cudaEvent_t tri_done = nullptr;
     int host_chunk = 2;           // views per sub-chunk when frames go to host memory (copy/compute overlap)
     int dev_chunk = 8;            // views per sub-chunk when frames stay on the device (overlap of raster tails)
     int async_chunk = 8;          // views per sub-chunk of a host-asynchronous call
@@ -171,6 +173,8 @@ int b2r_init(int device) {
     CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&g.chunk_done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&g.setup_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&g.tri_done, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&g.fork_stream, cudaStreamNonBlocking));
     for (int i = 0; i < Globals::N_AUX; ++i) CK(cudaStreamCreateWithFlags(&g.aux[i], cudaStreamNonBlocking));
     for (int i = 0; i < 16; ++i) CK(cudaEventCreateWithFlags(&g.aux_done[i], cudaEventDisableTiming));
     if (const char* hc = std::getenv("B2R_HOST_CHUNK")) g.host_chunk = std::max(1, std::atoi(hc));
@@ -199,6 +203,8 @@ int b2r_shutdown(void) {
     cudaStreamDestroy(g.stream);
     cudaStreamDestroy(g.copy_stream);
     cudaEventDestroy(g.chunk_done);
+    cudaEventDestroy(g.tri_done);
+    cudaStreamDestroy(g.fork_stream);
     for (int i = 0; i <= B2R_MAX_STAGES; ++i) cudaEventDestroy(g.stage_ev[i]);
     cudaFreeHost(g.pinned_flags);
     g = Globals();
@@ -589,6 +595,28 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
     g.n_stage = 0;
     if (g.timing) cudaEventRecord(g.stage_ev[0], g.stream);
 
+    // ---- per-view constants: evaluated once, staged in pinned memory, one asynchronous upload for the whole call ----
+    {
+        Globals::Staging& st = g.stage[g.stage_next++ % 4];
+        if (!st.done) CK(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
+        if (st.used) CK(cudaEventSynchronize(st.done));  // the upload that last used this slot has left host memory
+        if (st.cap < (size_t)n_views) {
+            if (st.host) cudaFreeHost(st.host);
+            st.host = nullptr; st.cap = 0;
+            CK(cudaMallocHost(&st.host, sizeof(ViewDev) * (size_t)std::max(n_views, 64)));
+            st.cap = (size_t)std::max(n_views, 64);
+        }
+        for (int i = 0; i < n_views; ++i) make_view(views[i], with_sky, st.host[i]);
+        CK(sc->views.reserve(n_views));
+        CK(cudaMemcpyAsync(sc->views.p, st.host, sizeof(ViewDev) * (size_t)n_views, cudaMemcpyHostToDevice, g.stream));
+        CK(cudaEventRecord(st.done, g.stream));
+        st.used = true;
+    }
+    // Triangle set-up only needs the view constants: it forks to its own stream here and joins before binning, so it
+    // overlaps the facing -> silhouette -> quad set-up chain (all of them small, latency-bound launches).
+    const bool fork = !g.timing && !dbg && F > 0;
+    if (fork) CK(cudaEventRecord(g.chunk_done, g.stream));
+
     // ---- light-dependent, view-independent: facing flags and silhouette quads ----
     CK(sc->facing.reserve(F + 4));
     CK(sc->sil.reserve(E));
@@ -608,24 +636,6 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
         }
     }
     stage_mark("silhouette");
-
-    // ---- per-view constants: evaluated once, staged in pinned memory, one asynchronous upload for the whole call ----
-    {
-        Globals::Staging& st = g.stage[g.stage_next++ % 4];
-        if (!st.done) CK(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
-        if (st.used) CK(cudaEventSynchronize(st.done));  // the upload that last used this slot has left host memory
-        if (st.cap < (size_t)n_views) {
-            if (st.host) cudaFreeHost(st.host);
-            st.host = nullptr; st.cap = 0;
-            CK(cudaMallocHost(&st.host, sizeof(ViewDev) * (size_t)std::max(n_views, 64)));
-            st.cap = (size_t)std::max(n_views, 64);
-        }
-        for (int i = 0; i < n_views; ++i) make_view(views[i], with_sky, st.host[i]);
-        CK(sc->views.reserve(n_views));
-        CK(cudaMemcpyAsync(sc->views.p, st.host, sizeof(ViewDev) * (size_t)n_views, cudaMemcpyHostToDevice, g.stream));
-        CK(cudaEventRecord(st.done, g.stream));
-        st.used = true;
-    }
 
     const cudaMemcpyKind kind = !host_out ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
     if (host_out && g.rgb_last_ticket[rslot] >= 0 && g.ticket - g.rgb_last_ticket[rslot] < 4)
@@ -659,14 +669,23 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
             uint8_t* status = want_status ? sc->status.p : nullptr;
 
             if (F > 0) {
-                k_tri_setup<<<dim3((F + 127) / 128, nv), 128, 0, g.stream>>>(S, dviews, Fr, sc->tris.p, status);
+                cudaStream_t ts = g.stream;
+                if (fork) {
+                    // later batches (and retries) overwrite records the previous raster launches were reading
+                    if (first > 0 || attempt > 0) CK(cudaEventRecord(g.chunk_done, g.stream));
+                    CK(cudaStreamWaitEvent(g.fork_stream, g.chunk_done, 0));
+                    ts = g.fork_stream;
+                }
+                k_tri_setup<<<dim3((F + 127) / 128, nv), 128, 0, ts>>>(S, dviews, Fr, sc->tris.p, status);
                 ++g.launches;
+                if (fork) CK(cudaEventRecord(g.tri_done, ts));
             }
             stage_mark("tri_setup");
             const int quad_blocks = std::max(1, std::min((sc->n_edges + 63) / 64, g.sm_count * 4));
             k_quad_setup<<<dim3(quad_blocks, nv), 64, 0, g.stream>>>(sc->sil.p, sc->counters.p, dviews, Fr, sc->quads.p, E);
             ++g.launches;
             stage_mark("quad_setup");
+            if (fork) CK(cudaStreamWaitEvent(g.stream, g.tri_done, 0));
             const int bin_blocks = g.bin_blocks ? g.bin_blocks : g.sm_count * 2;
             k_bin<false><<<dim3(bin_blocks, nv), 256, 0, g.stream>>>(Fr, sc->tris.p, sc->quads.p, sc->counters.p, E, B);
             k_scan<<<dim3(nv, 2), 1024, 0, g.stream>>>(Fr, B);
