@@ -127,6 +127,7 @@ struct b2r_scene {
     DevBuf<TriRec> tris;
     DevBuf<QuadRec> quads;
     DevBuf<int> tile_counts, tile_offs, tri_list, quad_list, overflow;
+    DevBuf<int2> pair_list;  // (quad, tile) pairs between the two binning passes
     DevBuf<int> winner;
     DevBuf<short> stencil;
     DevBuf<double> zplane;
@@ -441,7 +442,7 @@ int b2r_scene_destroy(b2r_scene* sc) {
     sc->sky.release(); sc->edge_v.release(); sc->edge_ptr.release(); sc->edge_inc.release(); sc->edge_model.release();
     sc->sil_state.release(); sc->facing.release(); sc->sil.release(); sc->counters.release(); sc->views.release();
     sc->tris.release(); sc->quads.release(); sc->tile_counts.release(); sc->tile_offs.release(); sc->tri_list.release();
-    sc->quad_list.release(); sc->overflow.release(); sc->winner.release(); sc->stencil.release(); sc->zplane.release();
+    sc->quad_list.release(); sc->pair_list.release(); sc->overflow.release(); sc->winner.release(); sc->stencil.release(); sc->zplane.release();
     sc->status.release(); sc->frame_f32.release(); sc->rgb[0].release(); sc->rgb[1].release();
     delete sc;
     return 0;
@@ -482,7 +483,7 @@ int b2r_scene_get_silhouette(b2r_scene* sc, int32_t* out_pairs, int32_t* out_mod
 static void b2r_scene_grow_lists(b2r_scene* sc, int need_tri, int need_quad) {
     if (!sc) return;
     if (need_tri) { sc->tri_cap = need_tri + need_tri / 4; sc->tri_list.release(); }
-    if (need_quad) { sc->quad_cap = need_quad + need_quad / 4; sc->quad_list.release(); }
+    if (need_quad) { sc->quad_cap = need_quad + need_quad / 4; sc->quad_list.release(); sc->pair_list.release(); }
 }
 extern "C" {
 
@@ -643,10 +644,11 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
     for (int attempt = 0; attempt < 4; ++attempt) {
         CK(sc->tris.reserve((size_t)VB * F));
         CK(sc->quads.reserve((size_t)VB * E));
-        CK(sc->tile_counts.reserve((size_t)VB * n_tiles * 2));
+        CK(sc->tile_counts.reserve((size_t)VB * n_tiles * 2 + (size_t)VB * (2 + BIN_HUGE_CAP)));  // + pair / huge-face counters and lists
         CK(sc->tile_offs.reserve((size_t)VB * (n_tiles + 1) * 2));
         CK(sc->tri_list.reserve((size_t)VB * sc->tri_cap));
         CK(sc->quad_list.reserve((size_t)VB * sc->quad_cap));
+        CK(sc->pair_list.reserve((size_t)VB * sc->quad_cap));
         CK(sc->overflow.reserve((size_t)VB * 2));
         CK(sc->winner.reserve((size_t)VB * npx));
         CK(sc->stencil.reserve((size_t)VB * npx));
@@ -658,7 +660,7 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
         for (int first = 0; first < n_views; first += VB) {
             const int nv = std::min(VB, n_views - first);
             const ViewDev* dviews = sc->views.p + first;
-            CK(cudaMemsetAsync(sc->tile_counts.p, 0, sizeof(int) * (size_t)VB * n_tiles * 2, g.stream));
+            CK(cudaMemsetAsync(sc->tile_counts.p, 0, sizeof(int) * ((size_t)VB * n_tiles * 2 + (size_t)VB * (2 + BIN_HUGE_CAP)), g.stream));
 
             BinDev B;
             B.tri_count = sc->tile_counts.p; B.quad_count = sc->tile_counts.p + (size_t)VB * n_tiles;
@@ -666,6 +668,8 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
             B.tri_list = sc->tri_list.p; B.quad_list = sc->quad_list.p;
             B.tri_cap = sc->tri_cap; B.quad_cap = sc->quad_cap; B.overflow = sc->overflow.p;
             B.share_cap = g.bin_share;
+            B.pair_list = sc->pair_list.p; B.pair_count = sc->tile_counts.p + (size_t)VB * n_tiles * 2;
+            B.huge_count = B.pair_count + VB; B.huge_list = B.huge_count + VB;
             uint8_t* status = want_status ? sc->status.p : nullptr;
 
             if (F > 0) {
@@ -777,7 +781,7 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
         for (int i = 0; i < n_views; ++i) { need_tri = std::max(need_tri, flags[2 * i]); need_quad = std::max(need_quad, flags[2 * i + 1]); }
         if (!need_tri && !need_quad) return 0;
         if (need_tri) { sc->tri_cap = need_tri + need_tri / 4; sc->tri_list.release(); }
-        if (need_quad) { sc->quad_cap = need_quad + need_quad / 4; sc->quad_list.release(); }
+        if (need_quad) { sc->quad_cap = need_quad + need_quad / 4; sc->quad_list.release(); sc->pair_list.release(); }
     }
     return fail("tile list capacity overflow");
 }

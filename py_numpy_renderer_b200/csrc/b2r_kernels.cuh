@@ -404,6 +404,10 @@ struct BinDev {
     int tri_cap, quad_cap;
     int* overflow;    // (views, 2) required sizes when a list does not fit
     int share_cap;    // most warps that split the tiles of one quad
+    int2* pair_list;  // (views, quad_cap) surviving (entry, tile) pairs found by the count pass, replayed by the fill pass
+    int* pair_count;  // (views)
+    int* huge_count;  // (views) faces whose box holds more than BIN_HUGE tiles: the fill pass spreads them over the grid
+    int* huge_list;   // (views, BIN_HUGE_CAP)
 };
 
 // One warp per primitive slot: lanes stride over the tiles of the primitive's box.
@@ -411,6 +415,8 @@ struct BinDev {
 // (screen-filling triangles) are handed to the whole warp through a ballot queue, lanes striding over the tiles.
 // Shadow quads: one WARP per quad (long slivers crossing many tiles, each with the exact per-tile classification).
 constexpr int BIN_SMALL = 4;
+constexpr int BIN_HUGE = 256, BIN_HUGE_CAP = 64;
+constexpr int BIN_PAIR_BUF = 128;  // per-warp shared-memory run of (quad, tile) pairs between two global appends
 constexpr int BIN_SUPER = 4;  // quads: tiles are classified in blocks of BIN_SUPER x BIN_SUPER first
 template <bool FILL>
 __global__ void k_bin(FrameDev Fr, const TriRec* __restrict__ tris, const QuadRec* __restrict__ quads,
@@ -458,6 +464,22 @@ __global__ void k_bin(FrameDev Fr, const TriRec* __restrict__ tris, const QuadRe
             queue &= queue - 1;
             const int s_tx0 = __shfl_sync(0xffffffffu, tx0, src), s_ty0 = __shfl_sync(0xffffffffu, ty0, src);
             const int s_tw = __shfl_sync(0xffffffffu, tw, src), s_nt = __shfl_sync(0xffffffffu, nt, src);
+            if (s_nt > BIN_HUGE) {
+                // A screen-filling triangle: thousands of list inserts, each waiting for its atomic, would make this
+                // one warp the critical path of the fill pass.  The count pass (fire-and-forget atomics) notes the
+                // face; the fill pass spreads the noted faces over the whole grid below.
+                if (!FILL) {
+                    if (lane == 0) {
+                        const int h = atomicAdd(B.huge_count + view, 1);
+                        if (h < BIN_HUGE_CAP) B.huge_list[view * BIN_HUGE_CAP + h] = base + src;
+                    }
+                } else {
+                    const int nh = min(B.huge_count[view], BIN_HUGE_CAP);
+                    const int* hl = B.huge_list + view * BIN_HUGE_CAP;
+                    const bool mine = (lane < nh && hl[lane] == base + src) || (lane + 32 < nh && hl[lane + 32] == base + src);
+                    if (__any_sync(0xffffffffu, mine)) continue;  // noted: handled by the grid-wide loop
+                }
+            }
             for (int i = lane; i < s_nt; i += 32) {
                 const int t = (s_ty0 + i / s_tw - Fr.tile_row0) * Fr.tiles_x + s_tx0 + i % s_tw;
                 if (FILL) tri_list[tri_off[t] + atomicAdd(tri_count + t, 1)] = base + src;
@@ -468,6 +490,45 @@ __global__ void k_bin(FrameDev Fr, const TriRec* __restrict__ tris, const QuadRe
     // A quad whose box spans the screen has thousands of tiles to classify, each a chain of dependent float64
     // operations: the grid's warps are split evenly over the quads (`share` warps each, striding over the tiles of
     // the box) so the launch is not as long as the biggest quad.
+    if (FILL) {
+        const int nh = min(B.huge_count[view], BIN_HUGE_CAP);
+        for (int h = 0; h < nh; ++h) {   // the noted screen-filling faces: one tile per thread of the grid
+            const int face = B.huge_list[view * BIN_HUGE_CAP + h];
+            const TriRec& r = tris[(size_t)view * Fr.n_faces + face];
+            const int bx0 = r.bx0, bx1 = r.bx1, by0 = max((int)r.by0, band_y0), by1 = min((int)r.by1, band_y1);
+            const int tx0 = bx0 / TILE_W, ty0 = by0 / TILE_H, tw = (bx1 - 1) / TILE_W - tx0 + 1;
+            const int nt = tw * ((by1 - 1) / TILE_H - ty0 + 1);
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nt; i += stride) {
+                const int t = (ty0 + i / tw - Fr.tile_row0) * Fr.tiles_x + tx0 + i % tw;
+                tri_list[tri_off[t] + atomicAdd(tri_count + t, 1)] = face;
+            }
+        }
+        // the count pass left the surviving (quad, tile) pairs behind: the fill pass only scatters them
+        const int n_pairs = min(B.pair_count[view], B.quad_cap);
+        const int2* pairs = B.pair_list + (size_t)view * B.quad_cap;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += stride) {
+            const int2 pr = pairs[i];
+            quad_list[quad_off[pr.y] + atomicAdd(quad_count + pr.y, 1)] = pr.x;
+        }
+        return;
+    }
+    // Count pass.  A quad whose box spans the screen has hundreds of tiles to classify, each a chain of dependent
+    // float64 operations: the grid's warps are split evenly over the quads (`share` warps each, striding over the
+    // blocks of the box).  Surviving pairs collect in a per-warp shared-memory run and reach the per-view pair list
+    // with one global atomic per run.
+    __shared__ int2 pair_buf[8][BIN_PAIR_BUF];
+    int2* const my_buf = pair_buf[threadIdx.x >> 5];
+    int2* const pair_list = B.pair_list + (size_t)view * B.quad_cap;
+    int n_buf = 0;  // warp-uniform
+    auto flush = [&]() {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(B.pair_count + view, n_buf);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        __syncwarp();
+        for (int i = lane; i < n_buf; i += 32) if (base + i < B.quad_cap) pair_list[base + i] = my_buf[i];
+        __syncwarp();
+        n_buf = 0;
+    };
     const int total_warps = stride >> 5;
     const int share = max(1, min(B.share_cap, total_warps / max(n_quads, 1)));
     const int warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -477,7 +538,7 @@ __global__ void k_bin(FrameDev Fr, const TriRec* __restrict__ tris, const QuadRe
         if (Q->n == 0) continue;
         const int bx0 = Q->bx0, bx1 = Q->bx1, by0 = max((int)Q->by0, band_y0), by1 = min((int)Q->by1, band_y1);
         if (by0 >= by1 || bx0 >= bx1) continue;
-        // Two levels.  The box of a shadow quad (a long diagonal sliver) holds ~20x more tiles than the quad touches,
+        // Two levels.  The box of a shadow quad (a long diagonal sliver) holds many more tiles than the quad touches,
         // so blocks of BIN_SUPER x BIN_SUPER tiles are classified first with the same exact corner test: a rejected
         // block rejects its tiles, a block that is inside everywhere makes its tiles "full" without further tests
         // (both follow from the monotonicity argument above, the block's rectangle containing the tiles').
@@ -508,22 +569,26 @@ __global__ void k_bin(FrameDev Fr, const TriRec* __restrict__ tris, const QuadRe
                 const int b_cls = __shfl_sync(0xffffffffu, s_cls, src & 31);
                 const int tx = __shfl_sync(0xffffffffu, stx, src & 31) * BIN_SUPER + sub % BIN_SUPER;
                 const int ty = __shfl_sync(0xffffffffu, sty, src & 31) * BIN_SUPER + sub / BIN_SUPER;
-                if (src < 0 || tx < tx0 || tx >= tx1 || ty < ty0 || ty >= ty1) continue;
-                const int x0 = max(bx0, tx * TILE_W), x1 = min(bx1, (tx + 1) * TILE_W) - 1;
-                const int y0 = max(by0, ty * TILE_H), y1 = min(by1, (ty + 1) * TILE_H) - 1;
-                const int cls = b_cls == 2 ? 2 : quad_tile_class(*Q, x0, x1, y0, y1);
-                if (cls == 0) continue;
-                int entry = prim;
-                // "full" only counts when the rectangle is the whole tile (clipped to the screen and the band)
-                if (FILL && cls == 2 && x0 == tx * TILE_W && x1 == min(Fr.W, (tx + 1) * TILE_W) - 1 &&
-                    y0 == max(band_y0, ty * TILE_H) && y1 == min(min(Fr.H, band_y1), (ty + 1) * TILE_H) - 1)
-                    entry |= QUAD_FULL_BIT;
-                const int t = (ty - Fr.tile_row0) * Fr.tiles_x + tx;
-                if (FILL) quad_list[quad_off[t] + atomicAdd(quad_count + t, 1)] = entry;
-                else atomicAdd(quad_count + t, 1);
+                int cls = 0, entry = prim, t = 0;
+                if (src >= 0 && tx >= tx0 && tx < tx1 && ty >= ty0 && ty < ty1) {
+                    const int x0 = max(bx0, tx * TILE_W), x1 = min(bx1, (tx + 1) * TILE_W) - 1;
+                    const int y0 = max(by0, ty * TILE_H), y1 = min(by1, (ty + 1) * TILE_H) - 1;
+                    cls = b_cls == 2 ? 2 : quad_tile_class(*Q, x0, x1, y0, y1);
+                    // "full" only counts when the rectangle is the whole tile (clipped to the screen and the band)
+                    if (cls == 2 && x0 == tx * TILE_W && x1 == min(Fr.W, (tx + 1) * TILE_W) - 1 &&
+                        y0 == max(band_y0, ty * TILE_H) && y1 == min(min(Fr.H, band_y1), (ty + 1) * TILE_H) - 1)
+                        entry |= QUAD_FULL_BIT;
+                    t = (ty - Fr.tile_row0) * Fr.tiles_x + tx;
+                    if (cls) atomicAdd(quad_count + t, 1);
+                }
+                const unsigned keep = __ballot_sync(0xffffffffu, cls != 0);
+                if (cls) my_buf[n_buf + __popc(keep & ((1u << lane) - 1))] = make_int2(entry, t);
+                n_buf += __popc(keep);
+                if (n_buf > BIN_PAIR_BUF - 32) flush();
             }
         }
     }
+    if (n_buf) flush();
 }
 
 // exclusive scan of the tile counts of one (view, kind); resets the counts to 0 so k_bin<true> can reuse them
