@@ -251,7 +251,7 @@ def main():
         for s in range(first, first + count):
             fp, views = packed_steps[s]
             slot = s % 2
-            flush.zero_()                                   # evict L2: 256 MiB > 126 MB (its ~45 us ARE timed)
+            flush.zero_()                                   # evict L2 BETWEEN steps: 256 MiB > 126 MB, timed (~45 us)
             if works[slot] is not None:
                 works[slot].wait()                          # frames_dev[slot] was handed to NCCL two steps ago
                 works[slot] = None
@@ -259,10 +259,10 @@ def main():
             ready.record(cur)
             lib_stream.wait_event(ready)
             dev.render_packed(fp, views, out=frames_dev[slot])          # asynchronous, frames stay in HBM
+            done = torch.cuda.Event()
+            done.record(lib_stream)
+            cur.wait_event(done)                            # the next flush must not start before this render ended
             if world > 1:
-                done = torch.cuda.Event()
-                done.record(lib_stream)
-                cur.wait_event(done)
                 works[slot] = dist.gather(frames_dev[slot], gathered[slot], dst=0, async_op=True)
             if per_step_sync:
                 torch.cuda.synchronize()

@@ -231,11 +231,11 @@ __global__ void k_tri_setup(SceneDev S, const ViewDev* __restrict__ views, Frame
                 // N of `bar_screen[Bi]` decides the evaluation order of the z interpolation: count covered &
                 // unclipped pixels, stopping at 2.
                 if (n_box <= COV_SERIAL_MAX) {
-                    int cnt = 0;
+                    int cnt = 0, px = r.bx0, py = r.by0;
                     for (int i = 0; i < n_box && cnt < 2; ++i) {
-                        const int px = r.bx0 + i / ny, py = r.by0 + i % ny;
                         float bu, bv, bw;
                         cnt += tri_pixel_in(r, cc, px, py, bu, bv, bw) ? 1 : 0;
+                        if (++py == r.by1) { py = r.by0; ++px; }
                     }
                     if (cnt == 1) r.flags |= TR_COV_ONE;
                     if (cnt == 0) { st = B2R_FACE_CLIPPED; r.flags = 0; }
@@ -267,15 +267,20 @@ __global__ void k_tri_setup(SceneDev S, const ViewDev* __restrict__ views, Frame
         // visit the box in a scattered order (i * prime mod n is a permutation): a triangle that covers a few
         // percent of its box yields two hits within the first iterations, the scan stays exhaustive otherwise
         const long long stride = (n_box % 1000003) ? 1000003 : 999983;
+        int j = (int)(((long long)lane * stride) % n_box);          // pixel i = base + lane sits at (i * stride) % n_box:
+        const int step = (int)((32 * stride) % n_box);              // advanced incrementally, no division in the loop
+        const double inv_ny = 1.0 / (double)ny;
         int cnt = 0;
         for (int base = 0; base < n_box && cnt < 2; base += 32) {
-            const int i = base + lane;
             bool in = false;
-            if (i < n_box) {
-                const int j = (int)(((long long)i * stride) % n_box);
+            if (base + lane < n_box) {
+                int q = (int)((double)j * inv_ny), rem = j - q * ny;  // j / ny, j % ny (estimate off by at most one)
+                if (rem >= ny) { ++q; rem -= ny; } else if (rem < 0) { --q; rem += ny; }
                 float bu, bv, bw;
-                in = tri_pixel_in(r, c2, r.bx0 + j / ny, r.by0 + j % ny, bu, bv, bw);
+                in = tri_pixel_in(r, c2, r.bx0 + q, r.by0 + rem, bu, bv, bw);
             }
+            j += step;
+            if (j >= n_box) j -= n_box;
             cnt += __popc(__ballot_sync(0xffffffffu, in));
         }
         if (lane == src) {
