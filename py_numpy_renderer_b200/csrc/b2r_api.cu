@@ -609,7 +609,11 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
         }
         for (int i = 0; i < n_views; ++i) make_view(views[i], with_sky, st.host[i]);
         CK(sc->views.reserve(n_views));
-        CK(cudaMemcpyAsync(sc->views.p, st.host, sizeof(ViewDev) * (size_t)n_views, cudaMemcpyHostToDevice, g.stream));
+        static_assert(sizeof(ViewDev) % 4 == 0, "ViewDev is copied in 32-bit words");
+        const size_t words = sizeof(ViewDev) / 4 * (size_t)n_views;
+        k_copy_words<<<(unsigned)std::min<size_t>((words + 255) / 256, 64), 256, 0, g.stream>>>(
+            reinterpret_cast<unsigned*>(sc->views.p), reinterpret_cast<const unsigned*>(st.host), words);
+        ++g.launches;
         CK(cudaEventRecord(st.done, g.stream));
         st.used = true;
     }
@@ -622,9 +626,9 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
     CK(sc->facing.reserve(F + 4));
     CK(sc->sil.reserve(E));
     CK(sc->counters.reserve(2 + sc->n_models));
-    CK(cudaMemsetAsync(sc->counters.p, 0, sizeof(int) * (2 + sc->n_models), g.stream));
     const unsigned* bg_packed = reinterpret_cast<const unsigned*>(sc->counters.p + 1 + sc->n_models);
-    k_frame_consts<<<1, 32, 0, g.stream>>>(Fr, reinterpret_cast<unsigned*>(sc->counters.p + 1 + sc->n_models));
+    k_frame_consts<<<1, 32, 0, g.stream>>>(Fr, sc->counters.p, 1 + sc->n_models,
+                                           reinterpret_cast<unsigned*>(sc->counters.p + 1 + sc->n_models));
     ++g.launches;
     if (F > 0) {
         k_facing<<<(F + 255) / 256, 256, 0, g.stream>>>(S, Fr.light, sc->facing.p);
@@ -660,7 +664,10 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
         for (int first = 0; first < n_views; first += VB) {
             const int nv = std::min(VB, n_views - first);
             const ViewDev* dviews = sc->views.p + first;
-            CK(cudaMemsetAsync(sc->tile_counts.p, 0, sizeof(int) * ((size_t)VB * n_tiles * 2 + (size_t)VB * (2 + BIN_HUGE_CAP)), g.stream));
+            const size_t count_words = (size_t)VB * n_tiles * 2 + (size_t)VB * (2 + BIN_HUGE_CAP);
+            k_zero_words<<<(unsigned)std::min<size_t>((count_words + 255) / 256, (size_t)g.sm_count * 4), 256, 0, g.stream>>>(
+                reinterpret_cast<unsigned*>(sc->tile_counts.p), count_words);
+            ++g.launches;
 
             BinDev B;
             B.tri_count = sc->tile_counts.p; B.quad_count = sc->tile_counts.p + (size_t)VB * n_tiles;
@@ -692,7 +699,7 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
             if (fork) CK(cudaStreamWaitEvent(g.stream, g.tri_done, 0));
             const int bin_blocks = g.bin_blocks ? g.bin_blocks : g.sm_count * 2;
             k_bin<false><<<dim3(bin_blocks, nv), 256, 0, g.stream>>>(Fr, sc->tris.p, sc->quads.p, sc->counters.p, E, B);
-            k_scan<<<dim3(nv, 2), 1024, 0, g.stream>>>(Fr, B);
+            k_scan<<<dim3(nv, 2), 1024, 0, g.stream>>>(Fr, B, flags + 2 * first);
             k_bin<true><<<dim3(bin_blocks, nv), 256, 0, g.stream>>>(Fr, sc->tris.p, sc->quads.p, sc->counters.p, E, B);
             g.launches += 3;
             stage_mark("bin");
@@ -746,7 +753,6 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
                 ++g.launches;
             }
             CK(cudaGetLastError());
-            CK(cudaMemcpyAsync(flags + 2 * first, sc->overflow.p, sizeof(int) * 2 * nv, cudaMemcpyDeviceToHost, g.stream));
             if (dbg) {  // debug planes: same stream, so the next chunk cannot overwrite the scratch planes early
                 if (dbg->z) CK(cudaMemcpyAsync(dbg->z + (size_t)first * npx, sc->zplane.p, sizeof(double) * nv * npx, kind, g.stream));
                 if (dbg->frame_f32) CK(cudaMemcpyAsync(dbg->frame_f32 + (size_t)first * npx * 3, sc->frame_f32.p, sizeof(float) * nv * npx * 3, kind, g.stream));
