@@ -126,7 +126,7 @@ struct b2r_scene {
     DevBuf<ViewDev> views;
     DevBuf<TriRec> tris;
     DevBuf<QuadRec> quads;
-    DevBuf<int> tile_counts, tile_offs, tri_list, quad_list, overflow;
+    DevBuf<int> tile_counts, tile_offs, tri_list, quad_list, overflow, tile_order;
     DevBuf<int2> pair_list;  // (quad, tile) pairs between the two binning passes
     DevBuf<int> winner;
     DevBuf<short> stencil;
@@ -442,7 +442,7 @@ int b2r_scene_destroy(b2r_scene* sc) {
     sc->sky.release(); sc->edge_v.release(); sc->edge_ptr.release(); sc->edge_inc.release(); sc->edge_model.release();
     sc->sil_state.release(); sc->facing.release(); sc->sil.release(); sc->counters.release(); sc->views.release();
     sc->tris.release(); sc->quads.release(); sc->tile_counts.release(); sc->tile_offs.release(); sc->tri_list.release();
-    sc->quad_list.release(); sc->pair_list.release(); sc->overflow.release(); sc->winner.release(); sc->stencil.release(); sc->zplane.release();
+    sc->quad_list.release(); sc->pair_list.release(); sc->overflow.release(); sc->tile_order.release(); sc->winner.release(); sc->stencil.release(); sc->zplane.release();
     sc->status.release(); sc->frame_f32.release(); sc->rgb[0].release(); sc->rgb[1].release();
     delete sc;
     return 0;
@@ -654,6 +654,7 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
         CK(sc->quad_list.reserve((size_t)VB * sc->quad_cap));
         CK(sc->pair_list.reserve((size_t)VB * sc->quad_cap));
         CK(sc->overflow.reserve((size_t)VB * 2));
+        CK(sc->tile_order.reserve((size_t)VB * n_tiles));
         CK(sc->winner.reserve((size_t)VB * npx));
         CK(sc->stencil.reserve((size_t)VB * npx));
         if (want_z) CK(sc->zplane.reserve((size_t)VB * npx));
@@ -675,6 +676,7 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
             B.tri_list = sc->tri_list.p; B.quad_list = sc->quad_list.p;
             B.tri_cap = sc->tri_cap; B.quad_cap = sc->quad_cap; B.overflow = sc->overflow.p;
             B.share_cap = g.bin_share;
+            B.order = sc->tile_order.p;
             B.pair_list = sc->pair_list.p; B.pair_count = sc->tile_counts.p + (size_t)VB * n_tiles * 2;
             B.huge_count = B.pair_count + VB; B.huge_list = B.huge_count + VB;
             uint8_t* status = want_status ? sc->status.p : nullptr;
@@ -700,8 +702,9 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
             const int bin_blocks = g.bin_blocks ? g.bin_blocks : g.sm_count * 2;
             k_bin<false><<<dim3(bin_blocks, nv), 256, 0, g.stream>>>(Fr, sc->tris.p, sc->quads.p, sc->counters.p, E, B);
             k_scan<<<dim3(nv, 2), 1024, 0, g.stream>>>(Fr, B, flags + 2 * first);
+            k_order<<<nv, 1024, 0, g.stream>>>(Fr, B);
             k_bin<true><<<dim3(bin_blocks, nv), 256, 0, g.stream>>>(Fr, sc->tris.p, sc->quads.p, sc->counters.p, E, B);
-            g.launches += 3;
+            g.launches += 4;
             stage_mark("bin");
             RasterOut O;
             O.winner = sc->winner.p; O.stencil = sc->stencil.p; O.z = want_z ? sc->zplane.p : nullptr; O.status = status;
@@ -721,8 +724,8 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
                 const int sv = std::min(sub, nv - v0);
                 cudaStream_t st = multi ? g.aux[n_sub % (!host_out ? g.aux_dev : g.aux_host)] : g.stream;
                 if (multi) CK(cudaStreamWaitEvent(st, g.setup_done, 0));
-                k_raster<<<dim3(Fr.tiles_x, Fr.tiles_y, sv), RASTER_THREADS, 0, st>>>(S, dviews, Fr, sc->tris.p,
-                                                                                   sc->quads.p, E, B, O, v0);
+                k_raster<<<(unsigned)sv * (unsigned)n_tiles, RASTER_THREADS, 0, st>>>(S, dviews, Fr, sc->tris.p,
+                                                                                   sc->quads.p, E, B, O, v0, sv);
                 ++g.launches;
                 stage_mark("raster");
                 k_shade<<<dim3((W + 31) / 32, (rows + B2R_SHADE_THREADS / 32 - 1) / (B2R_SHADE_THREADS / 32), sv),

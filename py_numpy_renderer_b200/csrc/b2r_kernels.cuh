@@ -413,6 +413,7 @@ struct BinDev {
     int* pair_count;  // (views)
     int* huge_count;  // (views) faces whose box holds more than BIN_HUGE tiles: the fill pass spreads them over the grid
     int* huge_list;   // (views, BIN_HUGE_CAP)
+    int* order;       // (views, n_tiles) tiles sorted by estimated cost class, heaviest first (raster launch order)
 };
 
 // One warp per primitive slot: lanes stride over the tiles of the primitive's box.
@@ -637,6 +638,38 @@ __global__ void k_scan(FrameDev Fr, BinDev B, int* __restrict__ host_flags) {  /
     }
 }
 
+// Launch order of the raster CTAs.  A tile under the figure's shadow volume costs ~100x a floor tile; launched in
+// screen order, the heavy tiles of the last view start when most of the grid has drained and the launch ends with a
+// long, nearly empty tail.  Tiles are therefore bucketed by an estimate of their cost (list lengths) and the raster
+// grid walks the buckets heaviest first, the views of the sub-chunk interleaved.  One CTA per view.
+constexpr int ORDER_CLASSES = 6;
+__device__ __forceinline__ int tile_cost_class(int n_tri, int n_quad) {
+    const int cost = 4 * n_quad + n_tri;
+    return cost >= 1024 ? 0 : cost >= 256 ? 1 : cost >= 64 ? 2 : cost >= 16 ? 3 : cost > 0 ? 4 : 5;
+}
+__global__ void k_order(FrameDev Fr, BinDev B) {
+    const int view = blockIdx.x;
+    const int n_tiles = Fr.tiles_x * Fr.tiles_y;
+    const int* tri_off = B.tri_off + (size_t)view * (n_tiles + 1);
+    const int* quad_off = B.quad_off + (size_t)view * (n_tiles + 1);
+    int* order = B.order + (size_t)view * n_tiles;
+    __shared__ int cnt[ORDER_CLASSES], base[ORDER_CLASSES];
+    if (threadIdx.x < ORDER_CLASSES) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (int t = threadIdx.x; t < n_tiles; t += blockDim.x)
+        atomicAdd(&cnt[tile_cost_class(tri_off[t + 1] - tri_off[t], quad_off[t + 1] - quad_off[t])], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int c = 0; c < ORDER_CLASSES; ++c) { base[c] = run; run += cnt[c]; cnt[c] = 0; }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) {
+        const int c = tile_cost_class(tri_off[t + 1] - tri_off[t], quad_off[t + 1] - quad_off[t]);
+        order[base[c] + atomicAdd(&cnt[c], 1)] = t;
+    }
+}
+
 // =====================================================================================================================
 // tile raster: z -> stencil -> winner, all in shared memory
 // =====================================================================================================================
@@ -810,13 +843,14 @@ __device__ __forceinline__ void raster_tris(RasterSmem& sm, const SceneDev& S, c
 #endif
 __global__ void __launch_bounds__(RASTER_THREADS, B2R_RASTER_MINB)
 k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec* __restrict__ tris,
-         const QuadRec* __restrict__ quads, int quad_stride, BinDev B, RasterOut O, int view0) {
+         const QuadRec* __restrict__ quads, int quad_stride, BinDev B, RasterOut O, int view0, int n_sub) {
     __shared__ RasterSmem sm;
-    const int view = blockIdx.z + view0;  // view0: first view of this sub-chunk within the set-up batch
+    // grid = n_sub views x n_tiles, the views of the sub-chunk interleaved, tiles in k_order's heaviest-first order
+    const int view = (int)(blockIdx.x % (unsigned)n_sub) + view0;  // view0: first view of this sub-chunk within the batch
     const ViewDev& V = views[view];
-    const int tx = blockIdx.x, ty = blockIdx.y + Fr.tile_row0;
     const int n_tiles = Fr.tiles_x * Fr.tiles_y;
-    const int tile = blockIdx.y * Fr.tiles_x + tx;
+    const int tile = B.order[(size_t)view * n_tiles + blockIdx.x / (unsigned)n_sub];
+    const int tx = tile % Fr.tiles_x, ty = tile / Fr.tiles_x + Fr.tile_row0;
     const int X0 = tx * TILE_W, Y0 = ty * TILE_H;
     const int X1 = min(X0 + TILE_W, Fr.W), Y1 = min(min(Y0 + TILE_H, Fr.H), Fr.row_end);
     const int Yb0 = max(Y0, Fr.row_begin);
