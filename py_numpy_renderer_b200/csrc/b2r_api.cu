@@ -40,7 +40,7 @@ struct Globals {
     cudaEvent_t tri_done = nullptr;
     int host_chunk = 2;           // views per sub-chunk when frames go to host memory (copy/compute overlap)
     int dev_chunk = 64;           // views per launch when frames stay on the device (whole batch: the cost-ordered raster grid has no tail to hide)
-    int async_chunk = 4;          // views per sub-chunk of a host-asynchronous call (swept: tools/knob_sweep_e2e.sh)
+    int async_chunk = 8;          // views per sub-chunk of a host-asynchronous call (swept: tools/knob_sweep_e2e.sh)
     int aux_host = 2, aux_dev = 3;  // how many auxiliary streams the sub-chunks rotate over
     int bin_blocks = 0, bin_share = 64;  // k_bin grid (0 = 2 per SM) and the most warps that share one quad
     // pinned staging ring for the per-view constants: a pageable source would make cudaMemcpyAsync synchronise the

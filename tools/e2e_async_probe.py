@@ -6,7 +6,7 @@ from py_numpy_renderer_b200 import _native
 import bench
 _native.init(0)
 scene = scenes.c3_synthetic((1080, 1920))
-B = 16
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 pinned = [torch.empty((B, 1080, 1920, 3), dtype=torch.uint8, pin_memory=True).numpy() for _ in range(2)]
 t_cam = t_enq = t_wait = 0.0
 pend = None
