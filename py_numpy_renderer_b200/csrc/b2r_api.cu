@@ -42,6 +42,7 @@ struct Globals {
     int dev_chunk = 64;           // views per launch when frames stay on the device (whole batch: the cost-ordered raster grid has no tail to hide)
     int async_chunk = 8;          // views per sub-chunk of a host-asynchronous call (swept: tools/knob_sweep_e2e.sh)
     int aux_host = 2, aux_dev = 3;  // how many auxiliary streams the sub-chunks rotate over
+    int init_tri_cap = 0, init_quad_cap = 0;  // B2R_TRI_CAP / B2R_QUAD_CAP: first per-view list capacities (tests of the grow path)
     int bin_blocks = 0, bin_share = 64;  // k_bin grid (0 = 2 per SM) and the most warps that share one quad
     // pinned staging ring for the per-view constants: a pageable source would make cudaMemcpyAsync synchronise the
     // stream, i.e. serialise the host with the previous chunk / previous asynchronous call
@@ -182,6 +183,8 @@ int b2r_init(int device) {
     if (const char* dc = std::getenv("B2R_DEV_CHUNK")) g.dev_chunk = std::max(1, std::atoi(dc));
     if (const char* ac = std::getenv("B2R_ASYNC_CHUNK")) g.async_chunk = std::max(1, std::atoi(ac));
     if (const char* a = std::getenv("B2R_AUX_HOST")) g.aux_host = std::min(Globals::N_AUX, std::max(1, std::atoi(a)));
+    if (const char* a = std::getenv("B2R_TRI_CAP")) g.init_tri_cap = std::max(1, std::atoi(a));
+    if (const char* a = std::getenv("B2R_QUAD_CAP")) g.init_quad_cap = std::max(1, std::atoi(a));
     if (const char* a = std::getenv("B2R_BIN_BLOCKS")) g.bin_blocks = std::max(1, std::atoi(a));
     if (const char* a = std::getenv("B2R_BIN_SHARE")) g.bin_share = std::max(1, std::atoi(a));
     if (const char* a = std::getenv("B2R_AUX_DEV")) g.aux_dev = std::min(Globals::N_AUX, std::max(1, std::atoi(a)));
@@ -589,9 +592,9 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
     const int tslot = (int)(ticket & 3), rslot = (int)(ticket & 1);
     int* const flags = g.pinned_flags + (size_t)tslot * 2 * MAX_FLAG_VIEWS;
     if (n_views > MAX_FLAG_VIEWS) return fail("too many views in one call (max 4096)");
-    if (sc->tri_cap == 0) sc->tri_cap = std::max(1 << 16, 4 * F + 8 * n_tiles);
-    if (sc->quad_cap == 0) sc->quad_cap = std::max(1 << 20, 32 * E);
-    sc->tri_cap = std::max(sc->tri_cap, 8 * n_tiles);
+    if (sc->tri_cap == 0) sc->tri_cap = g.init_tri_cap ? g.init_tri_cap : std::max(1 << 16, 4 * F + 8 * n_tiles);
+    if (sc->quad_cap == 0) sc->quad_cap = g.init_quad_cap ? g.init_quad_cap : std::max(1 << 20, 32 * E);
+    if (!g.init_tri_cap) sc->tri_cap = std::max(sc->tri_cap, 8 * n_tiles);
 
     g.n_stage = 0;
     if (g.timing) cudaEventRecord(g.stage_ev[0], g.stream);

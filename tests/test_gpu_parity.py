@@ -240,3 +240,49 @@ def test_verbose_render_prints_the_reference_log(name, capsys):
     out = capsys.readouterr().out
     assert out == meta['log']
     assert np.array_equal(rgb, exp['rgb'])
+
+
+_OVERFLOW_SCRIPT = r"""
+import sys, numpy as np
+sys.path[:0] = [{root!r}, {root!r} + '/tests']
+import golden_util as gu
+import py_numpy_renderer_b200 as b2r
+from py_numpy_renderer_b200 import _native
+scene, exp, meta = gu.load('g2_diablo_floor_point')
+scene.persist_silhouette = False
+# synchronous call: the lists overflow, the call grows them and renders again before it returns
+dbg = {{}}
+rgb = scene.render(debug=dbg)
+rep = gu.compare_planes(dict(rgb=rgb, z=dbg['z'], stencil=dbg['stencil'], winner=dbg['winner']), exp)
+assert rep['z_mismatch'] == 0 and rep['stencil_mismatch'] == 0 and rep['winner_mismatch'] == 0 and rep['rgb_px_gt1'] == 0, rep
+# asynchronous device-resident call on a fresh scene: the overflow is reported by the next sync, the retry is right
+scene2, exp2, _ = gu.load('g2_diablo_floor_point')
+scene2.persist_silhouette = False
+import torch
+out = torch.empty((1, *scene2.resolution, 3), dtype=torch.uint8, device='cuda:0')
+scene2.render_batch([scene2.camera], debug_cameras=[scene2.debug_camera], out=out)
+try:
+    _native.sync()
+    raise SystemExit('the overflow of the asynchronous render was not reported')
+except RuntimeError as e:
+    assert 'capacity' in str(e), e
+scene2.render_batch([scene2.camera], debug_cameras=[scene2.debug_camera], out=out)
+_native.sync()
+got = out[0].cpu().numpy()
+assert np.abs(got.astype(int) - exp2['rgb'].astype(int)).max() <= 1
+print('OVERFLOW-OK')
+"""
+
+
+def test_tile_list_capacity_overflow_grows_and_retries():
+    """Per-tile list capacities far too small (B2R_TRI_CAP / B2R_QUAD_CAP = 64 entries per view): the synchronous
+    call must grow them and still return the exact frame; an asynchronous call must report the overflow at the next
+    sync and be right when rendered again.  Separate process: the capacities are read at b2r_init."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, B2R_TRI_CAP="64", B2R_QUAD_CAP="64")
+    res = subprocess.run([sys.executable, "-c", _OVERFLOW_SCRIPT.format(root=root)], env=env, capture_output=True,
+                         text=True, timeout=600)
+    assert res.returncode == 0 and "OVERFLOW-OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
