@@ -286,3 +286,32 @@ def test_tile_list_capacity_overflow_grows_and_retries():
     res = subprocess.run([sys.executable, "-c", _OVERFLOW_SCRIPT.format(root=root)], env=env, capture_output=True,
                          text=True, timeout=600)
     assert res.returncode == 0 and "OVERFLOW-OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def test_async_pipeline_many_views_matches_single_frames():
+    """The throughput paths: 70 views in one call (two set-up batches of <= 64 views, several raster/shade
+    sub-chunks on auxiliary streams, cost-ordered tile launch) through (a) the synchronous host path, (b) the
+    device-resident path and (c) two host-asynchronous calls in flight -- all byte-identical, and identical to
+    frames rendered one at a time."""
+    torch = pytest.importorskip("torch")
+    from py_numpy_renderer_b200 import _native
+    scene = scenes.c3_synthetic((270, 480), tex=128)
+    n = 70
+    cams = scenes.orbit_cameras(n)
+    dcams = scenes.orbit_cameras(n, fovy=90, near=0.05, far=20)
+    host = scene.render_batch(cams, debug_cameras=dcams)
+    dev = torch.zeros((n, 270, 480, 3), dtype=torch.uint8, device="cuda:0")
+    torch.cuda.synchronize()
+    scene.render_batch(cams, debug_cameras=dcams, out=dev)
+    _native.sync()
+    assert np.array_equal(dev.cpu().numpy(), host)
+    pinned = [torch.empty((n, 270, 480, 3), dtype=torch.uint8, pin_memory=True).numpy() for _ in range(2)]
+    f0 = scene.render_batch_async(cams, debug_cameras=dcams, out=pinned[0])
+    f1 = scene.render_batch_async(cams[::-1], debug_cameras=dcams[::-1], out=pinned[1])
+    f0.result(); f1.result()
+    assert np.array_equal(pinned[0], host)
+    assert np.array_equal(pinned[1], host[::-1])
+    for k in (0, 33, 64, 69):                                  # 64: first view of the second set-up batch
+        scene.camera, scene.debug_camera = cams[k], dcams[k]
+        scene.persist_silhouette = False
+        assert np.array_equal(scene.render(), host[k])
