@@ -54,6 +54,10 @@ def parse_args():
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU sample (default: by core count)")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0,
                     help="--impl reference: wall-clock bound of the whole run (steps are seconds each on the CPU)")
+    ap.add_argument("--gather", default="window", choices=["window", "nccl"],
+                    help="N>1: how the frames reach rank 0 -- 'window': every rank's shading kernel stores into rank "
+                         "0's buffer over NVLink (CUDA IPC, parallel.FrameWindow), the only collective is a one-element "
+                         "all-reduce per step; 'nccl': one NCCL gather per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -246,8 +250,18 @@ def main():
             c.scene = scene
         packed_steps.append(dev.pack(cams, dcams, scene.light, scene.resolution, scene.system, bg))
     frames_dev = [torch.empty((B, H, W, 3), dtype=torch.uint8, device=device) for _ in range(2)]
+    win, gather_mode = None, ("none" if world == 1 else args.gather)
+    if world > 1 and args.gather == "window":
+        try:
+            win = parallel.FrameWindow(B, H, W, slots=2, dst=0)
+        except Exception as exc:                              # no IPC between these processes: fall back, and say so
+            print(f"[bench] rank {rank}: output window unavailable ({exc}); using the NCCL gather", file=sys.stderr)
+        ok = torch.tensor([1 if win is not None else 0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            win, gather_mode = None, "nccl (window unavailable)"
     gathered = [[torch.empty((B, H, W, 3), dtype=torch.uint8, device=device) for _ in range(world)]
-                for _ in range(2)] if (world > 1 and rank == 0) else [None, None]
+                for _ in range(2)] if (world > 1 and rank == 0 and win is None) else [None, None]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
     cur = torch.cuda.current_stream()
 
@@ -268,11 +282,14 @@ def main():
             ready = torch.cuda.Event()
             ready.record(cur)
             lib_stream.wait_event(ready)
-            dev.render_packed(fp, views, out=frames_dev[slot])          # asynchronous, frames stay in HBM
+            # asynchronous, frames stay in HBM: this rank's buffer, or its block of rank 0's window (peer stores)
+            dev.render_packed(fp, views, out=frames_dev[slot] if win is None else win.block_ptr(slot))
             done = torch.cuda.Event()
             done.record(lib_stream)
             cur.wait_event(done)                            # the next flush must not start before this render ended
-            if world > 1:
+            if win is not None:
+                works[slot] = win.fence(async_op=True)      # one-element all-reduce: the step's frames are on rank 0
+            elif world > 1:
                 works[slot] = dist.gather(frames_dev[slot], gathered[slot], dst=0, async_op=True)
             if per_step_sync:
                 torch.cuda.synchronize()
@@ -308,6 +325,11 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
+    if win is not None and rank == 0:   # every rank's block of the last step really holds a rendered frame
+        last = torch.as_tensor(win.frames((Wm + K - 1) % 2), device=device)
+        for r in range(world):
+            blk = last[r * B]
+            assert int(blk.max()) > int(blk.min()), f"window block of rank {r} is empty"
     value = K * B * world / (dev_ms / 1e3)
     # per-stage CUDA-event timing (library stream) on a few more steps of the same workload, synchronised per step
     n_stage_steps = min(K, 5)
@@ -375,7 +397,11 @@ def main():
             "dtype": "f64", "data": "synthetic" if args.workload == "synthetic" else "reference assets",
             "mpix_per_s": value * H * W / 1e6,
             "config": {"workload": workload, "resolution": [H, W], "frames_per_step_per_gpu": B,
-                       "parallelism": f"frames x{world} (weak), one NCCL gather per step overlapped with the next render" if world > 1 else "single GPU",
+                       "parallelism": (f"frames x{world} (weak); frames reach rank 0 by: " +
+                                       ("peer stores of the shading kernel into rank 0's window over NVLink + a "
+                                        "one-element all-reduce per step" if gather_mode == "window" else
+                                        f"{gather_mode} gather per step, overlapped with the next render"))
+                       if world > 1 else "single GPU",
                        "l2": "flushed before every step (256 MiB memset, inside the timed region)",
                        "timing": "one CUDA-event pair around the K steps (first flush .. last gather), MAX over ranks; "
                                  "stage times from a separate per-step-synchronised pass",

@@ -174,6 +174,18 @@ int64_t b2r_launch_count(void);
 int b2r_last_stage_ms(const char** names, float* ms);
 int b2r_set_stage_timing(int enabled);
 
+/* ---- multi-GPU output window (the reference has no multi-device path: this replaces the gather that
+ * follows `Scene.render()` per rank when frames are sharded) ------------------------------------------------------
+ * One process per GPU.  The assembling rank creates a device buffer and exports it (64-byte CUDA IPC handle, sent to
+ * the peers by the host plumbing); every peer opens the handle and passes `base + its block offset` as `out_rgb`
+ * of b2r_render(..., out_on_device = 1): the shading kernel's stores then land in the assembling GPU's HBM over
+ * NVLink / NVSwitch and no collective moves the frames.  A window cannot be opened by the process that created it. */
+#define B2R_WINDOW_HANDLE_BYTES 64
+int b2r_window_create(int64_t bytes, void** dev_ptr, void* handle_out);
+int b2r_window_open(const void* handle, void** dev_ptr);
+int b2r_window_close(void* dev_ptr);      /* opened with b2r_window_open */
+int b2r_window_destroy(void* dev_ptr);    /* created with b2r_window_create */
+
 /* ---- native OBJ tokenizer (host only) ---------------------------------------------------------
  * The arrays `Model.load_model` builds (core.py:257-318): vertices float32 (V,4), uv float32 (T,3), normals float32
  * (N,3), faces int32 (F,3,4) = [v, vt, vn, material slot] fan-triangulated and 0-based (-1 = absent), the `usemtl`

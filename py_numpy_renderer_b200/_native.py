@@ -50,6 +50,10 @@ _SYMBOLS = {
     "b2r_launch_count": (C.c_int64, []),
     "b2r_last_stage_ms": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b2r_set_stage_timing": (C.c_int, [C.c_int]),
+    "b2r_window_create": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
+    "b2r_window_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "b2r_window_close": (C.c_int, [C.c_void_p]),
+    "b2r_window_destroy": (C.c_int, [C.c_void_p]),
     "b2r_obj_load": (C.c_int, [C.c_char_p, C.c_void_p]),
     "b2r_obj_free": (None, [C.c_void_p]),
 }
@@ -274,6 +278,30 @@ class DeviceScene:
             info['face_status'] = info['face_status'][:, :self.packed.total_faces]
             info['n_silhouette'] = info['n_silhouette'][:, :self.packed.n_models]
         return frames, info
+
+
+def window_create(nbytes):
+    """Device buffer on this GPU that peer processes can map -> (device pointer, 64-byte IPC handle)."""
+    lib = init()
+    ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+    _check(lib.b2r_window_create(int(nbytes), C.byref(ptr), handle))
+    return int(ptr.value), handle.raw
+
+
+def window_open(handle: bytes):
+    """Map a peer's window (its IPC handle) into this process -> device pointer."""
+    lib = init()
+    ptr = C.c_void_p()
+    _check(lib.b2r_window_open(C.create_string_buffer(handle, 64), C.byref(ptr)))
+    return int(ptr.value)
+
+
+def window_close(ptr):
+    _check(init().b2r_window_close(C.c_void_p(ptr)))
+
+
+def window_destroy(ptr):
+    _check(init().b2r_window_destroy(C.c_void_p(ptr)))
 
 
 class PendingFrames:

@@ -262,6 +262,41 @@ int b2r_debug_stats(unsigned long long* out16, int reset) {
     if (reset) { unsigned long long z[16] = {0}; CK(cudaMemcpyToSymbol(g_stats, z, sizeof(z))); }
     return 0;
 }
+// ---- multi-GPU output window: CUDA IPC export / import of the assembling rank's frame buffer ----
+int b2r_window_create(int64_t bytes, void** dev_ptr, void* handle_out) {
+    if (!g.ready) return fail("b2r_init was not called");
+    if (bytes <= 0 || !dev_ptr || !handle_out) return fail("b2r_window_create: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == B2R_WINDOW_HANDLE_BYTES, "IPC handle size");
+    CK(cudaSetDevice(g.device));
+    void* p = nullptr;
+    CK(cudaMalloc(&p, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+    std::memcpy(handle_out, &h, sizeof(h));
+    *dev_ptr = p;
+    return 0;
+}
+int b2r_window_open(const void* handle, void** dev_ptr) {
+    if (!g.ready) return fail("b2r_init was not called");
+    if (!handle || !dev_ptr) return fail("b2r_window_open: bad arguments");
+    CK(cudaSetDevice(g.device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    CK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int b2r_window_close(void* dev_ptr) {
+    if (!dev_ptr) return 0;
+    CK(cudaIpcCloseMemHandle(dev_ptr));
+    return 0;
+}
+int b2r_window_destroy(void* dev_ptr) {
+    if (!dev_ptr) return 0;
+    CK(cudaFree(dev_ptr));
+    return 0;
+}
+
 int b2r_set_stage_timing(int enabled) { g.timing = enabled != 0; return 0; }
 int b2r_last_stage_ms(const char** names, float* ms) {
     for (int i = 0; i < g.n_stage; ++i) {

@@ -97,3 +97,76 @@ def gather_bands(local, bands, height: int, dst: int = 0):
     for r, (a, b) in enumerate(bands):
         out[:, height - b:height - a] = recv[r][:, :b - a]
     return out
+
+
+class _DevView:
+    """A raw device range presented through __cuda_array_interface__ (so torch / CuPy can wrap it without a copy)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+class FrameWindow:
+    """Frames of all ranks assembled on rank `dst` WITHOUT a collective: `dst` owns a device buffer of
+    (slots, world, n, H, W, 3) uint8 and exports it through CUDA IPC; every other rank maps it and hands
+    `block_ptr(slot)` to `render_batch(..., out=)`, so its shading kernel stores the finished pixels straight into
+    `dst`'s HBM over NVLink / NVSwitch.  What remains of the gather is `fence()`: a one-element all-reduce (NCCL) or a
+    host barrier (gloo) after which `dst` may read the slot.  Same node only; the handle travels through
+    torch.distributed's object broadcast, whatever the backend."""
+
+    def __init__(self, n, height, width, slots=2, dst=0):
+        from . import _native
+        d = dist()
+        self.rank, self.world = (d.get_rank(), d.get_world_size()) if d.is_initialized() else (0, 1)
+        self.dst, self.slots, self.shape = dst, slots, (n, height, width, 3)
+        self.block_bytes = n * height * width * 3
+        total = slots * self.world * self.block_bytes
+        self.owner = self.rank == dst
+        box = [None]
+        if self.owner:
+            self.base, handle = _native.window_create(total)
+            box = [handle]
+        if self.world > 1:
+            d.broadcast_object_list(box, src=dst)
+        if not self.owner:
+            self.base = _native.window_open(box[0])
+        self._token = None
+
+    def block_ptr(self, slot, rank=None):
+        """Device address this rank renders its n frames of `slot` to (an int: pass it as `out=`)."""
+        rank = self.rank if rank is None else rank
+        return self.base + (slot * self.world + rank) * self.block_bytes
+
+    def frames(self, slot):
+        """On `dst`: the assembled (world * n, H, W, 3) frames of `slot` as a zero-copy CUDA array-interface object
+        (torch.as_tensor(w.frames(s), device='cuda') wraps it)."""
+        if not self.owner:
+            return None
+        n, H, W, _ = self.shape
+        return _DevView(self.block_ptr(slot, 0), (self.world * n, H, W, 3))
+
+    def fence(self, stream_sync=None, async_op=False):
+        """Everything the ranks rendered into the window so far is complete and visible on `dst` once this (or the
+        returned work handle) finishes.  NCCL: a one-element all-reduce ordered after the current torch stream --
+        make that stream wait for the render first.  gloo: `stream_sync()` (e.g. _native.sync) then a host barrier."""
+        import torch
+        d = dist()
+        if self.world == 1:
+            if stream_sync:
+                stream_sync()
+            return None
+        if d.get_backend() == "nccl":
+            if self._token is None:
+                self._token = torch.zeros(1, dtype=torch.int32, device="cuda")
+            return d.all_reduce(self._token, async_op=async_op)
+        if stream_sync:
+            stream_sync()
+        d.barrier()
+        return None
+
+    def close(self):
+        from . import _native
+        if self.base:
+            (_native.window_destroy if self.owner else _native.window_close)(self.base)
+            self.base = 0
