@@ -54,10 +54,12 @@ def parse_args():
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU sample (default: by core count)")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0,
                     help="--impl reference: wall-clock bound of the whole run (steps are seconds each on the CPU)")
-    ap.add_argument("--gather", default="window", choices=["window", "nccl"],
+    ap.add_argument("--gather", default="auto", choices=["auto", "window", "window-copy", "nccl"],
                     help="N>1: how the frames reach rank 0 -- 'window': every rank's shading kernel stores into rank "
                          "0's buffer over NVLink (CUDA IPC, parallel.FrameWindow), the only collective is a one-element "
-                         "all-reduce per step; 'nccl': one NCCL gather per step")
+                         "all-reduce per step; 'window-copy': frames are rendered locally and pushed into the window by the "
+                         "copy engines while the next step renders; 'nccl': one NCCL gather per step; 'auto': window for "
+                         "N <= 2, window-copy beyond (seven ranks bursting 1.5 TB/s of stores into one GPU stall on NVLink)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -250,8 +252,10 @@ def main():
             c.scene = scene
         packed_steps.append(dev.pack(cams, dcams, scene.light, scene.resolution, scene.system, bg))
     frames_dev = [torch.empty((B, H, W, 3), dtype=torch.uint8, device=device) for _ in range(2)]
+    if args.gather == "auto":
+        args.gather = "window" if world <= 2 else "window-copy"
     win, gather_mode = None, ("none" if world == 1 else args.gather)
-    if world > 1 and args.gather == "window":
+    if world > 1 and args.gather.startswith("window"):
         try:
             win = parallel.FrameWindow(B, H, W, slots=2, dst=0)
         except Exception as exc:                              # no IPC between these processes: fall back, and say so
@@ -260,6 +264,9 @@ def main():
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 0:
             win, gather_mode = None, "nccl (window unavailable)"
+    push = win is not None and args.gather == "window-copy"
+    push_stream = torch.cuda.Stream() if push else None
+    win_blocks = [torch.as_tensor(win.block(s), device=device) for s in range(2)] if push else None
     gathered = [[torch.empty((B, H, W, 3), dtype=torch.uint8, device=device) for _ in range(world)]
                 for _ in range(2)] if (world > 1 and rank == 0 and win is None) else [None, None]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
@@ -283,11 +290,16 @@ def main():
             ready.record(cur)
             lib_stream.wait_event(ready)
             # asynchronous, frames stay in HBM: this rank's buffer, or its block of rank 0's window (peer stores)
-            dev.render_packed(fp, views, out=frames_dev[slot] if win is None else win.block_ptr(slot))
+            dev.render_packed(fp, views, out=frames_dev[slot] if (win is None or push) else win.block_ptr(slot))
             done = torch.cuda.Event()
             done.record(lib_stream)
             cur.wait_event(done)                            # the next flush must not start before this render ended
-            if win is not None:
+            if push:                                        # copy engines move the frames while the next step renders
+                push_stream.wait_event(done)
+                with torch.cuda.stream(push_stream):
+                    win_blocks[slot].copy_(frames_dev[slot], non_blocking=True)
+                    works[slot] = win.fence(async_op=True)
+            elif win is not None:
                 works[slot] = win.fence(async_op=True)      # one-element all-reduce: the step's frames are on rank 0
             elif world > 1:
                 works[slot] = dist.gather(frames_dev[slot], gathered[slot], dst=0, async_op=True)
@@ -400,6 +412,8 @@ def main():
                        "parallelism": (f"frames x{world} (weak); frames reach rank 0 by: " +
                                        ("peer stores of the shading kernel into rank 0's window over NVLink + a "
                                         "one-element all-reduce per step" if gather_mode == "window" else
+                                        "copy-engine pushes into rank 0's window over NVLink, overlapped with the next "
+                                        "render, + a one-element all-reduce per step" if gather_mode == "window-copy" else
                                         f"{gather_mode} gather per step, overlapped with the next render"))
                        if world > 1 else "single GPU",
                        "l2": "flushed before every step (256 MiB memset, inside the timed region)",

@@ -138,6 +138,12 @@ class FrameWindow:
         rank = self.rank if rank is None else rank
         return self.base + (slot * self.world + rank) * self.block_bytes
 
+    def block(self, slot):
+        """This rank's block of `slot` as a CUDA array-interface object (n, H, W, 3): `torch.as_tensor(w.block(s),
+        device='cuda').copy_(local, non_blocking=True)` pushes finished frames with the copy engines instead of the
+        shading kernel's own stores (useful when many ranks would otherwise burst into `dst` at the same moment)."""
+        return _DevView(self.block_ptr(slot), self.shape)
+
     def frames(self, slot):
         """On `dst`: the assembled (world * n, H, W, 3) frames of `slot` as a zero-copy CUDA array-interface object
         (torch.as_tensor(w.frames(s), device='cuda') wraps it)."""
