@@ -217,9 +217,11 @@ def main():
     if args.impl == "reference":
         return run_reference(args, rank, world)
 
+    from py_numpy_renderer_b200 import _native, parallel
+    cpus_before = len(os.sched_getaffinity(0))
+    numa_cpus = _native.bind_host_to_gpu(local)             # pinned buffers on the GPU's NUMA node (before torch threads)
     import torch
     import torch.distributed as dist
-    from py_numpy_renderer_b200 import _native, parallel
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
@@ -351,28 +353,33 @@ def main():
 
     # ---- end to end through the public API: host camera maths + H2D + render + D2H into pinned memory ----
     pinned = [torch.empty((B, H, W, 3), dtype=torch.uint8, pin_memory=True).numpy() for _ in range(2)]
-    e2e_steps = max(3, min(K, 30))
+    e2e_steps = max(3, min(K, 20))
     for s in range(2):
         cams, dcams = step_cameras(1000 + s, rank, world, B)
         scene.render_batch(cams, debug_cameras=dcams, out=pinned[s])
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    in_flight = None
-    for s in range(e2e_steps):
-        # camera construction + matrix evaluation of step s happen here while step s-1 renders / copies
-        cams, dcams = step_cameras(2000 + s, rank, world, B)
-        fut = scene.render_batch_async(cams, debug_cameras=dcams, out=pinned[s % 2])
-        if in_flight is not None:
-            in_flight.result()                                          # frames of step s-1 are in host memory
-        in_flight = fut
-    in_flight.result()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_fps = e2e_steps * B * world / float(t.item())
+    # three repetitions of e2e_steps steps, the median is reported (wall clock on a shared host: a single short run
+    # swings by tens of percent with whatever else uses the host's memory / PCIe fabric at that moment)
+    e2e_runs = []
+    for rep in range(3):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        in_flight = None
+        for s in range(e2e_steps):
+            # camera construction + matrix evaluation of step s happen here while step s-1 renders / copies
+            cams, dcams = step_cameras(2000 + 100 * rep + s, rank, world, B)
+            fut = scene.render_batch_async(cams, debug_cameras=dcams, out=pinned[s % 2])
+            if in_flight is not None:
+                in_flight.result()                                      # frames of step s-1 are in host memory
+            in_flight = fut
+        in_flight.result()
+        e2e_s = time.perf_counter() - t0
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_runs.append(e2e_steps * B * world / float(t.item()))
+    e2e_fps = sorted(e2e_runs)[1]
     sampler.stop_flag = True
     sampler.join(timeout=1)
 
@@ -423,7 +430,9 @@ def main():
             "e2e": {"value": e2e_fps, "unit": UNIT,
                     "h2d_bytes_per_step": B * ctypes.sizeof(_abi.View) + ctypes.sizeof(_abi.FrameParams),
                     "d2h_bytes_per_step": B * H * W * 3, "steps": e2e_steps,
-                    "api": "Scene.render_batch_async(cameras, out=pinned ndarray), two batches in flight"},
+                    "runs": [round(v, 1) for v in e2e_runs], "reported": "median of the three runs",
+                    "api": "Scene.render_batch_async(cameras, out=pinned ndarray), two batches in flight",
+                    "host_affinity": (f"{numa_cpus} of {cpus_before} CPUs (GPU-local, NVML)" if numa_cpus else "unchanged")},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline}
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
