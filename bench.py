@@ -410,7 +410,11 @@ def main():
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_frame": balg, "frames_per_launch": B,
                     "kernel_ms_per_launch": stage_avg[top], "stage_ms_per_step": stage_avg,
-                    "whole_frame_frac": balg["total"] * value / world / 1e9 / peak}
+                    "whole_frame_frac": balg["total"] * value / world / 1e9 / peak,
+                    # every stage against the same ceiling: the frame's algorithmic bytes over the stage's own time
+                    "stage_frac": {k: (balg["total"] * B / (v / 1e3) / 1e9 / peak) if v > 0 else None
+                                   for k, v in stage_avg.items()},
+                    "secondary_ceilings": "profiles/README.md (FP64 issue, shared / L2 atomics, PCIe: measured on the box)"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic" if args.workload == "synthetic" else "reference assets",
