@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B2R_ABI_VERSION 2
+#define B2R_ABI_VERSION 3
 #define B2R_MAX_POLY 12 /* a quad clipped by 6 planes has at most 10 vertices */
 
 /* Light kinds: obj/lightning.py:4-7 */
