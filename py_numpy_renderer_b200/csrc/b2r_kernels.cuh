@@ -457,11 +457,24 @@ __global__ void k_bin(FrameDev Fr, const TriRec* __restrict__ tris, const QuadRe
             nt = tw * ((by1 - 1) / TILE_H - ty0 + 1);
         }
         const bool small = valid && nt <= BIN_SMALL;
-        if (small) {
-            for (int i = 0; i < nt; ++i) {
+        // Small boxes: the faces of a warp are neighbours in the mesh and mostly fall into the same few tiles, so
+        // the lanes that hit the same tile share ONE atomic (match_any): with hundreds of micro-triangles per tile
+        // (BASELINE config 5) the per-tile counters are otherwise a same-address serialisation point.
+#pragma unroll
+        for (int i = 0; i < BIN_SMALL; ++i) {
+            const bool act = small && i < nt;
+            const unsigned am = __ballot_sync(0xffffffffu, act);
+            if (!am) break;
+            if (act) {
                 const int t = (ty0 + i / tw - Fr.tile_row0) * Fr.tiles_x + tx0 + i % tw;
-                if (FILL) tri_list[tri_off[t] + atomicAdd(tri_count + t, 1)] = slot;
-                else atomicAdd(tri_count + t, 1);
+                const unsigned peers = __match_any_sync(am, t);
+                const int leader = __ffs(peers) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(tri_count + t, __popc(peers));
+                if (FILL) {
+                    base = __shfl_sync(peers, base, leader);
+                    tri_list[tri_off[t] + base + __popc(peers & ((1u << lane) - 1))] = slot;
+                }
             }
         }
         unsigned queue = __ballot_sync(0xffffffffu, valid && !small);
