@@ -852,7 +852,7 @@ __device__ __forceinline__ void raster_tris(RasterSmem& sm, const SceneDev& S, c
 }
 
 #ifndef B2R_RASTER_MINB
-#define B2R_RASTER_MINB 8
+#define B2R_RASTER_MINB 9
 #endif
 __global__ void __launch_bounds__(RASTER_THREADS, B2R_RASTER_MINB)
 k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec* __restrict__ tris,
@@ -1407,7 +1407,7 @@ __device__ __forceinline__ bool skybox_pixel(const SceneDev& S, const ViewDev& V
 #define B2R_SHADE_THREADS 128
 #endif
 #ifndef B2R_SHADE_MINB
-#define B2R_SHADE_MINB 10
+#define B2R_SHADE_MINB 12
 #endif
 __global__ void __launch_bounds__(B2R_SHADE_THREADS, B2R_SHADE_MINB)
 k_shade(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec* __restrict__ tris,
