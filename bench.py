@@ -414,7 +414,10 @@ def main():
                     # every stage against the same ceiling: the frame's algorithmic bytes over the stage's own time
                     "stage_frac": {k: (balg["total"] * B / (v / 1e3) / 1e9 / peak) if v > 0 else None
                                    for k, v in stage_avg.items()},
-                    "secondary_ceilings": "profiles/README.md (FP64 issue, shared / L2 atomics, PCIe: measured on the box)"}
+                    "secondary_ceilings": "profiles/README.md (FP64 issue, shared / L2 atomics, PCIe: measured on the box)",
+                    "note": "HBM is the roofline the contract names, not what binds this path: the float64 semantics "
+                            "of the reference make raster / shade issue- and latency-bound (ncu, 16-view launch: issue "
+                            "slots 72 % / 64 % busy, DRAM 3 % / 7 % of peak)"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic" if args.workload == "synthetic" else "reference assets",
