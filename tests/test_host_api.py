@@ -213,3 +213,23 @@ def test_native_obj_tokenizer_on_diablo():
     a, b = b2r.Model.load_model(p, native=True), b2r.Model.load_model(p, native=False)
     _same_model(a, b)
     assert a._faces.shape == (5022, 3, 4) and a.vertices.shape == (2519, 4)
+
+
+def test_bind_host_to_gpu_is_harmless_without_nvml():
+    """No GPU / no NVML in the build container: the affinity helper changes nothing and says so."""
+    import os
+    from py_numpy_renderer_b200 import _native
+    before = os.sched_getaffinity(0)
+    got = _native.bind_host_to_gpu(0)
+    assert got is None or got == len(os.sched_getaffinity(0))
+    if got is None:
+        assert os.sched_getaffinity(0) == before
+
+
+def test_window_views_describe_the_blocks():
+    """`parallel._DevView` (what FrameWindow hands to torch / CuPy): CUDA array interface of a raw device range."""
+    from py_numpy_renderer_b200 import parallel
+    v = parallel._DevView(0x7f0000000000, (2, 4, 5, 3))
+    cai = v.__cuda_array_interface__
+    assert cai["shape"] == (2, 4, 5, 3) and cai["typestr"] == "|u1" and cai["data"] == (0x7f0000000000, False)
+    assert cai["strides"] is None and cai["version"] == 3
