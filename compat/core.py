@@ -5,5 +5,5 @@ import sys as _sys
 
 _sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
 from py_numpy_renderer_b200.core import *  # noqa: F401,F403,E402
-from py_numpy_renderer_b200.core import Camera, Light, Model, Scene, TextureMaps, Bound  # noqa: F401,E402
+from py_numpy_renderer_b200.core import Camera, Face, Light, Model, Scene, TextureMaps, Bound  # noqa: F401,E402
 from py_numpy_renderer_b200._native import Errors  # noqa: F401,E402

@@ -10,7 +10,7 @@ from .lightning import Lightning  # noqa: F401
 from .materials import Material, Texture  # noqa: F401
 from .transformation import scale, translation, rotate, rotate_xyz  # noqa: F401
 from .cube_map import CubeMap  # noqa: F401
-from .core import Model, Camera, Light, Scene, TextureMaps  # noqa: F401
+from .core import Model, Face, Camera, Light, Scene, TextureMaps  # noqa: F401
 
-__all__ = ["Model", "Camera", "Light", "Scene", "TextureMaps", "CubeMap", "Material", "Texture", "Lightning",
+__all__ = ["Model", "Face", "Camera", "Light", "Scene", "TextureMaps", "CubeMap", "Material", "Texture", "Lightning",
            "PROJECTION_TYPE", "SUBSYSTEM", "SYSTEM", "scale", "translation", "rotate", "rotate_xyz"]

@@ -59,6 +59,36 @@ def _fan(corners):
     return [[corners[0], corners[k], corners[k + 1]] for k in range(1, len(corners) - 1)]
 
 
+class Face:
+    """Read-only host view of one triangle (reference: `Face`, core.py:108-136).  The reference drives its three
+    passes by iterating such objects; here they only serve inspection (`model.faces`) -- the kernels work on the packed
+    arrays.  `material` follows the reference's lookup: the face's group name, falling back to 'default'."""
+
+    def __init__(self, model, vi, ti=None, ni=None, mtl=(0,)):
+        self.model = model
+        self._vi, self._ti, self._ni = vi, ti, ni
+        self.vertices = model.vertices[vi]
+        self.world_vertices = self.vertices.copy()
+        self.uv = None if model.uv is None else model.uv[ti]
+        self.normals = None if model.normals is None else model.normals[ni]
+        self.textures = model.textures
+        self.material = model.materials.get(model.material_group[mtl[0]], model.materials['default'])
+
+    def _unit_normal(self, pts):
+        a, b, c = pts[..., :3]
+        return normalize(np.cross(b - a, c - a)).squeeze()
+
+    @property
+    def unit_normal_world_space(self):
+        """normalize((b - a) x (c - a)) of the untransformed copy, in the vertex dtype (core.py:127-130)."""
+        return self._unit_normal(self.world_vertices)
+
+    @property
+    def unit_normal_current_space(self):
+        """Same on `vertices`, which the reference overwrites with screen coordinates while rasterising (132-136)."""
+        return self._unit_normal(self.vertices)
+
+
 class Model:
     def __init__(self, vertices, uv, normals, faces, shadowing: bool = False, materials: dict = None,
                  material_group: list = None, clip=True, depth_test=True):
@@ -78,6 +108,11 @@ class Model:
         self._scene_refs = []
 
     # -- reference API -----------------------------------------------------------------------------------------
+    @property
+    def faces(self):
+        """Iterator over `Face` views in file order (core.py:253-255)."""
+        return (Face(self, *f.T) for f in self._faces)
+
     @classmethod
     def load_model(cls, name, shadowing=True, native=None):
         """Wavefront OBJ (+MTL) loader producing the arrays of core.py:257-318: vertices f32 (V,4) with w=1,
@@ -298,6 +333,11 @@ class Light(PositionedObject, TransformationMatrixMixin):
     def smoothstep(edge0, edge1, x_array):
         t = np.clip((x_array - edge0) / (edge1 - edge0), 0.0, 1.0)
         return t * t * (3 - 2 * t)
+
+    @staticmethod
+    def reflect(I, N):
+        """Mirror the rows of `I` about the rows of `N`, normalised (core.py:493-495; unused by render())."""
+        return normalize(I - 2.0 * np.sum(N * I, axis=1)[..., np.newaxis] * N)
 
     def attenuation(self, fragment_position):
         distance = np.linalg.norm((self.position - fragment_position), axis=1)

@@ -233,3 +233,39 @@ def test_window_views_describe_the_blocks():
     cai = v.__cuda_array_interface__
     assert cai["shape"] == (2, 4, 5, 3) and cai["typestr"] == "|u1" and cai["data"] == (0x7f0000000000, False)
     assert cai["strides"] is None and cai["version"] == 3
+
+
+def test_model_faces_views_and_light_reflect():
+    """`model.faces` yields per-triangle views with the reference's attributes (core.py:108-136, 253-255); `Light.reflect`
+    (core.py:493-495)."""
+    import py_numpy_renderer_b200 as b2r
+    import scenes
+    model = scenes.floor_model()
+    faces = list(model.faces)
+    assert len(faces) == len(model._faces) == 2
+    f = faces[0]
+    assert f.vertices.shape == (3, 4) and f.uv.shape == (3, 3) and f.normals.shape == (3, 3)
+    assert f.material is model.materials['default'] and f.textures is model.textures and f.model is model
+    n = f.unit_normal_world_space
+    assert n.shape == (3,) and abs(float(np.linalg.norm(n)) - 1) < 1e-6 and abs(abs(float(n[1])) - 1) < 1e-6  # plane y = -1
+    assert np.array_equal(f.unit_normal_current_space, n)
+    out = b2r.Light.reflect(np.array([[1.0, -1.0, 0.0]]), np.array([[0.0, 1.0, 0.0]]))
+    assert np.allclose(out, np.array([[1.0, 1.0, 0.0]]) / np.sqrt(2))
+
+
+def test_model_faces_match_the_reference_when_it_is_importable():
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import refboot
+    if not refboot.available():
+        pytest.skip("reference sources not mounted")
+    import scenes
+    ref = refboot.boot()
+    mine = scenes.floor_model()
+    theirs = ref.Model(mine.vertices.copy(), mine.uv.copy(), mine.normals.copy(), mine._faces.copy())
+    for a, b in zip(mine.faces, theirs.faces):
+        assert np.array_equal(a.vertices, b.vertices) and np.array_equal(a.uv, b.uv) and np.array_equal(a.normals, b.normals)
+        assert np.array_equal(a.unit_normal_world_space, b.unit_normal_world_space)
+    I, N = np.array([[0.3, -0.8, 0.5], [1.0, 2.0, 3.0]]), np.array([[0.0, 1.0, 0.0], [0.6, 0.0, 0.8]])
+    import py_numpy_renderer_b200 as b2r
+    assert np.array_equal(b2r.Light.reflect(I, N), ref.Light.reflect(I, N))
