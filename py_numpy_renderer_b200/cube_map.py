@@ -28,6 +28,11 @@ class CubeMap:
         """uint8 RGB (alpha dropped) -- the reference divides by 255 here (cube_map.py:56-61)."""
         return np.asarray(Image.open(name))[..., :3].copy()
 
+    @staticmethod
+    def load_texture(name) -> np.ndarray:
+        """The reference's loader name and value: float64 RGB in [0, 1] (cube_map.py:56-61)."""
+        return CubeMap.load_texels(name) / 255
+
     @property
     def textures(self) -> np.ndarray:
         """The reference's float64 (6,S,S,3) view, for host-side inspection / tests."""
