@@ -4,8 +4,7 @@ import numpy as np
 import golden_util as gu, oracle as orc
 for name in gu.fixture_names():
     scene, exp, meta = gu.load(name)
-    ref = orc.render_scene(scene)
-    ref = {k: (v[0] if v is not None else None) for k, v in ref.items()}
+    ref = gu.oracle_frame(orc, scene)   # oracle + the host overlay pass where the debug frustum is visible (g10, g11)
     dbg = {}
     scene.persist_silhouette = False
     rgb = scene.render(debug=dbg)
