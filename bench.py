@@ -179,7 +179,7 @@ def run_reference(args, rank, world):
         return
     scene, workload = build_scene(args)
     cores = os.cpu_count() or 1
-    n_frames = args.cpu_frames or max(4, min(cores, 32))
+    n_frames = args.cpu_frames or max(4, min(cores, 128))   # one frame per host thread: every core works
     # One step = n_frames frames, one per host thread (the port has no parallelism inside a frame: the reference's
     # per-face N-dependent evaluation order needs whole-box counts), i.e. seconds per step whatever the sample.  The
     # run is bounded in wall time: warm-up samples and timed steps stop when --cpu-budget-s is used up, and the line
