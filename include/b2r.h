@@ -18,8 +18,17 @@
  * (core.py:394-429), so the library never re-derives a camera.
  *
  * Error model: every call returns 0 on success, non-zero on failure; `b2r_last_error()` gives the message
- * (thread-local).  The library never frees or keeps caller memory: create() copies what it needs to the device.
+ * (thread-local).  B2R_ERR_INDEX (2) from b2r_render / b2r_wait / b2r_sync means a texture lookup fell outside its map
+ * (UV < -1), where the reference raises IndexError (core.py:138-143, 162-173).  The library never frees or keeps
+ * caller memory: create() copies what it needs to the device.
  * There is NO CPU fallback: without a CUDA device every entry point except b2r_last_error/b2r_abi_version fails.
+ *
+ * State and threading: there is no process-global render state.  b2r_init(device) creates (or selects) the CONTEXT of
+ * that CUDA device -- its streams, events and pinned staging -- and makes it the calling thread's current context; a
+ * scene belongs to the context it was created on, so scenes on different devices coexist in one process and may be
+ * driven from different threads.  Every entry point locks the context it acts on (entry points taking a scene: the
+ * scene's; the others: the calling thread's current context, i.e. the device it last passed to b2r_init, else the most
+ * recently initialised one).
  */
 #ifndef B2R_H_
 #define B2R_H_
@@ -30,7 +39,7 @@
 extern "C" {
 #endif
 
-#define B2R_ABI_VERSION 3
+#define B2R_ABI_VERSION 4
 #define B2R_MAX_POLY 12 /* a quad clipped by 6 planes has at most 10 vertices */
 
 /* Light kinds: obj/lightning.py:4-7 */
@@ -73,7 +82,10 @@ typedef struct b2r_model_desc {
     int32_t n_vertices, n_uv, n_normals, n_faces, n_materials;
     int32_t vertex_dtype, uv_dtype, normal_dtype; /* B2R_F32 | B2R_F64 */
     int32_t clip;       /* Model.clip (triangular.py:80) */
-    int32_t depth_test; /* Model.depth_test (triangular.py:117); only 1 is supported (order-independent z) */
+    int32_t depth_test; /* Model.depth_test (triangular.py:117): 0 = the model's faces are z-TESTED but never write z.
+                           Still order independent: zbuf = min/max over the writing faces only, and the face that colours
+                           a pixel is the greatest index among {writing faces with z == zbuf} and {non-writing faces
+                           whose z passes the test against the final zbuf} */
 } b2r_model_desc;
 
 /* CubeMap.textures after the constructor's flips/rotations (cube_map.py:22-44): 6 faces ordered
@@ -137,9 +149,13 @@ typedef struct b2r_scene b2r_scene;
 int b2r_abi_version(void);
 const char* b2r_last_error(void);
 
-/* Select the CUDA device and create the library's stream.  Must precede everything else. */
+#define B2R_ERR_INDEX 2
+
+/* Create (first call) or select the context of CUDA device `device` and make it current for the calling thread.
+ * Must precede everything else.  b2r_shutdown drains and releases every context (destroy the scenes first). */
 int b2r_init(int device);
 int b2r_shutdown(void);
+int b2r_current_device(void); /* device of the calling thread's current context, -1 = none */
 
 int b2r_scene_create(const b2r_model_desc* models, int32_t n_models,
                      const b2r_texture_desc* textures, int32_t n_textures,
@@ -148,6 +164,10 @@ int b2r_scene_create(const b2r_model_desc* models, int32_t n_models,
 int b2r_scene_destroy(b2r_scene* scene);
 int b2r_scene_reset_silhouette(b2r_scene* scene);
 int64_t b2r_scene_device_bytes(const b2r_scene* scene);
+/* Restore a persistent silhouette set (e.g. after the device scene was rebuilt because a Model was transformed: in the
+ * reference `model.silhouette` lives on the Model and survives `model @ M`).  pairs (n,2): scene-global vertex indices
+ * in stored orientation, as b2r_scene_get_silhouette returns them; pairs that are no edge of the scene are ignored. */
+int b2r_scene_set_silhouette(b2r_scene* scene, const int32_t* pairs, int32_t n);
 /* Read the persistent silhouette set back (`model.silhouette`, core.py:251): out_pairs (capacity,2) scene-global
  * vertex indices in stored orientation, out_model (capacity) owning model.  Returns the number of edges. */
 int b2r_scene_get_silhouette(b2r_scene* scene, int32_t* out_pairs, int32_t* out_model, int32_t capacity);
@@ -159,7 +179,9 @@ int b2r_scene_get_silhouette(b2r_scene* scene, int32_t* out_pairs, int32_t* out_
 int b2r_render(b2r_scene* scene, const b2r_frame_params* params, const b2r_view* views, int32_t n_views,
                uint8_t* out_rgb, const b2r_debug_out* debug /* nullable */, int32_t out_on_device);
 /* out_on_device == 2: host pointers, but the call returns as soon as everything is enqueued; the frames (and the
- * capacity check) are complete after b2r_wait(b2r_last_ticket()).  Up to two such calls may be in flight. */
+ * capacity check) are complete after b2r_wait(b2r_last_ticket()).  Only these calls take a ticket.  Up to four may be
+ * in flight per context: a fifth first completes the oldest (the host blocks; its outcome is kept for its b2r_wait).
+ * With out_on_device == 1, b2r_sync reports a tile-list overflow of ANY render enqueued since the previous b2r_sync. */
 int64_t b2r_last_ticket(void);
 int b2r_wait(int64_t ticket);
 int b2r_sync(void);

@@ -195,10 +195,36 @@ def fixtures(ref):
                           quadratic=0.002),
                models=lambda: [ref.Model.load_model(cube_path(5)) @ T.scale(0.5) @ T.rotate_xyz((20, 30, 10)),
                                floor(ref)])
+    # Model(depth_test=False): decals in front of / behind the figure, before / between / after the writing models in
+    # add_model order (the face that colours a pixel depends on that order)
+    yield dict(name='g12_depth_test_false', resolution=(216, 288), system='LH', subsystem='OPENGL', camera=CAM,
+               debug_camera=DCAM, light=LIGHT,
+               models=lambda: [decal(ref, -0.6, 0.2, -0.3, 0.6, 0.9), diablo(ref, False),
+                               decal(ref, -1.0, 1.0, -0.8, 1.0, -0.9), floor(ref), decal(ref, 0.3, 1.2, -0.9, 0.1, 0.3)])
+    yield dict(name='g13_depth_test_false_rh', resolution=(150, 200), system='RH', subsystem='DIRECTX',
+               camera=cam_kwargs((2.5, 2.0, 4.0), fovy=50, near=0.5, far=20, backface_culling=True),
+               debug_camera=cam_kwargs((2.5, 2.0, 4.0), fovy=80, near=0.25, far=40, backface_culling=True),
+               light=dict(position=[3, 4, 2], light_type='POINT_LIGHTNING', ambient_strength=0.2, linear=0.02,
+                          quadratic=0.002),
+               models=lambda: [ref.Model.load_model(cube_path(5)) @ T.scale(0.5) @ T.rotate_xyz((20, 30, 10)),
+                               decal(ref, -1.5, 1.0, -0.5, 1.2, 0.8), floor(ref), decal(ref, -0.5, 1.5, -0.9, 0.6, -0.6)])
     yield dict(name='g9_diablo_transformed', resolution=(180, 240), system='LH', subsystem='OPENGL', camera=CAM,
                debug_camera=DCAM, light=dict(LIGHT, position=[-1.5, 2.5, 2.0]),
                models=lambda: [diablo(ref, True, 8) @ T.scale(0.8) @ T.translation((0.1, 0.0, -0.2))
                                @ T.rotate_xyz((0, 25, 0)), floor(ref, 8)])
+
+
+def decal(ref, x0, x1, y0, y1, z):
+    """Double-sided quad in the plane z = const (one side survives culling) that is z-TESTED but never writes z:
+    Model(depth_test=False), core.py:232-236 / triangular.py:117."""
+    v = np.array([[x0, y0, z, 1], [x1, y0, z, 1], [x1, y1, z, 1], [x0, y1, z, 1]], np.float32)
+    uv = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]], np.float32)
+    n = np.array([[0, 0, 1]], np.float32)
+    tris = [(0, 1, 2), (0, 2, 3), (0, 2, 1), (0, 3, 2)]
+    f = np.zeros((4, 3, 4), np.int32)
+    for i, t in enumerate(tris):
+        f[i, :, 0] = f[i, :, 1] = t
+    return ref.Model(v, uv, n, f, depth_test=False)
 
 
 def texture_u8(arr):
@@ -237,7 +263,7 @@ def dump_model(prefix, m, out):
                 meta = arr.dtype.metadata or {}
                 rec[attr] = dict(key=key, signed=bool(signed), tangent=bool(meta.get('tangent', False)))
         mats.append(rec)
-    return dict(groups=list(m.material_group), mats=mats, clip=bool(m.clip))
+    return dict(groups=list(m.material_group), mats=mats, clip=bool(m.clip), depth_test=bool(m.depth_test))
 
 
 def generate(spec, ref):

@@ -100,6 +100,7 @@ typedef struct {
     int32_t* winner1; /* (H,W) last face that coloured the pixel in pass 1 */
     int32_t* winner3; /* (H,W) last face that coloured the pixel in pass 3 */
     float lut_unorm[256], lut_snorm[256];
+    int index_error;  /* a texture lookup fell outside its map: the reference raises IndexError (core.py:138-173) */
 } ctx_t;
 
 static inline double load_real(const void* base, int dtype, int64_t idx) {
@@ -166,9 +167,10 @@ static void get_uv_texel(const ctx_t* C, const b2r_texture_desc* T, const double
     int32_t r = (int32_t)(rv * (T->height - 1));
     if (c < 0) c += T->width;
     if (r < 0) r += T->height;
-    if (c < 0 || c >= T->width) c = 0;   /* IndexError in the reference */
-    if (r < 0 || r >= T->height) r = 0;
-    (void)C;
+    /* below -size NumPy's fancy indexing raises IndexError (NaN: astype(int32) gives INT_MIN): remembered, the
+     * render still completes so that the planes can be inspected */
+    if (c < 0 || c >= T->width || cu != cu) { c = 0; ((ctx_t*)C)->index_error = 1; }
+    if (r < 0 || r >= T->height || rv != rv) { r = 0; ((ctx_t*)C)->index_error = 1; }
     *row = r; *col = c;
 }
 static inline void texel_f32(const ctx_t* C, const b2r_texture_desc* T, int row, int col, float out[3]) {
@@ -715,7 +717,7 @@ int orc_render_view(const b2r_model_desc* models, int32_t n_models, const b2r_te
     if (out_winner1) memcpy(out_winner1, C.winner1, (size_t)npx * sizeof(int32_t));
     if (out_frame_f32) memcpy(out_frame_f32, C.frame, (size_t)npx * 3 * sizeof(float));
     free(C.frame); free(C.z); free(C.stencil); free(C.winner1); free(C.winner3);
-    return 0;
+    return C.index_error ? 2 : 0;  /* 2: the reference would have raised IndexError */
 }
 
 /* n_views frames, views rendered concurrently on `threads` host threads (frames are independent: this is how
@@ -724,7 +726,7 @@ typedef struct {
     const b2r_model_desc* models; int32_t n_models; const b2r_texture_desc* textures; int32_t n_textures;
     const b2r_cubemap_desc* sky; const b2r_frame_params* fp; const b2r_view* views; int32_t n_views;
     uint8_t* out_rgb; double* out_z; int16_t* out_stencil; int32_t* out_winner; uint8_t* face_status; int32_t* n_sil;
-    int total_faces; int next; pthread_mutex_t lock;
+    int total_faces; int next; int rc; pthread_mutex_t lock;
 } job_t;
 
 static void* worker(void* arg) {
@@ -735,12 +737,13 @@ static void* worker(void* arg) {
         int v = J->next++;
         pthread_mutex_unlock(&J->lock);
         if (v >= J->n_views) break;
-        orc_render_view(J->models, J->n_models, J->textures, J->n_textures, J->sky, J->fp, J->views + v,
+        const int rc = orc_render_view(J->models, J->n_models, J->textures, J->n_textures, J->sky, J->fp, J->views + v,
                         J->out_rgb + (int64_t)v * npx * 3, J->out_z ? J->out_z + (int64_t)v * npx : 0,
                         J->out_stencil ? J->out_stencil + (int64_t)v * npx : 0,
                         J->out_winner ? J->out_winner + (int64_t)v * npx : 0,
                         J->face_status ? J->face_status + (int64_t)v * J->total_faces : 0,
                         J->n_sil ? J->n_sil + (int64_t)v * J->n_models : 0, 0, 0);
+        if (rc) { pthread_mutex_lock(&J->lock); J->rc = rc; pthread_mutex_unlock(&J->lock); }
     }
     return 0;
 }
@@ -757,11 +760,11 @@ int orc_render(const b2r_model_desc* models, int32_t n_models, const b2r_texture
     for (int mi = 0; mi < n_models; ++mi) J.total_faces += models[mi].n_faces;
     pthread_mutex_init(&J.lock, 0);
     if (threads > n_views) threads = n_views;
-    if (threads <= 1) { worker(&J); return 0; }
+    if (threads <= 1) { worker(&J); return J.rc; }
     pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)threads);
     for (int t = 0; t < threads; ++t) pthread_create(&th[t], 0, worker, &J);
     for (int t = 0; t < threads; ++t) pthread_join(th[t], 0);
     free(th);
     pthread_mutex_destroy(&J.lock);
-    return 0;
+    return J.rc;
 }

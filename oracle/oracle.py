@@ -52,6 +52,8 @@ def render_packed(packed, fp, views, threads=1, planes=True):
     rc = lib().orc_render(packed.models, C.c_int32(packed.n_models), packed.textures, C.c_int32(packed.n_textures),
                           packed.sky_ptr, C.byref(fp), views, C.c_int32(n), _ptr(rgb), _ptr(z), _ptr(st), _ptr(win),
                           _ptr(status), _ptr(nsil), C.c_int32(threads))
+    if rc == 2:
+        raise IndexError("oracle: texture lookup out of range (the reference raises IndexError here)")
     if rc != 0:
         raise RuntimeError("oracle failed")
     return dict(rgb=rgb, z=z, stencil=st, winner=win, face_status=status[:, :packed.total_faces],
@@ -77,8 +79,10 @@ def render_scene(scene, cameras=None, threads=1, planes=True, extra=False):
     rgb = np.empty((H, W, 3), np.uint8); z = np.empty((H, W)); st = np.empty((H, W), np.int16)
     win = np.empty((H, W), np.int32); win1 = np.empty((H, W), np.int32); frame = np.empty((H, W, 3), np.float32)
     status = np.zeros(max(1, packed.total_faces), np.uint8); nsil = np.zeros(max(1, packed.n_models), np.int32)
-    lib().orc_render_view(packed.models, C.c_int32(packed.n_models), packed.textures, C.c_int32(packed.n_textures),
+    rc = lib().orc_render_view(packed.models, C.c_int32(packed.n_models), packed.textures, C.c_int32(packed.n_textures),
                           packed.sky_ptr, C.byref(fp), C.byref(views[0]), _ptr(rgb), _ptr(z), _ptr(st), _ptr(win),
                           _ptr(status), _ptr(nsil), _ptr(frame), _ptr(win1))
+    if rc == 2:
+        raise IndexError("oracle: texture lookup out of range (the reference raises IndexError here)")
     return dict(rgb=rgb, z=z, stencil=st, winner=win, winner1=win1, frame_f32=frame,
                 face_status=status[:packed.total_faces], n_silhouette=nsil[:packed.n_models])

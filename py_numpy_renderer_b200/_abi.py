@@ -13,7 +13,8 @@ from .constants import SYSTEM
 from .lightning import Lightning
 from .materials import Texture
 
-B2R_ABI_VERSION = 3
+B2R_ABI_VERSION = 4
+B2R_ERR_INDEX = 2
 B2R_F32, B2R_F64 = 0, 1
 B2R_TEX_UNORM, B2R_TEX_SNORM = 0, 1
 B2R_BG_COLOR, B2R_BG_CUBEMAP = 0, 1
@@ -107,10 +108,6 @@ class PackedScene:
         self.face_counts = []
         for mi, m in enumerate(models):
             md = self.models[mi]
-            if not m.depth_test:
-                raise NotImplementedError(
-                    "Model(depth_test=False) is order-dependent in the reference (SURVEY.md A.5) and is not "
-                    "supported by the order-independent device pipeline")
             v, md.vertex_dtype = _real(m.vertices, 'vertices')
             if v.ndim != 2 or v.shape[1] != 4:
                 raise ValueError("Model.vertices must have shape (V, 4)")
@@ -146,7 +143,7 @@ class PackedScene:
                     raise TypeError("tangent-space normal map needs vertex normals (core.py:193)")
             self.keep.append(mats)
             md.materials, md.n_materials = mats, len(slots)
-            md.clip, md.depth_test = int(bool(m.clip)), 1
+            md.clip, md.depth_test = int(bool(m.clip)), int(bool(m.depth_test))
         self.n_textures = len(self.textures_py)
         self.textures = (TextureDesc * max(1, self.n_textures))()
         for ti, t in enumerate(self.textures_py):

@@ -37,6 +37,8 @@ _SYMBOLS = {
     "b2r_last_error": (C.c_char_p, []),
     "b2r_init": (C.c_int, [C.c_int]),
     "b2r_shutdown": (C.c_int, []),
+    "b2r_current_device": (C.c_int, []),
+    "b2r_scene_set_silhouette": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32]),
     "b2r_scene_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "b2r_scene_destroy": (C.c_int, [C.c_void_p]),
     "b2r_scene_reset_silhouette": (C.c_int, [C.c_void_p]),
@@ -72,8 +74,16 @@ def load_obj(path):
     lib = load_library()
     o = ObjArrays()
     rc = lib.b2r_obj_load(os.fsencode(path), C.byref(o))
+    if rc == 2:
+        if os.path.isdir(path):
+            raise IsADirectoryError(path)
+        raise FileNotFoundError(path)
+    if rc == 3:  # the reference's np.array(tokens, dtype=np.int32) raises ValueError on a non-numeric index (core.py:72-74)
+        raise ValueError(f"malformed face statement in {path!r}")
+    if rc == 4:
+        raise MemoryError(path)
     if rc != 0:
-        raise FileNotFoundError(path) if rc == 2 else RuntimeError(f"b2r_obj_load({path!r}) failed ({rc})")
+        raise RuntimeError(f"b2r_obj_load({path!r}) failed ({rc})")
     try:
         def take(ptr, n, width, dtype):
             return np.ctypeslib.as_array(ptr, shape=(n, width)).astype(dtype, copy=True) if n else None
@@ -109,6 +119,8 @@ def load_library():
 
 
 def _check(rc):
+    if rc == _abi.B2R_ERR_INDEX:  # a texture lookup fell outside its map: the reference's fancy indexing raises here
+        raise IndexError("b2r: " + (load_library().b2r_last_error() or b"").decode())
     if rc != 0:
         raise RuntimeError("b2r: " + (load_library().b2r_last_error() or b"").decode())
 
@@ -117,9 +129,11 @@ def init(device=None):
     """Bind the library to a CUDA device (default: LOCAL_RANK or 0)."""
     global _inited_device
     lib = load_library()
+    explicit = device is not None
     if device is None:
         device = int(os.environ.get("LOCAL_RANK", "0")) if _inited_device is None else _inited_device
-    if _inited_device != device:
+    if explicit or _inited_device != device:
+        # creates the device's context on first use, afterwards only makes it the calling thread's current one
         _check(lib.b2r_init(int(device)))
         _inited_device = device
     return lib
@@ -189,6 +203,7 @@ class DeviceScene:
                                          p.n_textures, C.cast(p.sky_ptr, C.c_void_p) if p.sky is not None else None,
                                          C.byref(self.handle)))
         self.has_sky = skybox is not None
+        self.models_py = list(models)
         self.vertex_base = np.cumsum([0] + [int(m.n_vertices) for m in p.models[:p.n_models]])
 
     def close(self):
@@ -223,6 +238,13 @@ class DeviceScene:
         sel = owner[:n] == model_index
         base = int(self.vertex_base[model_index])
         return {(int(a) - base, int(b) - base) for a, b in pairs[:n][sel]}
+
+    def restore_silhouette(self, per_model_sets):
+        """Upload persistent silhouette sets (one set of local (a, b) pairs per model, None / empty = nothing)."""
+        pairs = [(int(a) + int(self.vertex_base[i]), int(b) + int(self.vertex_base[i]))
+                 for i, sset in enumerate(per_model_sets) if sset for a, b in sset]
+        arr = np.ascontiguousarray(np.array(pairs, np.int32).reshape(-1, 2))
+        _check(self.lib.b2r_scene_set_silhouette(self.handle, arr.ctypes.data, len(arr)))
 
     def pack(self, cameras, debug_cameras, light, resolution, system, background, persist_silhouette=False, band=None):
         """Host-side evaluation of the per-view constants (the reference's NumPy camera maths) -> (fp, views)."""

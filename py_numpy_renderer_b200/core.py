@@ -218,7 +218,7 @@ class Model:
             got = scene._silhouette_of(self)
             if got is not None:
                 return got
-        return set()
+        return set(getattr(self, '_silhouette_saved', None) or ())
 
 
 _MEMO = {}
@@ -379,6 +379,7 @@ class Scene:
         self.persist_silhouette = True   # Appendix B-3 behaviour; False = every render starts from an empty set
         self.verbose = True              # print the three per-model lines of core.py:634-636
         self._device = None
+        self._persist_dirty = False      # the device scene holds a persistent silhouette the host has not seen
 
     def add_model(self, model: Model):
         self.models.append(model)
@@ -387,7 +388,14 @@ class Scene:
 
     # -- device plumbing ---------------------------------------------------------------------------------------
     def _invalidate_device(self):
+        """The device mirror is rebuilt after `model @ M`, `textures.register`, `add_model`.  In the reference
+        `model.silhouette` lives on the Model and survives all of these (core.py:251), so the persistent set is read
+        back here and restored into the new device scene."""
         if self._device is not None:
+            if self._persist_dirty:
+                for i, m in enumerate(self._device.models_py):
+                    m._silhouette_saved = self._device.silhouette_of(i)
+                self._persist_dirty = False
             self._device.close()
             self._device = None
 
@@ -395,6 +403,10 @@ class Scene:
         from . import _native
         if self._device is None:
             self._device = _native.DeviceScene(self.models, self.skybox if isinstance(self.skybox, CubeMap) else None)
+            saved = [getattr(m, '_silhouette_saved', None) for m in self.models]
+            if any(saved):
+                self._device.restore_silhouette(saved)
+                self._persist_dirty = True
         return self._device
 
     def _silhouette_of(self, model):
@@ -421,6 +433,7 @@ class Scene:
         mode = 'overlay' if lines else (True if debug is not None else ('status' if self.verbose else False))
         frames, info = dev.render([self.camera], [self.debug_camera], self.light, self.resolution, self.system,
                                   self._background(), persist_silhouette=self.persist_silhouette, want_debug=mode)
+        self._persist_dirty = self._persist_dirty or bool(self.persist_silhouette)
         if isinstance(self.skybox, CubeMap):
             # fill_frame_from_skybox zeroes the translation row of the *cached* camera.lookat in place
             # (cube_map.py:94-96, Appendix B-3); keep the side effect for callers that look at it afterwards.

@@ -4,10 +4,13 @@
 // are only known on the device (silhouette length, tile-list totals) stay on the device (grid-stride kernels read
 // them), with capacity overflow reported through a flag that is read back with the frame.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -19,7 +22,19 @@ namespace {
 
 thread_local std::string t_error;
 
-struct Globals {
+constexpr int MAX_FLAG_VIEWS = 4096;
+constexpr int N_TICKET_SLOTS = 4;
+constexpr int FLAG_REGIONS = N_TICKET_SLOTS + 2;   // + one for synchronous host renders, one scratch region (device-out)
+constexpr int STICKY_SLOTS = 1024;
+constexpr int STICKY_INTS = 4;                     // need_tri, need_quad, texture-index error, pad
+constexpr int REGION_INTS = 2 * MAX_FLAG_VIEWS + 16;  // 2 ints per view + [2*MAX_FLAG_VIEWS] = texture-index error word
+
+// Everything the library owns on ONE CUDA device: streams, events, pinned staging.  There is no process-global
+// render state: b2r_init(device) creates (or selects) the context of that device, a scene is bound to the context it
+// was created on, and two scenes on two devices can live -- and render from two threads -- in one process.  Entry
+// points lock the context they act on.
+struct Context {
+    std::recursive_mutex mu;
     bool ready = false;
     int device = -1;
     int sm_count = 148;
@@ -28,8 +43,10 @@ struct Globals {
     bool timing = false;
     int n_stage = 0;
     const char* stage_name[B2R_MAX_STAGES];
-    cudaEvent_t stage_ev[B2R_MAX_STAGES + 1];
-    int* pinned_flags = nullptr;  // overflow read-back, 2 ints per view
+    cudaEvent_t stage_ev[B2R_MAX_STAGES + 1] = {};
+    int* pinned_flags = nullptr;  // overflow read-back, FLAG_REGIONS x (2 ints per view)
+    int* sticky = nullptr;        // pinned, STICKY_SLOTS x STICKY_INTS: "a tile list overflowed" per scene, survives until b2r_sync
+    std::vector<int> sticky_free;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_done = nullptr;
     static constexpr int N_AUX = 3;   // sub-chunks of one batch render concurrently: the long tail of a raster launch
@@ -48,21 +65,36 @@ struct Globals {
     // stream, i.e. serialise the host with the previous chunk / previous asynchronous call
     struct Staging { ViewDev* host = nullptr; size_t cap = 0; cudaEvent_t done = nullptr; bool used = false; } stage[4];
     unsigned stage_next = 0;
-    // host-asynchronous renders (out_on_device == 2): ticket t uses slot t % 4 for its events and overflow flags
+    // host-asynchronous renders (out_on_device == 2) -- and only those -- take a ticket; ticket t lives in slot t % 4
+    // until b2r_wait(t) or until the slot is needed again (it is then completed first, its outcome remembered)
     long long ticket = 0;
-    cudaEvent_t ticket_copy[4] = {}, ticket_compute[4] = {};
-    int ticket_views[4] = {};
-    struct b2r_scene* ticket_scene[4] = {};
-    long long rgb_last_ticket[2] = {-1, -1};  // which ticket last copied out of rgb[slot]
-    int pending_views = 0;        // asynchronous render whose overflow flags were not checked yet
-    int* pending_flags = nullptr;
-    struct b2r_scene* pending_scene = nullptr;
-} g;
-constexpr int MAX_FLAG_VIEWS = 4096;
+    struct TicketSlot { long long id = 0; bool open = false; int views = 0; struct b2r_scene* scene = nullptr;
+                        cudaEvent_t copy = nullptr, compute = nullptr; } tk[N_TICKET_SLOTS];
+    std::map<long long, std::string> late_fail;  // tickets completed at slot reuse that had failed
+    std::vector<struct b2r_scene*> pending;      // scenes with device-resident renders since the last b2r_sync
+};
+
+constexpr int MAX_DEVICES = 64;
+std::mutex g_table_mu;
+Context* g_ctx[MAX_DEVICES] = {};
+std::atomic<int> g_last_device{-1};
+thread_local int t_device = -1;
+
+// the context of the calling thread: the device it last passed to b2r_init, else the most recently initialised one
+Context* current_ctx() {
+    const int d = t_device >= 0 ? t_device : g_last_device.load();
+    if (d < 0 || d >= MAX_DEVICES) return nullptr;
+    Context* c = g_ctx[d];
+    return (c && c->ready) ? c : nullptr;
+}
 
 int fail(const std::string& msg) {
     t_error = msg;
     return 1;
+}
+int fail_index() {  // the reference raises IndexError: a texture lookup below -size (core.py:138-143, 162-173)
+    t_error = "texture lookup out of range (UV < -1): index out of bounds";
+    return B2R_ERR_INDEX;
 }
 #define CK(call)                                                                                        \
     do {                                                                                                \
@@ -71,6 +103,12 @@ int fail(const std::string& msg) {
             return fail(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" +   \
                         std::to_string(__LINE__) + ")");                                                \
     } while (0)
+// entry points without a scene argument act on the calling thread's context
+#define CTX_OR_FAIL()                                                     \
+    Context* cxp_ = current_ctx();                                        \
+    if (!cxp_) return fail("b2r_init was not called");                    \
+    Context& g = *cxp_;                                                   \
+    std::lock_guard<std::recursive_mutex> lock_(g.mu)
 
 template <class T>
 struct DevBuf {
@@ -93,7 +131,7 @@ struct DevBuf {
     size_t bytes() const { return n * sizeof(T); }
 };
 
-void stage_mark(const char* name) {
+void stage_mark(Context& g, const char* name) {
     if (!g.timing || g.n_stage >= B2R_MAX_STAGES) return;
     g.stage_name[g.n_stage] = name;
     cudaEventRecord(g.stage_ev[g.n_stage + 1], g.stream);
@@ -103,6 +141,9 @@ void stage_mark(const char* name) {
 }  // namespace
 
 struct b2r_scene {
+    Context* cx = nullptr;   // the device context this scene lives on
+    int sticky_slot = -1;    // index into cx->sticky (overflow flags of device-resident renders)
+    bool in_pending = false;
     // static geometry
     DevBuf<double4> pos;
     DevBuf<double2> uv;
@@ -118,6 +159,7 @@ struct b2r_scene {
     DevBuf<int> edge_ptr, edge_inc, edge_model;
     DevBuf<int8_t> sil_state;
     int n_faces = 0, n_edges = 0, n_models = 0;
+    bool has_no_zwrite = false;  // some model has depth_test == False
     std::vector<int> model_faces;
     size_t static_bytes = 0;
     // per-render scratch (grown on demand)
@@ -135,6 +177,9 @@ struct b2r_scene {
     DevBuf<float> frame_f32;
     DevBuf<uint8_t> status;
     DevBuf<uint8_t> rgb[2];  // device staging of host-bound frames, alternating so that copies of call t overlap call t+1
+    cudaEvent_t rgb_copied[2] = {nullptr, nullptr};  // the frames of the host render that last used rgb[i] have left it
+    bool rgb_used[2] = {false, false};
+    unsigned host_seq = 0;   // host-bound renders of this scene so far (selects rgb[host_seq & 1])
     int tri_cap = 0, quad_cap = 0;  // per-view capacity of the tile lists (grown after an overflow)
 
     SceneDev dev() const {
@@ -147,6 +192,7 @@ struct b2r_scene {
 };
 
 static void b2r_scene_grow_lists(struct b2r_scene* sc, int need_tri, int need_quad);
+static int b2r_scene_check_sticky(struct b2r_scene* sc);
 
 extern "C" {
 
@@ -154,109 +200,180 @@ int b2r_abi_version(void) { return B2R_ABI_VERSION; }
 const char* b2r_last_error(void) { return t_error.c_str(); }
 
 int b2r_init(int device) {
-    if (g.ready && g.device == device) return 0;
+    if (device < 0 || device >= MAX_DEVICES) return fail("device index out of range");
+    std::lock_guard<std::mutex> table_lock(g_table_mu);
+    if (g_ctx[device] && g_ctx[device]->ready) { t_device = device; g_last_device = device; return 0; }
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
         return fail(std::string("no CUDA device available (") + cudaGetErrorString(e) +
                     "); this library has no CPU fallback");
-    if (device < 0 || device >= count) return fail("device index out of range");
+    if (device >= count) return fail("device index out of range");
     CK(cudaSetDevice(device));
+    if (!g_ctx[device]) g_ctx[device] = new Context();
+    Context& g = *g_ctx[device];
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     g.sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     for (int i = 0; i <= B2R_MAX_STAGES; ++i) CK(cudaEventCreate(&g.stage_ev[i]));
-    CK(cudaMallocHost(&g.pinned_flags, sizeof(int) * 2 * MAX_FLAG_VIEWS * 4));
-    for (int i = 0; i < 4; ++i) {
-        CK(cudaEventCreateWithFlags(&g.ticket_copy[i], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&g.ticket_compute[i], cudaEventDisableTiming));
+    CK(cudaMallocHost(&g.pinned_flags, sizeof(int) * REGION_INTS * FLAG_REGIONS));
+    std::memset(g.pinned_flags, 0, sizeof(int) * REGION_INTS * FLAG_REGIONS);
+    CK(cudaMallocHost(&g.sticky, sizeof(int) * STICKY_INTS * STICKY_SLOTS));
+    std::memset(g.sticky, 0, sizeof(int) * STICKY_INTS * STICKY_SLOTS);
+    g.sticky_free.clear();
+    for (int i = STICKY_SLOTS - 1; i >= 0; --i) g.sticky_free.push_back(i);
+    for (int i = 0; i < N_TICKET_SLOTS; ++i) {
+        CK(cudaEventCreateWithFlags(&g.tk[i].copy, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&g.tk[i].compute, cudaEventDisableTiming));
     }
     CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&g.chunk_done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&g.setup_done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&g.tri_done, cudaEventDisableTiming));
     CK(cudaStreamCreateWithFlags(&g.fork_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < Globals::N_AUX; ++i) CK(cudaStreamCreateWithFlags(&g.aux[i], cudaStreamNonBlocking));
+    for (int i = 0; i < Context::N_AUX; ++i) CK(cudaStreamCreateWithFlags(&g.aux[i], cudaStreamNonBlocking));
     for (int i = 0; i < 16; ++i) CK(cudaEventCreateWithFlags(&g.aux_done[i], cudaEventDisableTiming));
     if (const char* hc = std::getenv("B2R_HOST_CHUNK")) g.host_chunk = std::max(1, std::atoi(hc));
     if (const char* dc = std::getenv("B2R_DEV_CHUNK")) g.dev_chunk = std::max(1, std::atoi(dc));
     if (const char* ac = std::getenv("B2R_ASYNC_CHUNK")) g.async_chunk = std::max(1, std::atoi(ac));
-    if (const char* a = std::getenv("B2R_AUX_HOST")) g.aux_host = std::min(Globals::N_AUX, std::max(1, std::atoi(a)));
+    if (const char* a = std::getenv("B2R_AUX_HOST")) g.aux_host = std::min(Context::N_AUX, std::max(1, std::atoi(a)));
     if (const char* a = std::getenv("B2R_TRI_CAP")) g.init_tri_cap = std::max(1, std::atoi(a));
     if (const char* a = std::getenv("B2R_QUAD_CAP")) g.init_quad_cap = std::max(1, std::atoi(a));
     if (const char* a = std::getenv("B2R_BIN_BLOCKS")) g.bin_blocks = std::max(1, std::atoi(a));
     if (const char* a = std::getenv("B2R_BIN_SHARE")) g.bin_share = std::max(1, std::atoi(a));
-    if (const char* a = std::getenv("B2R_AUX_DEV")) g.aux_dev = std::min(Globals::N_AUX, std::max(1, std::atoi(a)));
+    if (const char* a = std::getenv("B2R_AUX_DEV")) g.aux_dev = std::min(Context::N_AUX, std::max(1, std::atoi(a)));
     float lut[2][256];
     for (int i = 0; i < 256; ++i) {  // core.py:96-104: f32(u8/255), f32(u8/255*2-1) with float64 intermediates
         const double t = (double)i / 255;
         lut[0][i] = (float)t;
         lut[1][i] = (float)(t * 2 - 1);
     }
-    CK(cudaMemcpyToSymbol(c_lut, lut, sizeof(lut)));
+    CK(cudaMemcpyToSymbol(c_lut, lut, sizeof(lut)));  // __constant__ symbols are per device: uploaded for every context
     g.device = device;
     g.ready = true;
     g.launches = 0;
+    t_device = device;
+    g_last_device = device;
     return 0;
 }
 
+// Releases every context: all streams are drained first, then every resource b2r_init / b2r_render created is
+// destroyed.  Scenes must be destroyed before (a scene outliving its context only frees its own allocations).
 int b2r_shutdown(void) {
-    if (!g.ready) return 0;
-    cudaStreamSynchronize(g.stream);
-    cudaStreamDestroy(g.stream);
-    cudaStreamDestroy(g.copy_stream);
-    cudaEventDestroy(g.chunk_done);
-    cudaEventDestroy(g.tri_done);
-    cudaStreamDestroy(g.fork_stream);
-    for (int i = 0; i <= B2R_MAX_STAGES; ++i) cudaEventDestroy(g.stage_ev[i]);
-    cudaFreeHost(g.pinned_flags);
-    g = Globals();
+    std::lock_guard<std::mutex> table_lock(g_table_mu);
+    for (int d = 0; d < MAX_DEVICES; ++d) {
+        Context* c = g_ctx[d];
+        if (!c) continue;
+        {
+            std::lock_guard<std::recursive_mutex> lock(c->mu);
+            Context& g = *c;
+            if (g.ready) {
+                cudaSetDevice(g.device);
+                cudaStreamSynchronize(g.stream); cudaStreamSynchronize(g.copy_stream); cudaStreamSynchronize(g.fork_stream);
+                for (int i = 0; i < Context::N_AUX; ++i) cudaStreamSynchronize(g.aux[i]);
+                cudaStreamDestroy(g.stream); cudaStreamDestroy(g.copy_stream); cudaStreamDestroy(g.fork_stream);
+                for (int i = 0; i < Context::N_AUX; ++i) cudaStreamDestroy(g.aux[i]);
+                cudaEventDestroy(g.chunk_done); cudaEventDestroy(g.setup_done); cudaEventDestroy(g.tri_done);
+                for (int i = 0; i < 16; ++i) cudaEventDestroy(g.aux_done[i]);
+                for (int i = 0; i <= B2R_MAX_STAGES; ++i) cudaEventDestroy(g.stage_ev[i]);
+                for (int i = 0; i < N_TICKET_SLOTS; ++i) { cudaEventDestroy(g.tk[i].copy); cudaEventDestroy(g.tk[i].compute); }
+                for (auto& st : g.stage) { if (st.host) cudaFreeHost(st.host); if (st.done) cudaEventDestroy(st.done); }
+                cudaFreeHost(g.pinned_flags);
+                cudaFreeHost(g.sticky);
+                g.ready = false;
+            }
+        }
+        delete c;
+        g_ctx[d] = nullptr;
+    }
+    g_last_device = -1;
+    t_device = -1;
     return 0;
+}
+
+int b2r_current_device(void) {
+    Context* c = current_ctx();
+    return c ? c->device : -1;
+}
+
+static int check_overflow_flags(const int* flags, int n_views, struct b2r_scene* sc) {
+    int need_tri = 0, need_quad = 0;
+    for (int i = 0; i < n_views; ++i) { need_tri = std::max(need_tri, flags[2 * i]); need_quad = std::max(need_quad, flags[2 * i + 1]); }
+    if (!need_tri && !need_quad) return flags[2 * MAX_FLAG_VIEWS] ? fail_index() : 0;
+    b2r_scene_grow_lists(sc, need_tri, need_quad);
+    return fail("tile list capacity overflow in an asynchronous render: affected frames show background only; "
+                "capacity was raised, render again");
 }
 
 int b2r_sync(void) {
-    if (!g.ready) return fail("b2r_init was not called");
+    CTX_OR_FAIL();
     CK(cudaSetDevice(g.device));
     CK(cudaStreamSynchronize(g.stream));
     CK(cudaStreamSynchronize(g.copy_stream));
-    if (g.pending_views > 0) {  // an asynchronous render ran since the last check: did its tile lists fit?
-        int need_tri = 0, need_quad = 0;
-        for (int i = 0; i < g.pending_views; ++i) { need_tri = std::max(need_tri, g.pending_flags[2 * i]); need_quad = std::max(need_quad, g.pending_flags[2 * i + 1]); }
-        g.pending_views = 0;
-        if (need_tri || need_quad) {
-            b2r_scene_grow_lists(g.pending_scene, need_tri, need_quad);
-            return fail("tile list capacity overflow in an asynchronous render: affected frames show background only; "
-                        "capacity was raised, render again");
-        }
-    }
-    return 0;
+    // device-resident renders since the last sync: the per-scene sticky flags say whether every tile list fitted
+    int rc = 0;
+    for (b2r_scene* sc : g.pending) rc |= b2r_scene_check_sticky(sc);
+    g.pending.clear();
+    return rc;
 }
-int64_t b2r_last_ticket(void) { return (int64_t)g.ticket; }
+int64_t b2r_last_ticket(void) {
+    Context* c = current_ctx();
+    return c ? (int64_t)c->ticket : 0;
+}
+
+// completes the ticket held by a slot: waits for its copies and kernels (context lock dropped meanwhile when `lk`
+// is given), checks the overflow flags.  Returns 0 / 1 like an entry point.
+static int finish_ticket_slot(Context& g, int tslot, std::unique_lock<std::recursive_mutex>* lk) {
+    Context::TicketSlot& T = g.tk[tslot];
+    if (!T.open) return 0;
+    const long long id = T.id;
+    cudaEvent_t ev_copy = T.copy, ev_compute = T.compute;
+    if (lk) lk->unlock();
+    cudaError_t e1 = cudaEventSynchronize(ev_copy), e2 = cudaEventSynchronize(ev_compute);
+    if (lk) lk->lock();
+    if (!T.open || T.id != id) {   // someone else completed it meanwhile
+        auto it = g.late_fail.find(id);
+        if (it == g.late_fail.end()) return 0;
+        const std::string msg = it->second;
+        g.late_fail.erase(it);
+        return fail(msg);
+    }
+    T.open = false;
+    if (e1 != cudaSuccess || e2 != cudaSuccess)
+        return fail(std::string("asynchronous render failed: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    const int* flags = g.pinned_flags + (size_t)tslot * REGION_INTS;
+    return check_overflow_flags(flags, T.views, T.scene);
+}
+
 int b2r_wait(int64_t ticket) {
-    if (!g.ready) return fail("b2r_init was not called");
+    Context* cxp = current_ctx();
+    if (!cxp) return fail("b2r_init was not called");
+    Context& g = *cxp;
+    std::unique_lock<std::recursive_mutex> lk(g.mu);
     if (ticket <= 0 || ticket > g.ticket) return fail("b2r_wait: unknown ticket");
-    if (g.ticket - ticket >= 4) return 0;  // long gone: its slot has been reused, so it was complete
     CK(cudaSetDevice(g.device));
-    const int tslot = (int)(ticket & 3);
-    CK(cudaEventSynchronize(g.ticket_copy[tslot]));
-    CK(cudaEventSynchronize(g.ticket_compute[tslot]));
-    const int* flags = g.pinned_flags + (size_t)tslot * 2 * MAX_FLAG_VIEWS;
-    int need_tri = 0, need_quad = 0;
-    for (int i = 0; i < g.ticket_views[tslot]; ++i) { need_tri = std::max(need_tri, flags[2 * i]); need_quad = std::max(need_quad, flags[2 * i + 1]); }
-    g.ticket_views[tslot] = 0;
-    if (need_tri || need_quad) {
-        b2r_scene_grow_lists(g.ticket_scene[tslot], need_tri, need_quad);
-        return fail("tile list capacity overflow in an asynchronous render: affected frames show background only; "
-                    "capacity was raised, render again");
-    }
-    return 0;
+    const int tslot = (int)(ticket % N_TICKET_SLOTS);
+    if (g.tk[tslot].open && g.tk[tslot].id == ticket) return finish_ticket_slot(g, tslot, &lk);
+    // already completed: by an earlier b2r_wait, or because its slot was needed again (outcome remembered)
+    auto it = g.late_fail.find(ticket);
+    if (it == g.late_fail.end()) return 0;
+    const std::string msg = it->second;
+    g.late_fail.erase(it);
+    return fail(msg);
 }
-void* b2r_stream(void) { return (void*)g.stream; }
-int64_t b2r_launch_count(void) { return (int64_t)g.launches; }
+void* b2r_stream(void) {
+    Context* c = current_ctx();
+    return c ? (void*)c->stream : nullptr;
+}
+int64_t b2r_launch_count(void) {
+    Context* c = current_ctx();
+    return c ? (int64_t)c->launches : 0;
+}
 // Work counters of a -DB2R_STATS build (all zero otherwise): copies 16 values, optionally resets them.
 int b2r_debug_stats(unsigned long long* out16, int reset) {
-    if (!g.ready) return fail("b2r_init was not called");
+    CTX_OR_FAIL();
+    CK(cudaSetDevice(g.device));
     CK(cudaStreamSynchronize(g.stream));
     CK(cudaMemcpyFromSymbol(out16, g_stats, sizeof(unsigned long long) * 16));
     if (reset) { unsigned long long z[16] = {0}; CK(cudaMemcpyToSymbol(g_stats, z, sizeof(z))); }
@@ -264,7 +381,7 @@ int b2r_debug_stats(unsigned long long* out16, int reset) {
 }
 // ---- multi-GPU output window: CUDA IPC export / import of the assembling rank's frame buffer ----
 int b2r_window_create(int64_t bytes, void** dev_ptr, void* handle_out) {
-    if (!g.ready) return fail("b2r_init was not called");
+    CTX_OR_FAIL();
     if (bytes <= 0 || !dev_ptr || !handle_out) return fail("b2r_window_create: bad arguments");
     static_assert(sizeof(cudaIpcMemHandle_t) == B2R_WINDOW_HANDLE_BYTES, "IPC handle size");
     CK(cudaSetDevice(g.device));
@@ -278,7 +395,7 @@ int b2r_window_create(int64_t bytes, void** dev_ptr, void* handle_out) {
     return 0;
 }
 int b2r_window_open(const void* handle, void** dev_ptr) {
-    if (!g.ready) return fail("b2r_init was not called");
+    CTX_OR_FAIL();
     if (!handle || !dev_ptr) return fail("b2r_window_open: bad arguments");
     CK(cudaSetDevice(g.device));
     cudaIpcMemHandle_t h;
@@ -297,8 +414,16 @@ int b2r_window_destroy(void* dev_ptr) {
     return 0;
 }
 
-int b2r_set_stage_timing(int enabled) { g.timing = enabled != 0; return 0; }
+int b2r_set_stage_timing(int enabled) {
+    CTX_OR_FAIL();
+    g.timing = enabled != 0;
+    return 0;
+}
 int b2r_last_stage_ms(const char** names, float* ms) {
+    Context* cxp = current_ctx();
+    if (!cxp) return 0;
+    Context& g = *cxp;
+    std::lock_guard<std::recursive_mutex> lock(g.mu);
     for (int i = 0; i < g.n_stage; ++i) {
         names[i] = g.stage_name[i];
         ms[i] = 0.f;
@@ -313,15 +438,16 @@ static inline double load_real(const void* base, int dtype, size_t idx) {
 
 int b2r_scene_create(const b2r_model_desc* models, int32_t n_models, const b2r_texture_desc* textures,
                      int32_t n_textures, const b2r_cubemap_desc* skybox, b2r_scene** out_scene) {
-    if (!g.ready) return fail("b2r_init was not called");
+    CTX_OR_FAIL();
     if (!out_scene) return fail("out_scene is NULL");
     CK(cudaSetDevice(g.device));
     b2r_scene* sc = new b2r_scene();
+    sc->cx = &g;
     sc->n_models = n_models;
     size_t nv = 0, nt = 0, nn = 0, nf = 0, nm = 0;
     for (int i = 0; i < n_models; ++i) {
         const b2r_model_desc& m = models[i];
-        if (!m.depth_test) { delete sc; return fail("Model.depth_test=False is order dependent; not supported"); }
+        if (!m.depth_test) sc->has_no_zwrite = true;
         if (!m.vertices || !m.faces || m.n_vertices <= 0) { delete sc; return fail("model without vertices/faces"); }
         nv += m.n_vertices; nt += m.uv ? m.n_uv : 0; nn += m.normals ? m.n_normals : 0; nf += m.n_faces;
         nm += std::max(1, m.n_materials);
@@ -362,7 +488,7 @@ int b2r_scene_create(const b2r_model_desc* models, int32_t n_models, const b2r_t
         }
         const int base_flags = (m.clip ? FS_CLIP : 0) | (m.vertex_dtype == B2R_F32 ? FS_VTX_F32 : 0) |
                                (m.uv ? FS_HAS_UV : 0) | (m.uv && m.uv_dtype == B2R_F32 ? FS_UV_F32 : 0) |
-                               (m.normals ? FS_HAS_NORMALS : 0);
+                               (m.normals ? FS_HAS_NORMALS : 0) | (m.depth_test ? 0 : FS_NO_ZWRITE);
         auto wrap = [](int idx, int n) { if (idx < 0) idx += n; return (idx < 0 || idx >= n) ? 0 : idx; };
         for (size_t f = 0; f < (size_t)m.n_faces; ++f) {
             const int32_t* r = m.faces + f * 12;
@@ -465,16 +591,28 @@ int b2r_scene_create(const b2r_model_desc* models, int32_t n_models, const b2r_t
     cudaMemsetAsync(sc->sil_state.p, 0, std::max(1, sc->n_edges), g.stream);
     cudaError_t e = cudaStreamSynchronize(g.stream);  // staging vectors die here
     if (e != cudaSuccess) { b2r_scene_destroy(sc); return fail(std::string("scene upload: ") + cudaGetErrorString(e)); }
+    for (int i = 0; i < 2; ++i)
+        if (cudaEventCreateWithFlags(&sc->rgb_copied[i], cudaEventDisableTiming) != cudaSuccess) { b2r_scene_destroy(sc); return fail("event create"); }
     *out_scene = sc;
     return 0;
 }
 
 int b2r_scene_destroy(b2r_scene* sc) {
     if (!sc) return 0;
-    if (g.ready) cudaSetDevice(g.device);
-    if (g.ready) { cudaStreamSynchronize(g.stream); cudaStreamSynchronize(g.copy_stream); }
-    if (g.pending_scene == sc) { g.pending_scene = nullptr; g.pending_views = 0; }
-    for (int i = 0; i < 4; ++i) if (g.ticket_scene[i] == sc) { g.ticket_scene[i] = nullptr; g.ticket_views[i] = 0; }
+    Context& g = *sc->cx;
+    std::lock_guard<std::recursive_mutex> lock_(g.mu);
+    if (g.ready) {
+        cudaSetDevice(g.device);
+        cudaStreamSynchronize(g.stream); cudaStreamSynchronize(g.copy_stream); cudaStreamSynchronize(g.fork_stream);
+        for (int i = 0; i < Context::N_AUX; ++i) cudaStreamSynchronize(g.aux[i]);
+        g.pending.erase(std::remove(g.pending.begin(), g.pending.end(), sc), g.pending.end());
+        for (int i = 0; i < N_TICKET_SLOTS; ++i)   // everything is drained: open tickets of this scene complete here
+            if (g.tk[i].open && g.tk[i].scene == sc) {
+                if (finish_ticket_slot(g, i, nullptr)) g.late_fail[g.tk[i].id] = t_error;
+            }
+        if (sc->sticky_slot >= 0) { for (int k = 0; k < STICKY_INTS; ++k) g.sticky[STICKY_INTS * sc->sticky_slot + k] = 0; g.sticky_free.push_back(sc->sticky_slot); }
+    }
+    for (int i = 0; i < 2; ++i) if (sc->rgb_copied[i]) cudaEventDestroy(sc->rgb_copied[i]);
     sc->pos.release(); sc->uv.release(); sc->nrm.release(); sc->faces.release(); sc->shade.release(); sc->mats.release(); sc->tex.release();
     for (uchar4* d : sc->tex_data) cudaFree(d);
     sc->sky.release(); sc->edge_v.release(); sc->edge_ptr.release(); sc->edge_inc.release(); sc->edge_model.release();
@@ -488,6 +626,9 @@ int b2r_scene_destroy(b2r_scene* sc) {
 
 int b2r_scene_reset_silhouette(b2r_scene* sc) {
     if (!sc) return fail("scene is NULL");
+    Context& g = *sc->cx;
+    std::lock_guard<std::recursive_mutex> lock_(g.mu);
+    CK(cudaSetDevice(g.device));
     CK(cudaMemsetAsync(sc->sil_state.p, 0, std::max(1, sc->n_edges), g.stream));
     return 0;
 }
@@ -497,6 +638,9 @@ int64_t b2r_scene_device_bytes(const b2r_scene* sc) { return sc ? (int64_t)sc->s
 // read the persistent silhouette back: out_pairs (n_edges, 2) GLOBAL vertex ids as stored (a,b); returns count
 int b2r_scene_get_silhouette(b2r_scene* sc, int32_t* out_pairs, int32_t* out_model, int32_t capacity) {
     if (!sc) return -1;
+    Context& g = *sc->cx;
+    std::lock_guard<std::recursive_mutex> lock_(g.mu);
+    if (cudaSetDevice(g.device) != cudaSuccess) return -1;
     std::vector<int8_t> st(std::max(1, sc->n_edges));
     std::vector<int2> ev(std::max(1, sc->n_edges));
     std::vector<int> em(std::max(1, sc->n_edges));
@@ -517,11 +661,48 @@ int b2r_scene_get_silhouette(b2r_scene* sc, int32_t* out_pairs, int32_t* out_mod
     return n;
 }
 
+int b2r_scene_set_silhouette(b2r_scene* sc, const int32_t* pairs, int32_t n) {
+    if (!sc || (n > 0 && !pairs)) return fail("b2r_scene_set_silhouette: bad arguments");
+    Context& g = *sc->cx;
+    std::lock_guard<std::recursive_mutex> lock_(g.mu);
+    CK(cudaSetDevice(g.device));
+    CK(cudaStreamSynchronize(g.stream));
+    const int E = sc->n_edges;
+    std::vector<int2> ev(std::max(1, E));
+    std::vector<int8_t> st(std::max(1, E), 0);
+    if (E > 0) CK(cudaMemcpy(ev.data(), sc->edge_v.p, (size_t)E * sizeof(int2), cudaMemcpyDeviceToHost));
+    std::map<std::pair<int, int>, int> index;
+    for (int e = 0; e < E; ++e) index[{ev[e].x, ev[e].y}] = e;
+    for (int i = 0; i < n; ++i) {
+        const int a = pairs[2 * i], b = pairs[2 * i + 1];
+        auto it = index.find({a, b});
+        if (it != index.end()) { st[it->second] = 1; continue; }   // stored as (lo, hi) of the canonical record
+        it = index.find({b, a});
+        if (it != index.end()) st[it->second] = 2;                 // stored reversed
+    }
+    if (E > 0) CK(cudaMemcpy(sc->sil_state.p, st.data(), (size_t)E, cudaMemcpyHostToDevice));
+    return 0;
+}
+
 }  // extern "C"
 static void b2r_scene_grow_lists(b2r_scene* sc, int need_tri, int need_quad) {
     if (!sc) return;
     if (need_tri) { sc->tri_cap = need_tri + need_tri / 4; sc->tri_list.release(); }
     if (need_quad) { sc->quad_cap = need_quad + need_quad / 4; sc->quad_list.release(); sc->pair_list.release(); }
+}
+// Device-resident renders only enqueue work; whether their tile lists fitted is known once the stream has drained.
+// k_scan leaves the required size in the scene's sticky pinned slot when a list overflows (in ANY call since the last
+// check -- a later, fitting call does not erase it).  Caller holds the context lock and has synchronised the stream.
+static int b2r_scene_check_sticky(b2r_scene* sc) {
+    if (!sc || sc->sticky_slot < 0) return 0;
+    sc->in_pending = false;
+    volatile int* st = sc->cx->sticky + STICKY_INTS * sc->sticky_slot;
+    const int need_tri = st[0], need_quad = st[1], bad_index = st[2];
+    st[0] = 0; st[1] = 0; st[2] = 0;
+    if (!need_tri && !need_quad) return bad_index ? fail_index() : 0;
+    b2r_scene_grow_lists(sc, need_tri, need_quad);
+    return fail("tile list capacity overflow in an asynchronous render: affected frames show background only; "
+                "capacity was raised, render again");
 }
 extern "C" {
 
@@ -578,8 +759,10 @@ static void make_view(const b2r_view& v, bool with_sky, ViewDev& D) {
 
 int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views, int32_t n_views, uint8_t* out_rgb,
                const b2r_debug_out* dbg, int32_t out_on_device) {
-    if (!g.ready) return fail("b2r_init was not called");
     if (!sc || !fp || !views || n_views <= 0 || !out_rgb) return fail("b2r_render: bad arguments");
+    Context& g = *sc->cx;
+    std::lock_guard<std::recursive_mutex> lock_(g.mu);
+    if (!g.ready) return fail("the scene's device context was shut down");
     CK(cudaSetDevice(g.device));  // the current device is per host thread; callers may render from a worker thread
     const int H = fp->height, W = fp->width;
     if (H <= 0 || W <= 0 || H > 32000 || W > 32000) return fail("resolution out of range");
@@ -610,7 +793,10 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
     Fr.n_faces = sc->n_faces;
     Fr.sky_size = sc->sky_size;
     Fr.want_status = want_status;
-    Fr.full_stencil = (dbg && dbg->stencil) ? 1 : 0;
+    Fr.err_flag = nullptr;  // set below, once the read-back region of this call is known
+    // stencil counts are only needed under faces -- which, with a Model(depth_test=False) around, is no longer the
+    // same as "pixels whose z-buffer was written": count everywhere then
+    Fr.full_stencil = ((dbg && dbg->stencil) || sc->has_no_zwrite) ? 1 : 0;
     const int n_tiles = Fr.tiles_x * Fr.tiles_y;
     const int F = sc->n_faces, E = std::max(1, sc->n_edges);
     const size_t npx = (size_t)H * W;
@@ -623,10 +809,38 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
     VB = std::min(VB, 64);
     const bool host_out = out_on_device != 1;
     const bool host_async = out_on_device == 2 && !dbg;
-    const long long ticket = ++g.ticket;
-    const int tslot = (int)(ticket & 3), rslot = (int)(ticket & 1);
-    int* const flags = g.pinned_flags + (size_t)tslot * 2 * MAX_FLAG_VIEWS;
     if (n_views > MAX_FLAG_VIEWS) return fail("too many views in one call (max 4096)");
+    // Overflow read-back region.  Host-asynchronous renders take a ticket (slot t % 4; a slot still held by an
+    // un-awaited ticket is completed first -- the host blocks here, i.e. at most four such calls are in flight);
+    // synchronous host renders use their own region (checked before this call returns); device-resident renders write
+    // a scratch region nobody reads and report through the scene's sticky flags at the next b2r_sync.
+    int tslot = -1;
+    long long ticket = 0;
+    if (host_async) {
+        ticket = ++g.ticket;
+        tslot = (int)(ticket % N_TICKET_SLOTS);
+        if (g.tk[tslot].open) {
+            const long long old = g.tk[tslot].id;
+            if (finish_ticket_slot(g, tslot, nullptr)) g.late_fail[old] = t_error;
+            if (g.late_fail.size() > 64) g.late_fail.erase(g.late_fail.begin());
+        }
+    }
+    int* const flags = g.pinned_flags + (size_t)(host_async ? tslot : ((host_out || dbg) ? N_TICKET_SLOTS : N_TICKET_SLOTS + 1)) * REGION_INTS;
+    int* sticky = nullptr;
+    if (!host_out && !dbg) {
+        if (sc->sticky_slot < 0) {
+            if (g.sticky_free.empty()) return fail("too many scenes with device-resident renders");
+            sc->sticky_slot = g.sticky_free.back();
+            g.sticky_free.pop_back();
+        }
+        sticky = g.sticky + STICKY_INTS * sc->sticky_slot;
+    }
+    // where the shader reports a texture lookup outside its map; the region's word is free again: its previous user
+    // (ticket / synchronous call) has completed
+    int* const err_flag = sticky ? sticky + 2 : flags + 2 * MAX_FLAG_VIEWS;
+    if (!sticky) *err_flag = 0;
+    const int rslot = host_out ? (int)(sc->host_seq++ & 1) : 0;
+    Fr.err_flag = err_flag;  // pinned + unified addressing: the host pointer is valid on the device
     if (sc->tri_cap == 0) sc->tri_cap = g.init_tri_cap ? g.init_tri_cap : std::max(1 << 16, 4 * F + 8 * n_tiles);
     if (sc->quad_cap == 0) sc->quad_cap = g.init_quad_cap ? g.init_quad_cap : std::max(1 << 20, 32 * E);
     if (!g.init_tri_cap) sc->tri_cap = std::max(sc->tri_cap, 8 * n_tiles);
@@ -636,7 +850,7 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
 
     // ---- per-view constants: evaluated once, staged in pinned memory, one asynchronous upload for the whole call ----
     {
-        Globals::Staging& st = g.stage[g.stage_next++ % 4];
+        Context::Staging& st = g.stage[g.stage_next++ % 4];
         if (!st.done) CK(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
         if (st.used) CK(cudaEventSynchronize(st.done));  // the upload that last used this slot has left host memory
         if (st.cap < (size_t)n_views) {
@@ -678,11 +892,11 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
             ++g.launches;
         }
     }
-    stage_mark("silhouette");
+    stage_mark(g, "silhouette");
 
     const cudaMemcpyKind kind = !host_out ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-    if (host_out && g.rgb_last_ticket[rslot] >= 0 && g.ticket - g.rgb_last_ticket[rslot] < 4)
-        CK(cudaStreamWaitEvent(g.stream, g.ticket_copy[g.rgb_last_ticket[rslot] & 3], 0));  // its frames have left rgb[rslot]
+    if (host_out && sc->rgb_used[rslot])
+        CK(cudaStreamWaitEvent(g.stream, sc->rgb_copied[rslot], 0));  // the frames of the render before last have left rgb[rslot]
     for (int attempt = 0; attempt < 4; ++attempt) {
         CK(sc->tris.reserve((size_t)VB * F));
         CK(sc->quads.reserve((size_t)VB * E));
@@ -731,19 +945,19 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
                 ++g.launches;
                 if (fork) CK(cudaEventRecord(g.tri_done, ts));
             }
-            stage_mark("tri_setup");
+            stage_mark(g, "tri_setup");
             const int quad_blocks = std::max(1, std::min((sc->n_edges + 63) / 64, g.sm_count * 4));
             k_quad_setup<<<dim3(quad_blocks, nv), 64, 0, g.stream>>>(sc->sil.p, sc->counters.p, dviews, Fr, sc->quads.p, E);
             ++g.launches;
-            stage_mark("quad_setup");
+            stage_mark(g, "quad_setup");
             if (fork) CK(cudaStreamWaitEvent(g.stream, g.tri_done, 0));
             const int bin_blocks = g.bin_blocks ? g.bin_blocks : g.sm_count * 2;
             k_bin<false><<<dim3(bin_blocks, nv), 256, 0, g.stream>>>(Fr, sc->tris.p, sc->quads.p, sc->counters.p, E, B);
-            k_scan<<<dim3(nv, 2), 1024, 0, g.stream>>>(Fr, B, flags + 2 * first);
+            k_scan<<<dim3(nv, 2), 1024, 0, g.stream>>>(Fr, B, flags + 2 * first, sticky);
             k_order<<<nv, 1024, 0, g.stream>>>(Fr, B);
             k_bin<true><<<dim3(bin_blocks, nv), 256, 0, g.stream>>>(Fr, sc->tris.p, sc->quads.p, sc->counters.p, E, B);
             g.launches += 4;
-            stage_mark("bin");
+            stage_mark(g, "bin");
             RasterOut O;
             O.winner = sc->winner.p; O.stencil = sc->stencil.p; O.z = want_z ? sc->zplane.p : nullptr; O.status = status;
             uint8_t* rgb_dev = (!host_out ? out_rgb : sc->rgb[rslot].p) + (size_t)first * npx * 3;
@@ -765,12 +979,12 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
                 k_raster<<<(unsigned)sv * (unsigned)n_tiles, RASTER_THREADS, 0, st>>>(S, dviews, Fr, sc->tris.p,
                                                                                    sc->quads.p, E, B, O, v0, sv);
                 ++g.launches;
-                stage_mark("raster");
+                stage_mark(g, "raster");
                 k_shade<<<dim3((W + 31) / 32, (rows + B2R_SHADE_THREADS / 32 - 1) / (B2R_SHADE_THREADS / 32), sv),
                           B2R_SHADE_THREADS, 0, st>>>(S, dviews, Fr, sc->tris.p, sc->winner.p, sc->stencil.p, rgb_dev, v0,
                                                       want_f32 ? sc->frame_f32.p : nullptr, bg_packed);
                 ++g.launches;
-                stage_mark("shade");
+                stage_mark(g, "shade");
                 cudaEvent_t done = g.aux_done[n_sub % 16];
                 if (multi || host_out) CK(cudaEventRecord(done, st));
                 if (multi) CK(cudaStreamWaitEvent(g.stream, done, 0));  // the batch is complete on the main stream
@@ -807,26 +1021,25 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
             }
         }
         if (host_out) {
-            CK(cudaEventRecord(g.ticket_copy[tslot], g.copy_stream));
-            g.rgb_last_ticket[rslot] = ticket;
+            CK(cudaEventRecord(sc->rgb_copied[rslot], g.copy_stream));
+            sc->rgb_used[rslot] = true;
         }
         if (host_async) {  // frames are on their way: b2r_wait(ticket) blocks until they (and the overflow flags) landed
-            CK(cudaEventRecord(g.ticket_compute[tslot], g.stream));
-            g.ticket_views[tslot] = n_views;
-            g.ticket_scene[tslot] = sc;
+            Context::TicketSlot& T = g.tk[tslot];
+            CK(cudaEventRecord(T.copy, g.copy_stream));
+            CK(cudaEventRecord(T.compute, g.stream));
+            T.id = ticket; T.views = n_views; T.scene = sc; T.open = true;
             return 0;
         }
         if (!host_out && !dbg) {  // asynchronous mode: capacity overflow is reported by the next b2r_sync
-            g.pending_views = n_views;
-            g.pending_scene = sc;
-            g.pending_flags = flags;
+            if (!sc->in_pending) { g.pending.push_back(sc); sc->in_pending = true; }
             return 0;
         }
         CK(cudaStreamSynchronize(g.stream));
         CK(cudaStreamSynchronize(g.copy_stream));
         int need_tri = 0, need_quad = 0;
         for (int i = 0; i < n_views; ++i) { need_tri = std::max(need_tri, flags[2 * i]); need_quad = std::max(need_quad, flags[2 * i + 1]); }
-        if (!need_tri && !need_quad) return 0;
+        if (!need_tri && !need_quad) return *err_flag ? fail_index() : 0;
         if (need_tri) { sc->tri_cap = need_tri + need_tri / 4; sc->tri_list.release(); }
         if (need_quad) { sc->quad_cap = need_quad + need_quad / 4; sc->quad_list.release(); sc->pair_list.release(); }
     }

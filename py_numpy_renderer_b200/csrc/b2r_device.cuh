@@ -23,6 +23,7 @@ enum : int {
     FS_UV_F32 = 4,      // uv deltas of tangent_() evaluated in float32
     FS_HAS_UV = 8,
     FS_HAS_NORMALS = 16,
+    FS_NO_ZWRITE = 32,  // Model.depth_test == False: tested against z, never writes it (triangular.py:117)
 };
 struct FaceStatic {  // 48 B, indices are GLOBAL (scene-level concatenated arrays)
     int v[3];
@@ -92,6 +93,7 @@ struct FrameDev {
     int sky_size;
     int want_status;
     int full_stencil;  // stencil counts are wanted for every pixel (debug plane), not only under faces
+    int* err_flag;     // mapped pinned host word: set to 1 when a texture lookup falls outside its map (IndexError)
 };
 
 // ---- per-view, per-face raster record (written by tri_setup, read by raster + shade) ---------------------------
@@ -100,6 +102,7 @@ enum : int {
     TR_NEEDS_CLIP = 2,  // per-pixel clip test cannot be skipped
     TR_BOX_ONE = 4,     // bbox holds exactly one pixel  -> N==1 evaluation order in barycentric()
     TR_COV_ONE = 8,     // exactly one covered & unclipped pixel -> N==1 order for the z interpolation
+    TR_NO_ZWRITE = 16,  // face of a Model(depth_test=False)
 };
 struct TriRec {  // 128 B (8-byte aligned on purpose: staged copies in shared memory sit on a 136-byte pitch)
     double ax, ay, v0x, v0y, v1x, v1y;  // screen a, b-a, c-a                          48

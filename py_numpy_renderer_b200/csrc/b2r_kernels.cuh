@@ -209,7 +209,7 @@ __global__ void k_tri_setup(SceneDev S, const ViewDev* __restrict__ views, Frame
             const int n_box = nx * ny;
             if (n_box == 0) st = B2R_FACE_CLIPPED;
             else {
-                r.flags = TR_VALID | (n_box == 1 ? TR_BOX_ONE : 0);
+                r.flags = TR_VALID | (n_box == 1 ? TR_BOX_ONE : 0) | ((fs.flags & FS_NO_ZWRITE) ? TR_NO_ZWRITE : 0);
 #pragma unroll
                 for (int i = 0; i < 3; ++i) r.zl[i] = linearize_z(sz[i], V);
                 if (fs.flags & FS_CLIP) {
@@ -612,7 +612,7 @@ __global__ void k_bin(FrameDev Fr, const TriRec* __restrict__ tris, const QuadRe
 
 // exclusive scan of the tile counts of one (view, kind); resets the counts to 0 so k_bin<true> can reuse them
 // as cursors.  One CTA of 1024 threads.
-__global__ void k_scan(FrameDev Fr, BinDev B, int* __restrict__ host_flags) {  // host_flags: mapped pinned memory
+__global__ void k_scan(FrameDev Fr, BinDev B, int* __restrict__ host_flags, int* sticky) {  // both: mapped pinned memory
     const int view = blockIdx.x, kind = blockIdx.y;
     const int n_tiles = Fr.tiles_x * Fr.tiles_y;
     int* count = (kind ? B.quad_count : B.tri_count) + (size_t)view * n_tiles;
@@ -648,6 +648,9 @@ __global__ void k_scan(FrameDev Fr, BinDev B, int* __restrict__ host_flags) {  /
         const int cap = kind ? B.quad_cap : B.tri_cap;
         B.overflow[view * 2 + kind] = carry > cap ? carry : 0;
         host_flags[view * 2 + kind] = carry > cap ? carry : 0;  // read by the host after the stream / ticket completes
+        // device-resident renders: overflow of ANY call since the last b2r_sync must survive later, fitting calls.
+        // Racing views all store a sufficient-or-retried size (the host grows the list and the caller renders again).
+        if (sticky && carry > cap) sticky[kind] = carry;
     }
 }
 
@@ -719,6 +722,13 @@ __device__ __forceinline__ bool tri_misses_rect(const TriRec& r, int x0, int x1,
     const double Ev = 8.0 * u32 * (gv + amax_v) + 1e-30, Ew = 8.0 * u32 * (gw + amax_w) + 1e-30;
     const double Eu = Ev + Ew + 8.0 * u32 * (1.0 + amax_v + amax_w);
     return tmax[0] < -Eu || tmax[1] < -Ev || tmax[2] < -Ew;
+}
+
+// Relaxed atomic store to shared memory: several lanes / warps may name the same pixel as "last improver" in the same
+// round (the verification pass sorts it out), so the store must be an atomic access to be defined behaviour.  Costs the
+// same as a plain STS.
+__device__ __forceinline__ void store_relaxed_smem(int* p, int v) {
+    asm volatile("st.relaxed.cta.shared.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
 
 constexpr int RASTER_WARPS = RASTER_THREADS / 32;
@@ -834,12 +844,21 @@ __device__ __forceinline__ void raster_tris(RasterSmem& sm, const SceneDev& S, c
                 const int p = (py - Y0) * TILE_W + (px - X0);
                 const unsigned long long key = zkey(z);
                 if (PASS == 1) {
+                    // a face of a Model(depth_test=False) never writes z (triangular.py:117); it may still colour the
+                    // pixel, which only the full winner pass resolves
+                    if (r.flags & TR_NO_ZWRITE) { sm.need_full = 1; continue; }
                     const unsigned long long old = rh ? atomicMin(&sm.z[p], key) : atomicMax(&sm.z[p], key);
                     if (old == key) sm.need_full = 1;                       // exact tie: the greatest face index wins
-                    else if (rh ? (key < old) : (key > old)) sm.id[p] = face;  // last improver (verified afterwards)
-                } else if (key == sm.z[p]) {
-                    atomicMax(&sm.id[p], face);
-                    bits |= 2 | (sm.st[p] == 0 ? 4 : 0);
+                    else if (rh ? (key < old) : (key > old)) store_relaxed_smem(&sm.id[p], face);  // last improver (verified afterwards)
+                } else {
+                    // writing faces colour where they ARE the z-buffer; non-writing ones wherever they pass the test
+                    // against the final z-buffer (zbuf >= z for RH, <= for LH)
+                    const unsigned long long kb = sm.z[p];
+                    const bool pass = (r.flags & TR_NO_ZWRITE) ? (rh ? (kb >= key) : (kb <= key)) : (key == kb);
+                    if (pass) {
+                        atomicMax(&sm.id[p], face);
+                        bits |= 2 | (sm.st[p] == 0 ? 4 : 0);
+                    }
                 }
             }
             if (PASS == 3 && status_view) {
@@ -1137,7 +1156,9 @@ k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRe
 // =====================================================================================================================
 // shading
 // =====================================================================================================================
-__device__ __forceinline__ void texel_fetch(const TextureDev& T, const double P[3], const double uu[3], const double vv[3],
+// Returns false when the lookup falls outside the map, where NumPy's fancy indexing raises IndexError in the
+// reference: an index below -size (the upper side is clipped), or a NaN coordinate (astype(int32) yields INT_MIN).
+__device__ __forceinline__ bool texel_fetch(const TextureDev& T, const double P[3], const double uu[3], const double vv[3],
                                             float out[3]) {
     // Face.get_UV (core.py:138-143): clip(max=1), scale by (size-1), truncate, python-style negative wrap
     double cu = gemv3(P[0], P[1], P[2], uu[0], uu[1], uu[2]);
@@ -1149,11 +1170,13 @@ __device__ __forceinline__ void texel_fetch(const TextureDev& T, const double P[
     int row = (int)(rv * (double)(T.height - 1));
     if (col < 0) col += T.width;
     if (row < 0) row += T.height;
-    if (col < 0 || col >= T.width) col = 0;
-    if (row < 0 || row >= T.height) row = 0;
+    bool ok = (cu == cu) && (rv == rv);
+    if (col < 0 || col >= T.width) { col = 0; ok = false; }
+    if (row < 0 || row >= T.height) { row = 0; ok = false; }
     const uchar4 t = __ldg(T.texels + (size_t)row * T.width + col);
     const float* lut = c_lut[T.decode];
     out[0] = lut[t.x]; out[1] = lut[t.y]; out[2] = lut[t.z];
+    return ok;
 }
 
 // normalize() for shading vectors: x * rsqrt(|x|^2).  Within an ulp or two of the reference's x / sqrt(.) -- far
@@ -1220,8 +1243,10 @@ __global__ void k_frame_consts(FrameDev Fr, int* __restrict__ counters, int n_co
 __device__ __forceinline__ float clip01(double v) { return (float)(v < 0.05 ? 0.05 : (v > 1.0 ? 1.0 : v)); }
 
 // general_shading for one pixel (triangular.py:135-171)
-__device__ void shade_face_pixel(const SceneDev& S, const ViewDev& V, const LightDev& L, const TriRec& r, int face,
+// Returns false when a texture lookup fell outside its map (the reference raises IndexError there).
+__device__ bool shade_face_pixel(const SceneDev& S, const ViewDev& V, const LightDev& L, const TriRec& r, int face,
                                  int px, int py, bool lit, float out[3]) {
+    bool tex_ok = true;
     const ShadeStatic& fs = S.shade[face];
     const MaterialDev& M = S.mats[fs.material];
     float bu, bv, bw;
@@ -1238,7 +1263,7 @@ __device__ void shade_face_pixel(const SceneDev& S, const ViewDev& V, const Ligh
     double albedo[3];
     if (M.map_Kd >= 0) {
         float t[3];
-        texel_fetch(S.tex[M.map_Kd], P, uu, vv, t);
+        tex_ok = texel_fetch(S.tex[M.map_Kd], P, uu, vv, t) && tex_ok;
         albedo[0] = (double)t[0]; albedo[1] = (double)t[1]; albedo[2] = (double)t[2];
     } else {
         albedo[0] = M.Kd[0]; albedo[1] = M.Kd[1]; albedo[2] = M.Kd[2];
@@ -1253,7 +1278,7 @@ __device__ void shade_face_pixel(const SceneDev& S, const ViewDev& V, const Ligh
     if (!lit) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) out[k] = clip01(att * L.ambient[k] * albedo[k]);
-        return;
+        return tex_ok;
     }
     // Face.get_normals (core.py:175-189)
     const double (*vn)[3] = fs.vn;
@@ -1261,7 +1286,7 @@ __device__ void shade_face_pixel(const SceneDev& S, const ViewDev& V, const Ligh
     if (M.norm >= 0) {
         const TextureDev& T = S.tex[M.norm];
         float t[3];
-        texel_fetch(T, P, uu, vv, t);
+        tex_ok = texel_fetch(T, P, uu, vv, t) && tex_ok;
         if (T.tangent) {  // Face.tangent_ (core.py:191-224)
             double n[3];
 #pragma unroll
@@ -1346,7 +1371,7 @@ __device__ void shade_face_pixel(const SceneDev& S, const ViewDev& V, const Ligh
     double spec_light[3];
     if (M.map_Ks >= 0) {  // core.py:145-153: float32 texel * 255
         float t[3];
-        texel_fetch(S.tex[M.map_Ks], P, uu, vv, t);
+        tex_ok = texel_fetch(S.tex[M.map_Ks], P, uu, vv, t) && tex_ok;
         const double s = (double)__fmul_rn(t[0], 255.0f);
         spec_light[0] = spec_light[1] = spec_light[2] = s;
     } else {
@@ -1364,6 +1389,7 @@ __device__ void shade_face_pixel(const SceneDev& S, const ViewDev& V, const Ligh
         const double diffuse = nl * L.color[k];
         out[k] = clip01(att * albedo[k] * (L.ambient[k] + diffuse + specular));
     }
+    return tex_ok;
 }
 
 // cube_map.py:63-101 for one background pixel; returns false when neither screen triangle covers it
@@ -1425,7 +1451,8 @@ k_shade(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec
         const size_t g = (size_t)view * Fr.H * Fr.W + (size_t)py * Fr.W + px;
         const int face = winner[g];
         if (face >= 0) {
-            shade_face_pixel(S, V, Fr.light, tris[(size_t)view * Fr.n_faces + face], face, px, py, stencil[g] == 0, c);
+            if (!shade_face_pixel(S, V, Fr.light, tris[(size_t)view * Fr.n_faces + face], face, px, py, stencil[g] == 0, c))
+                *Fr.err_flag = 1;  // mapped pinned memory: the host raises IndexError like the reference
         } else if (Fr.bg_mode == B2R_BG_CUBEMAP) {
             skybox_pixel(S, V, Fr.sky_size, px, py, c);
         } else {

@@ -28,14 +28,27 @@ struct Cursor {
 };
 }  // namespace
 
+// Return codes: 0 ok, 1 bad arguments, 2 file cannot be read (FileNotFoundError / OSError on the Python side),
+// 3 malformed number in a face statement (the reference raises ValueError from np.array(..., dtype=int32),
+// core.py:72-74), 4 out of memory.  No C++ exception crosses the C boundary.
+static int obj_load_impl(const char* path, b2r_obj* out);
 extern "C" int b2r_obj_load(const char* path, b2r_obj* out) {
     if (!path || !out) return 1;
     std::memset(out, 0, sizeof(*out));
+    try {
+        return obj_load_impl(path, out);
+    } catch (...) {
+        b2r_obj_free(out);
+        return 4;
+    }
+}
+
+static int obj_load_impl(const char* path, b2r_obj* out) {
     FILE* fh = std::fopen(path, "rb");
     if (!fh) return 2;
-    std::fseek(fh, 0, SEEK_END);
+    if (std::fseek(fh, 0, SEEK_END) != 0) { std::fclose(fh); return 2; }
     const long size = std::ftell(fh);
-    std::fseek(fh, 0, SEEK_SET);
+    if (size < 0 || std::fseek(fh, 0, SEEK_SET) != 0) { std::fclose(fh); return 2; }  // e.g. a directory
     std::string text((size_t)size, '\0');
     if (size > 0 && std::fread(&text[0], 1, (size_t)size, fh) != (size_t)size) { std::fclose(fh); return 2; }
     std::fclose(fh);
@@ -80,10 +93,13 @@ extern "C" int b2r_obj_load(const char* path, b2r_obj* out) {
                     if (c.p < c.end && *c.p != '/' && *c.p != ' ' && *c.p != '\t' && *c.p != '\r' && *c.p != '\n') {
                         char* stop = nullptr;
                         idx[k] = (int32_t)std::strtol(c.p, &stop, 10);
+                        if (stop == c.p) return 3;  // not a number: int('x') raises ValueError in the reference
                         c.p = stop;
                     }
                     if (c.p < c.end && *c.p == '/') ++c.p; else break;
                 }
+                // a corner token must end here ("1x", "1/2/3/4" are malformed in the reference as well)
+                if (c.p < c.end && *c.p != ' ' && *c.p != '\t' && *c.p != '\r' && *c.p != '\n') return 3;
                 for (int k = 0; k < 3; ++k) corner.push_back(idx[k]);
                 corner.push_back(current + 1);
             }

@@ -58,7 +58,8 @@ def load(name, resolution=None):
             mats[gname] = mat
         model = b2r.Model(data[p + 'vertices'], data[p + 'uv'] if p + 'uv' in data else None,
                           data[p + 'normals'] if p + 'normals' in data else None, data[p + 'faces'],
-                          materials=mats, material_group=list(mm['groups']), clip=mm['clip'])
+                          materials=mats, material_group=list(mm['groups']), clip=mm['clip'],
+                          depth_test=mm.get('depth_test', True))
         models.append(model)
     skymap = meta.get('skymap')
     if 'sky_texels' in data:

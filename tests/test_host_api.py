@@ -137,10 +137,11 @@ def test_light_defaults_and_packing():
     assert ld.spot_cos_outer == np.cos(np.deg2rad(20)) and ld.spot_cos_inner == np.cos(np.deg2rad(10))
 
 
-def test_depth_test_false_is_fenced():
+def test_depth_test_false_reaches_the_abi():
+    """Model(depth_test=False) (reference core.py:232-236, triangular.py:117) is passed through, not fenced."""
     m = b2r.Model(np.zeros((3, 4), np.float32), None, None, np.zeros((1, 3, 4), np.int32), depth_test=False)
-    with pytest.raises(NotImplementedError):
-        _abi.PackedScene([m])
+    packed = _abi.PackedScene([m, b2r.Model(np.zeros((3, 4), np.float32), None, None, np.zeros((1, 3, 4), np.int32))])
+    assert packed.models[0].depth_test == 0 and packed.models[1].depth_test == 1
 
 
 def test_fast_look_at_equals_numpy_formulation():

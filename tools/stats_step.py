@@ -5,8 +5,9 @@ sys.path[:0] = [R, R + '/tests']
 import numpy as np, torch, scenes
 from py_numpy_renderer_b200 import _native
 views = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+workload = sys.argv[2] if len(sys.argv) > 2 else "synthetic"
 lib = _native.init(0)
-scene = scenes.c3_synthetic((1080, 1920))
+scene = scenes.kat2(scenes.asset_root(), (1080, 1920)) if workload == "diablo" else scenes.c3_synthetic((1080, 1920))
 out = torch.empty((views, 1080, 1920, 3), dtype=torch.uint8, device="cuda:0")
 buf = (ctypes.c_ulonglong * 16)()
 names = ["quad_tile_pairs", "pairs_rejected_by_depth_range", "pairs_with_pixel_work", "stencil_pixel_items",
