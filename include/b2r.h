@@ -192,7 +192,7 @@ int64_t b2r_launch_count(void);
 
 /* Stage timing of the most recent b2r_render in milliseconds (CUDA events on the library stream); valid after
  * a sync.  names/ms arrays sized >= B2R_MAX_STAGES; returns the number of stages. */
-#define B2R_MAX_STAGES 16
+#define B2R_MAX_STAGES 64
 int b2r_last_stage_ms(const char** names, float* ms);
 int b2r_set_stage_timing(int enabled);
 

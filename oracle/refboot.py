@@ -20,6 +20,9 @@ import numpy as np
 
 REF_ROOT = os.environ.get("B2R_REFERENCE_ROOT", "/root/reference")
 ASSETS = os.path.join(REF_ROOT, "obj")
+# The reference's own .py files, unmodified, zipped by __graft_entry__.build() into the git-ignored baseline/_ref/ (which
+# travels to the GPU box): lets bench.py time the NumPy reference itself there.  Python imports straight from the zip.
+REF_ZIP = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "ref_src.zip")
 
 _booted = None
 
@@ -28,14 +31,22 @@ def available() -> bool:
     return os.path.isfile(os.path.join(ASSETS, "core.py"))
 
 
+def importable() -> bool:
+    """The reference can be imported: from /root/reference (build container) or from the staged zip (GPU box)."""
+    return available() or os.path.isfile(REF_ZIP)
+
+
 def boot():
     """Import the reference (SURVEY.md Appendix C recipe).  Returns a namespace of its public names."""
     global _booted
     if _booted is not None:
         return _booted
-    if not available():
-        raise RuntimeError(f"reference not found under {REF_ROOT}")
-    sys.path[:0] = [REF_ROOT, ASSETS]
+    if available():
+        sys.path[:0] = [REF_ROOT, ASSETS]
+    elif os.path.isfile(REF_ZIP):
+        sys.path[:0] = [REF_ZIP, REF_ZIP + "/obj"]
+    else:
+        raise RuntimeError(f"reference not found under {REF_ROOT} nor staged as {REF_ZIP}")
     if "matplotlib" not in sys.modules:  # import-time-only dependency of triangular.py:2
         mp, mpp = types.ModuleType("matplotlib"), types.ModuleType("matplotlib.path")
         mpp.Path = object
@@ -106,3 +117,62 @@ def instrumented_render(scene, quiet=True):
     stencil = state["stencil"] if state["stencil"] is not None else np.zeros((H, W), np.int16)
     return dict(rgb=rgb, frame_f32=state["frame"].copy(), z=state["z"].copy(), stencil=stencil.copy(),
                 winner1=w1, winner3=w3, log=sink.getvalue())
+
+
+def to_reference_scene(scene, camera=None, debug_camera=None):
+    """Rebuild a product-side `py_numpy_renderer_b200.Scene` (host objects only) with the reference's OWN classes: fresh
+    Models (model.silhouette persists in the reference, SURVEY B-3), float32 texture arrays as TextureMaps.register
+    stores them (core.py:90-105), cameras / light with the same constructor arguments.  Used by bench.py's NumPy-reference
+    arm and by tests; `camera` / `debug_camera` override the scene's own."""
+    ref = boot()
+    from py_numpy_renderer_b200.cube_map import CubeMap as MyCubeMap
+    from py_numpy_renderer_b200.materials import Texture
+
+    def ref_texture(t):
+        arr = t.texels / 255
+        if t.signed:
+            arr = arr * 2 - 1
+        return np.array(arr, dtype=np.dtype(np.float32, metadata={'tangent': bool(t.tangent)}))
+
+    def ref_camera(c):
+        return ref.Camera(tuple(np.asarray(c.position).tolist()), center=np.array(c.center), show=False,
+                          backface_culling=c.backface_culling, x_offset=c.x_offset, y_offset=c.y_offset,
+                          projection_type=c.projection_type, up=c.up,
+                          near=c.near, far=c.far, fovy=c.fovy)
+
+    models = []
+    for m in scene.models:
+        rm = ref.Model(np.array(m.vertices, copy=True), None if m.uv is None else np.array(m.uv, copy=True),
+                       None if m.normals is None else np.array(m.normals, copy=True), np.array(m._faces, copy=True),
+                       clip=m.clip, depth_test=m.depth_test)
+        rm.material_group = list(m.material_group)
+        mats = {}
+        for name, mat in m.materials.items():
+            rmat = type(rm.materials['default'])()
+            for key in ("Kd", "Ks", "Ns"):
+                object.__setattr__(rmat, key, getattr(mat, key))
+            for key in ("map_Kd", "map_Ks", "norm"):
+                t = getattr(mat, key, None)
+                if isinstance(t, Texture):
+                    object.__setattr__(rmat, key, ref_texture(t))
+            mats[name] = rmat
+        rm.materials = mats
+        models.append(rm)
+    L = scene.light
+    light = ref.Light(tuple(np.asarray(L.position).tolist()), light_type=getattr(ref.Lightning, L.light_type.name),
+                      center=tuple(np.asarray(L.center).tolist()), color=tuple(np.asarray(L.color).tolist()),
+                      ambient_strength=0, diffuse=L.diffuse, specular_strength=L.specular_strength,
+                      constant=L.constant, linear=L.linear, quadratic=L.quadratic)
+    light.ambient = np.array(L.ambient, dtype=float)
+    sky = scene.skybox
+    if isinstance(sky, MyCubeMap):
+        rsky = ref.CubeMap.__new__(ref.CubeMap)       # textures as CubeMap.__init__ leaves them (cube_map.py:22-61)
+        rsky.textures = np.asarray(sky.texels) / 255
+        rsky.faces = [np.array([[-1, 1, 1, 1], [1, 1, 1, 1], [-1, -1, 1, 1]]),      # cube_map.py:46-54
+                      np.array([[1, 1, 1, 1], [1, -1, 1, 1], [-1, -1, 1, 1]])]
+        sky = rsky
+    rs = ref.Scene(ref_camera(camera or scene.camera), light, debug_camera=ref_camera(debug_camera or scene.debug_camera),
+                   resolution=tuple(scene.resolution), system=scene.system, subsystem=scene.subsystem, skymap=sky)
+    for rm in models:
+        rs.add_model(rm)
+    return rs

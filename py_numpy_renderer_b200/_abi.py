@@ -20,7 +20,7 @@ B2R_TEX_UNORM, B2R_TEX_SNORM = 0, 1
 B2R_BG_COLOR, B2R_BG_CUBEMAP = 0, 1
 B2R_FACE_RENDERED, B2R_FACE_BACK_FACE_CULLING, B2R_FACE_WRONG_MIN_MAX = 0, 1, 2
 B2R_FACE_EMPTY_B, B2R_FACE_EMPTY_Z, B2R_FACE_CLIPPED = 4, 8, 16
-B2R_MAX_STAGES = 16
+B2R_MAX_STAGES = 64
 
 _d = C.c_double
 _i = C.c_int32

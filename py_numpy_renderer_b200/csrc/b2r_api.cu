@@ -52,15 +52,22 @@ struct Context {
     static constexpr int N_AUX = 3;   // sub-chunks of one batch render concurrently: the long tail of a raster launch
     cudaStream_t aux[N_AUX] = {};     // (a few very heavy tiles) is filled by the next sub-chunk's work
     cudaEvent_t aux_done[16] = {};
+    cudaEvent_t aux_last[N_AUX] = {};  // last tile / shading work enqueued on each auxiliary stream
     cudaEvent_t setup_done = nullptr;
     cudaStream_t fork_stream = nullptr;  // k_tri_setup runs here, next to the facing -> silhouette -> quad chain
     cudaEvent_t tri_done = nullptr;
     int host_chunk = 2;           // views per sub-chunk when frames go to host memory (copy/compute overlap)
-    int dev_chunk = 64;           // views per launch when frames stay on the device (whole batch: the cost-ordered raster grid has no tail to hide)
+    int dev_chunk = 64;           // views per tile launch when frames stay on the device (a whole pipeline part: the cost-ordered grid has no tail to hide)
+    int pipe_views = 1 << 20;     // B2R_PIPE: views per pipeline part (set-up + binning of part p+1 under the tile kernels of part p).
+                                  // OFF by default: measured on the B200 (diablo, 64 views) 13.5 k frames/s unsplit against 12.6 k with
+                                  // parts of 8 / 16 / 32 views -- the cost-ordered tile grid loses more to its shorter launches than
+                                  // the 0.4 ms of set-up it hides
     int async_chunk = 8;          // views per sub-chunk of a host-asynchronous call (swept: tools/knob_sweep_e2e.sh)
     int aux_host = 2, aux_dev = 3;  // how many auxiliary streams the sub-chunks rotate over
     int init_tri_cap = 0, init_quad_cap = 0;  // B2R_TRI_CAP / B2R_QUAD_CAP: first per-view list capacities (tests of the grow path)
     int bin_blocks = 0, bin_share = 64;  // k_bin grid (0 = 2 per SM) and the most warps that share one quad
+    int fused = 0;                // B2R_FUSED: 0 = k_tile<false> + k_shade_packed (one packed word per pixel between them; production),
+                                  // 1 = k_tile<true> (shading inside the tile kernel; measured slower, kept for A/B)
     // pinned staging ring for the per-view constants: a pageable source would make cudaMemcpyAsync synchronise the
     // stream, i.e. serialise the host with the previous chunk / previous asynchronous call
     struct Staging { ViewDev* host = nullptr; size_t cap = 0; cudaEvent_t done = nullptr; bool used = false; } stage[4];
@@ -149,6 +156,7 @@ struct b2r_scene {
     DevBuf<double2> uv;
     DevBuf<double> nrm;
     DevBuf<FaceStatic> faces;
+    DevBuf<int4> face_vf;
     DevBuf<ShadeStatic> shade;
     DevBuf<MaterialDev> mats;
     DevBuf<TextureDev> tex;
@@ -168,10 +176,13 @@ struct b2r_scene {
     DevBuf<int> counters;  // [0] silhouette count, [1..n_models] per-model counts, [1+n_models] tonemapped background
     DevBuf<ViewDev> views;
     DevBuf<TriRec> tris;
+    DevBuf<TriBox> boxes;     // (views, F) what binning needs of a face
+    DevBuf<int> coop_list;    // (views, F) faces queued for k_tri_count; their counts sit behind the tile counters
     DevBuf<QuadRec> quads;
     DevBuf<int> tile_counts, tile_offs, tri_list, quad_list, overflow, tile_order;
     DevBuf<int2> pair_list;  // (quad, tile) pairs between the two binning passes
     DevBuf<int> winner;
+    DevBuf<unsigned> packed;  // winner | lit << 31 per pixel (B2R_FUSED=2)
     DevBuf<short> stencil;
     DevBuf<double> zplane;
     DevBuf<float> frame_f32;
@@ -181,17 +192,18 @@ struct b2r_scene {
     bool rgb_used[2] = {false, false};
     unsigned host_seq = 0;   // host-bound renders of this scene so far (selects rgb[host_seq & 1])
     int tri_cap = 0, quad_cap = 0;  // per-view capacity of the tile lists (grown after an overflow)
+    int sil_cap = 0;                // capacity of the silhouette / per-view quad records (edges that can be extruded at once)
 
     SceneDev dev() const {
         SceneDev S;
-        S.pos = pos.p; S.uv = uv.p; S.nrm = nrm.p; S.faces = faces.p; S.shade = shade.p; S.mats = mats.p; S.tex = tex.p; S.sky = sky.p;
+        S.pos = pos.p; S.uv = uv.p; S.nrm = nrm.p; S.faces = faces.p; S.face_vf = face_vf.p; S.shade = shade.p; S.mats = mats.p; S.tex = tex.p; S.sky = sky.p;
         S.edge_v = edge_v.p; S.edge_ptr = edge_ptr.p; S.edge_inc = edge_inc.p;
         S.n_faces = n_faces; S.n_edges = n_edges;
         return S;
     }
 };
 
-static void b2r_scene_grow_lists(struct b2r_scene* sc, int need_tri, int need_quad);
+static void b2r_scene_grow_lists(struct b2r_scene* sc, int need_tri, int need_quad, int need_sil = 0);
 static int b2r_scene_check_sticky(struct b2r_scene* sc);
 
 extern "C" {
@@ -215,7 +227,11 @@ int b2r_init(int device) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     g.sm_count = prop.multiProcessorCount;
-    CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    // the main stream carries the small, latency-bound set-up launches of the pipeline: highest priority, so that they
+    // are not queued behind the tile kernels (auxiliary streams, default priority) they are meant to overlap
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CK(cudaStreamCreateWithPriority(&g.stream, cudaStreamNonBlocking, prio_hi));
     for (int i = 0; i <= B2R_MAX_STAGES; ++i) CK(cudaEventCreate(&g.stage_ev[i]));
     CK(cudaMallocHost(&g.pinned_flags, sizeof(int) * REGION_INTS * FLAG_REGIONS));
     std::memset(g.pinned_flags, 0, sizeof(int) * REGION_INTS * FLAG_REGIONS);
@@ -231,9 +247,10 @@ int b2r_init(int device) {
     CK(cudaEventCreateWithFlags(&g.chunk_done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&g.setup_done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&g.tri_done, cudaEventDisableTiming));
-    CK(cudaStreamCreateWithFlags(&g.fork_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithPriority(&g.fork_stream, cudaStreamNonBlocking, prio_hi));
     for (int i = 0; i < Context::N_AUX; ++i) CK(cudaStreamCreateWithFlags(&g.aux[i], cudaStreamNonBlocking));
     for (int i = 0; i < 16; ++i) CK(cudaEventCreateWithFlags(&g.aux_done[i], cudaEventDisableTiming));
+    for (int i = 0; i < Context::N_AUX; ++i) CK(cudaEventCreateWithFlags(&g.aux_last[i], cudaEventDisableTiming));
     if (const char* hc = std::getenv("B2R_HOST_CHUNK")) g.host_chunk = std::max(1, std::atoi(hc));
     if (const char* dc = std::getenv("B2R_DEV_CHUNK")) g.dev_chunk = std::max(1, std::atoi(dc));
     if (const char* ac = std::getenv("B2R_ASYNC_CHUNK")) g.async_chunk = std::max(1, std::atoi(ac));
@@ -242,14 +259,9 @@ int b2r_init(int device) {
     if (const char* a = std::getenv("B2R_QUAD_CAP")) g.init_quad_cap = std::max(1, std::atoi(a));
     if (const char* a = std::getenv("B2R_BIN_BLOCKS")) g.bin_blocks = std::max(1, std::atoi(a));
     if (const char* a = std::getenv("B2R_BIN_SHARE")) g.bin_share = std::max(1, std::atoi(a));
+    if (const char* a = std::getenv("B2R_PIPE")) g.pipe_views = std::max(1, std::atoi(a));
+    if (const char* a = std::getenv("B2R_FUSED")) g.fused = std::atoi(a) != 0;
     if (const char* a = std::getenv("B2R_AUX_DEV")) g.aux_dev = std::min(Context::N_AUX, std::max(1, std::atoi(a)));
-    float lut[2][256];
-    for (int i = 0; i < 256; ++i) {  // core.py:96-104: f32(u8/255), f32(u8/255*2-1) with float64 intermediates
-        const double t = (double)i / 255;
-        lut[0][i] = (float)t;
-        lut[1][i] = (float)(t * 2 - 1);
-    }
-    CK(cudaMemcpyToSymbol(c_lut, lut, sizeof(lut)));  // __constant__ symbols are per device: uploaded for every context
     g.device = device;
     g.ready = true;
     g.launches = 0;
@@ -276,6 +288,7 @@ int b2r_shutdown(void) {
                 for (int i = 0; i < Context::N_AUX; ++i) cudaStreamDestroy(g.aux[i]);
                 cudaEventDestroy(g.chunk_done); cudaEventDestroy(g.setup_done); cudaEventDestroy(g.tri_done);
                 for (int i = 0; i < 16; ++i) cudaEventDestroy(g.aux_done[i]);
+                for (int i = 0; i < Context::N_AUX; ++i) cudaEventDestroy(g.aux_last[i]);
                 for (int i = 0; i <= B2R_MAX_STAGES; ++i) cudaEventDestroy(g.stage_ev[i]);
                 for (int i = 0; i < N_TICKET_SLOTS; ++i) { cudaEventDestroy(g.tk[i].copy); cudaEventDestroy(g.tk[i].compute); }
                 for (auto& st : g.stage) { if (st.host) cudaFreeHost(st.host); if (st.done) cudaEventDestroy(st.done); }
@@ -300,8 +313,9 @@ int b2r_current_device(void) {
 static int check_overflow_flags(const int* flags, int n_views, struct b2r_scene* sc) {
     int need_tri = 0, need_quad = 0;
     for (int i = 0; i < n_views; ++i) { need_tri = std::max(need_tri, flags[2 * i]); need_quad = std::max(need_quad, flags[2 * i + 1]); }
-    if (!need_tri && !need_quad) return flags[2 * MAX_FLAG_VIEWS] ? fail_index() : 0;
-    b2r_scene_grow_lists(sc, need_tri, need_quad);
+    const int need_sil = flags[2 * MAX_FLAG_VIEWS + 1];
+    if (!need_tri && !need_quad && !need_sil) return flags[2 * MAX_FLAG_VIEWS] ? fail_index() : 0;
+    b2r_scene_grow_lists(sc, need_tri, need_quad, need_sil);
     return fail("tile list capacity overflow in an asynchronous render: affected frames show background only; "
                 "capacity was raised, render again");
 }
@@ -485,6 +499,8 @@ int b2r_scene_create(const b2r_model_desc* models, int32_t n_models, const b2r_t
             M.map_Ks = src.map_Ks < n_textures ? src.map_Ks : -1;
             M.norm = src.norm < n_textures ? src.norm : -1;
             M.ns_int = (src.Ns >= 0 && src.Ns <= 4096 && src.Ns == std::floor(src.Ns)) ? (int)src.Ns : -1;
+            M.ns_log2 = -1; M.pad = 0;
+            for (int k = 0; k <= 12; ++k) if (M.ns_int == (1 << k)) M.ns_log2 = k;
         }
         const int base_flags = (m.clip ? FS_CLIP : 0) | (m.vertex_dtype == B2R_F32 ? FS_VTX_F32 : 0) |
                                (m.uv ? FS_HAS_UV : 0) | (m.uv && m.uv_dtype == B2R_F32 ? FS_UV_F32 : 0) |
@@ -559,7 +575,9 @@ int b2r_scene_create(const b2r_model_desc* models, int32_t n_models, const b2r_t
         R.material = F.material;
         R.flags = F.flags;
     }
-    UP(pos, pos); UP(uv, uv); UP(nrm, nrm); UP(faces, faces); UP(shade, shade); UP(mats, mats);
+    std::vector<int4> face_vf(nf);
+    for (size_t f = 0; f < nf; ++f) face_vf[f] = make_int4(faces[f].v[0], faces[f].v[1], faces[f].v[2], faces[f].flags);
+    UP(pos, pos); UP(uv, uv); UP(nrm, nrm); UP(faces, faces); UP(face_vf, face_vf); UP(shade, shade); UP(mats, mats);
     UP(edge_v, edge_v); UP(edge_ptr, edge_ptr); UP(edge_inc, edge_inc); UP(edge_model, edge_model);
     // textures: uint8 RGB -> RGBX so that one texel is one aligned 32-bit load
     std::vector<TextureDev> tex(std::max(1, n_textures));
@@ -613,12 +631,12 @@ int b2r_scene_destroy(b2r_scene* sc) {
         if (sc->sticky_slot >= 0) { for (int k = 0; k < STICKY_INTS; ++k) g.sticky[STICKY_INTS * sc->sticky_slot + k] = 0; g.sticky_free.push_back(sc->sticky_slot); }
     }
     for (int i = 0; i < 2; ++i) if (sc->rgb_copied[i]) cudaEventDestroy(sc->rgb_copied[i]);
-    sc->pos.release(); sc->uv.release(); sc->nrm.release(); sc->faces.release(); sc->shade.release(); sc->mats.release(); sc->tex.release();
+    sc->pos.release(); sc->uv.release(); sc->nrm.release(); sc->faces.release(); sc->face_vf.release(); sc->shade.release(); sc->mats.release(); sc->tex.release();
     for (uchar4* d : sc->tex_data) cudaFree(d);
     sc->sky.release(); sc->edge_v.release(); sc->edge_ptr.release(); sc->edge_inc.release(); sc->edge_model.release();
     sc->sil_state.release(); sc->facing.release(); sc->sil.release(); sc->counters.release(); sc->views.release();
-    sc->tris.release(); sc->quads.release(); sc->tile_counts.release(); sc->tile_offs.release(); sc->tri_list.release();
-    sc->quad_list.release(); sc->pair_list.release(); sc->overflow.release(); sc->tile_order.release(); sc->winner.release(); sc->stencil.release(); sc->zplane.release();
+    sc->tris.release(); sc->boxes.release(); sc->coop_list.release(); sc->quads.release(); sc->tile_counts.release(); sc->tile_offs.release(); sc->tri_list.release();
+    sc->quad_list.release(); sc->pair_list.release(); sc->overflow.release(); sc->tile_order.release(); sc->winner.release(); sc->packed.release(); sc->stencil.release(); sc->zplane.release();
     sc->status.release(); sc->frame_f32.release(); sc->rgb[0].release(); sc->rgb[1].release();
     delete sc;
     return 0;
@@ -685,8 +703,9 @@ int b2r_scene_set_silhouette(b2r_scene* sc, const int32_t* pairs, int32_t n) {
 }
 
 }  // extern "C"
-static void b2r_scene_grow_lists(b2r_scene* sc, int need_tri, int need_quad) {
+static void b2r_scene_grow_lists(b2r_scene* sc, int need_tri, int need_quad, int need_sil) {
     if (!sc) return;
+    if (need_sil) { sc->sil_cap = std::min(std::max(1, sc->n_edges), need_sil + need_sil / 4); sc->sil.release(); sc->quads.release(); }
     if (need_tri) { sc->tri_cap = need_tri + need_tri / 4; sc->tri_list.release(); }
     if (need_quad) { sc->quad_cap = need_quad + need_quad / 4; sc->quad_list.release(); sc->pair_list.release(); }
 }
@@ -697,10 +716,10 @@ static int b2r_scene_check_sticky(b2r_scene* sc) {
     if (!sc || sc->sticky_slot < 0) return 0;
     sc->in_pending = false;
     volatile int* st = sc->cx->sticky + STICKY_INTS * sc->sticky_slot;
-    const int need_tri = st[0], need_quad = st[1], bad_index = st[2];
-    st[0] = 0; st[1] = 0; st[2] = 0;
-    if (!need_tri && !need_quad) return bad_index ? fail_index() : 0;
-    b2r_scene_grow_lists(sc, need_tri, need_quad);
+    const int need_tri = st[0], need_quad = st[1], bad_index = st[2], need_sil = st[3];
+    st[0] = 0; st[1] = 0; st[2] = 0; st[3] = 0;
+    if (!need_tri && !need_quad && !need_sil) return bad_index ? fail_index() : 0;
+    b2r_scene_grow_lists(sc, need_tri, need_quad, need_sil);
     return fail("tile list capacity overflow in an asynchronous render: affected frames show background only; "
                 "capacity was raised, render again");
 }
@@ -798,13 +817,20 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
     // same as "pixels whose z-buffer was written": count everywhere then
     Fr.full_stencil = ((dbg && dbg->stencil) || sc->has_no_zwrite) ? 1 : 0;
     const int n_tiles = Fr.tiles_x * Fr.tiles_y;
-    const int F = sc->n_faces, E = std::max(1, sc->n_edges);
+    const int F = sc->n_faces;
+    // Silhouette / quad records: far fewer edges are extruded at once than the mesh has (diablo 1 381 of 7 533, the 1M-
+    // triangle torus ~3 000 of 1.5 M), so the records are sized by a capacity that grows on overflow like the tile lists
+    if (sc->sil_cap == 0) sc->sil_cap = std::min(std::max(1, sc->n_edges), std::max(16384, sc->n_edges / 16));
+    int E = sc->sil_cap;
     const size_t npx = (size_t)H * W;
     const SceneDev S = sc->dev();
 
     // Chunking.  Device-resident output: as many views per launch as the scratch budget allows.  Host output: small
     // chunks, so that the D2H copy of chunk i (copy stream) overlaps the kernels of chunk i+1 (compute stream).
-    const size_t per_view = (size_t)F * sizeof(TriRec) + (size_t)E * sizeof(QuadRec) + npx * 6 + (want_z ? npx * 8 : 0);
+    const bool fused = g.fused != 0;
+    const bool want_planes = dbg && (dbg->winner || dbg->stencil);  // debug winner / stencil planes in HBM
+    const size_t per_view = (size_t)F * (sizeof(TriRec) + sizeof(TriBox) + sizeof(int)) + (size_t)E * sizeof(QuadRec) + (want_planes ? npx * 6 : 0) +
+                            (fused ? 0 : npx * 4) + (want_z ? npx * 8 : 0) + (want_f32 ? npx * 12 : 0);
     int VB = (int)std::max<size_t>(1, std::min<size_t>(n_views, ((size_t)6 << 30) / std::max<size_t>(per_view, 1)));
     VB = std::min(VB, 64);
     const bool host_out = out_on_device != 1;
@@ -838,7 +864,9 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
     // where the shader reports a texture lookup outside its map; the region's word is free again: its previous user
     // (ticket / synchronous call) has completed
     int* const err_flag = sticky ? sticky + 2 : flags + 2 * MAX_FLAG_VIEWS;
+    int* const need_sil_flag = flags + 2 * MAX_FLAG_VIEWS + 1;
     if (!sticky) *err_flag = 0;
+    *need_sil_flag = 0;
     const int rslot = host_out ? (int)(sc->host_seq++ & 1) : 0;
     Fr.err_flag = err_flag;  // pinned + unified addressing: the host pointer is valid on the device
     if (sc->tri_cap == 0) sc->tri_cap = g.init_tri_cap ? g.init_tri_cap : std::max(1 << 16, 4 * F + 8 * n_tiles);
@@ -874,41 +902,48 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
     const bool fork = !g.timing && !dbg && F > 0;
     if (fork) CK(cudaEventRecord(g.chunk_done, g.stream));
 
-    // ---- light-dependent, view-independent: facing flags and silhouette quads ----
-    CK(sc->facing.reserve(F + 4));
-    CK(sc->sil.reserve(E));
-    CK(sc->counters.reserve(2 + sc->n_models));
-    const unsigned* bg_packed = reinterpret_cast<const unsigned*>(sc->counters.p + 1 + sc->n_models);
-    k_frame_consts<<<1, 32, 0, g.stream>>>(Fr, sc->counters.p, 1 + sc->n_models,
-                                           reinterpret_cast<unsigned*>(sc->counters.p + 1 + sc->n_models));
-    ++g.launches;
-    if (F > 0) {
-        k_facing<<<(F + 255) / 256, 256, 0, g.stream>>>(S, Fr.light, sc->facing.p);
-        ++g.launches;
-        if (sc->n_edges > 0) {
-            k_silhouette<<<(sc->n_edges + 255) / 256, 256, 0, g.stream>>>(
-                S, Fr.light, sc->facing.p, fp->persist_silhouette ? sc->sil_state.p : nullptr, sc->sil.p,
-                sc->counters.p, sc->counters.p + 1, sc->edge_model.p);
-            ++g.launches;
-        }
-    }
-    stage_mark(g, "silhouette");
-
     const cudaMemcpyKind kind = !host_out ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
     if (host_out && sc->rgb_used[rslot])
         CK(cudaStreamWaitEvent(g.stream, sc->rgb_copied[rslot], 0));  // the frames of the render before last have left rgb[rslot]
+    const unsigned* bg_packed = nullptr;
     for (int attempt = 0; attempt < 4; ++attempt) {
+        E = sc->sil_cap;   // may have grown after an overflow
+        // ---- light-dependent, view-independent: facing flags and silhouette quads ----
+        CK(sc->facing.reserve(F + 4));
+        CK(sc->sil.reserve(E));
+        CK(sc->counters.reserve(2 + sc->n_models));
+        bg_packed = reinterpret_cast<const unsigned*>(sc->counters.p + 1 + sc->n_models);
+        k_frame_consts<<<1, 32, 0, g.stream>>>(Fr, sc->counters.p, 1 + sc->n_models,
+                                               reinterpret_cast<unsigned*>(sc->counters.p + 1 + sc->n_models));
+        ++g.launches;
+        if (F > 0) {
+            k_facing<<<(F + 255) / 256, 256, 0, g.stream>>>(S, Fr.light, sc->facing.p);
+            ++g.launches;
+            if (sc->n_edges > 0) {
+                k_silhouette<<<(sc->n_edges + 255) / 256, 256, 0, g.stream>>>(
+                    S, Fr.light, sc->facing.p, fp->persist_silhouette ? sc->sil_state.p : nullptr, attempt == 0 ? 1 : 0,
+                    sc->sil.p, E, sc->counters.p, sc->counters.p + 1, sc->edge_model.p);
+                ++g.launches;
+            }
+        }
+        stage_mark(g, "silhouette");
+
         CK(sc->tris.reserve((size_t)VB * F));
+        CK(sc->boxes.reserve((size_t)VB * F));
         CK(sc->quads.reserve((size_t)VB * E));
-        CK(sc->tile_counts.reserve((size_t)VB * n_tiles * 2 + (size_t)VB * (2 + BIN_HUGE_CAP)));  // + pair / huge-face counters and lists
+        CK(sc->tile_counts.reserve((size_t)VB * n_tiles * 2 + (size_t)VB * (3 + BIN_HUGE_CAP)));  // + pair / huge-face / queued-face counters and lists
+        CK(sc->coop_list.reserve((size_t)VB * F));
         CK(sc->tile_offs.reserve((size_t)VB * (n_tiles + 1) * 2));
         CK(sc->tri_list.reserve((size_t)VB * sc->tri_cap));
         CK(sc->quad_list.reserve((size_t)VB * sc->quad_cap));
         CK(sc->pair_list.reserve((size_t)VB * sc->quad_cap));
         CK(sc->overflow.reserve((size_t)VB * 2));
         CK(sc->tile_order.reserve((size_t)VB * n_tiles));
-        CK(sc->winner.reserve((size_t)VB * npx));
-        CK(sc->stencil.reserve((size_t)VB * npx));
+        if (want_planes) {
+            CK(sc->winner.reserve((size_t)VB * npx));
+            CK(sc->stencil.reserve((size_t)VB * npx));
+        }
+        if (!fused) CK(sc->packed.reserve((size_t)VB * npx));
         if (want_z) CK(sc->zplane.reserve((size_t)VB * npx));
         if (want_f32) CK(sc->frame_f32.reserve((size_t)VB * npx * 3));
         if (want_status) CK(sc->status.reserve((size_t)VB * F + 8));
@@ -917,7 +952,7 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
         for (int first = 0; first < n_views; first += VB) {
             const int nv = std::min(VB, n_views - first);
             const ViewDev* dviews = sc->views.p + first;
-            const size_t count_words = (size_t)VB * n_tiles * 2 + (size_t)VB * (2 + BIN_HUGE_CAP);
+            const size_t count_words = (size_t)VB * n_tiles * 2 + (size_t)VB * (3 + BIN_HUGE_CAP);
             k_zero_words<<<(unsigned)std::min<size_t>((count_words + 255) / 256, (size_t)g.sm_count * 4), 256, 0, g.stream>>>(
                 reinterpret_cast<unsigned*>(sc->tile_counts.p), count_words);
             ++g.launches;
@@ -931,77 +966,101 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
             B.order = sc->tile_order.p;
             B.pair_list = sc->pair_list.p; B.pair_count = sc->tile_counts.p + (size_t)VB * n_tiles * 2;
             B.huge_count = B.pair_count + VB; B.huge_list = B.huge_count + VB;
+            int* const coop_count = B.huge_list + (size_t)VB * BIN_HUGE_CAP;
             uint8_t* status = want_status ? sc->status.p : nullptr;
 
-            if (F > 0) {
-                cudaStream_t ts = g.stream;
-                if (fork) {
-                    // later batches (and retries) overwrite records the previous raster launches were reading
-                    if (first > 0 || attempt > 0) CK(cudaEventRecord(g.chunk_done, g.stream));
-                    CK(cudaStreamWaitEvent(g.fork_stream, g.chunk_done, 0));
-                    ts = g.fork_stream;
-                }
-                k_tri_setup<<<dim3((F + 127) / 128, nv), 128, 0, ts>>>(S, dviews, Fr, sc->tris.p, status);
-                ++g.launches;
-                if (fork) CK(cudaEventRecord(g.tri_done, ts));
-            }
-            stage_mark(g, "tri_setup");
-            const int quad_blocks = std::max(1, std::min((sc->n_edges + 63) / 64, g.sm_count * 4));
-            k_quad_setup<<<dim3(quad_blocks, nv), 64, 0, g.stream>>>(sc->sil.p, sc->counters.p, dviews, Fr, sc->quads.p, E);
-            ++g.launches;
-            stage_mark(g, "quad_setup");
-            if (fork) CK(cudaStreamWaitEvent(g.stream, g.tri_done, 0));
-            const int bin_blocks = g.bin_blocks ? g.bin_blocks : g.sm_count * 2;
-            k_bin<false><<<dim3(bin_blocks, nv), 256, 0, g.stream>>>(Fr, sc->tris.p, sc->quads.p, sc->counters.p, E, B);
-            k_scan<<<dim3(nv, 2), 1024, 0, g.stream>>>(Fr, B, flags + 2 * first, sticky);
-            k_order<<<nv, 1024, 0, g.stream>>>(Fr, B);
-            k_bin<true><<<dim3(bin_blocks, nv), 256, 0, g.stream>>>(Fr, sc->tris.p, sc->quads.p, sc->counters.p, E, B);
-            g.launches += 4;
-            stage_mark(g, "bin");
-            RasterOut O;
-            O.winner = sc->winner.p; O.stencil = sc->stencil.p; O.z = want_z ? sc->zplane.p : nullptr; O.status = status;
             uint8_t* rgb_dev = (!host_out ? out_rgb : sc->rgb[rslot].p) + (size_t)first * npx * 3;
-            const int rows = row_end - row_begin;
-            // raster + shade (+ copy) in sub-chunks: set-up and binning above ran once for the whole batch, so a
-            // sub-chunk costs two launches.  Sub-chunks are independent (per-view planes, read-only lists): they go
-            // round-robin to a few auxiliary streams so that the tail of one raster launch overlaps the next, and
-            // their frames leave over PCIe (copy stream) while later sub-chunks render.
-            // host-asynchronous calls overlap their copies with the NEXT call, so they keep whole-batch launches
+            TileOut T;
+            T.rgb = rgb_dev; T.f32 = want_f32 ? sc->frame_f32.p : nullptr; T.bg_packed = bg_packed;
+            T.packed = fused ? nullptr : sc->packed.p;
+            T.winner = want_planes ? sc->winner.p : nullptr; T.stencil = want_planes ? sc->stencil.p : nullptr;
+            T.z = want_z ? sc->zplane.p : nullptr; T.status = status;
+            // later batches (and retries) overwrite records the previous raster launches were reading: the main stream
+            // has joined all of them at the end of the previous batch, the forked set-up stream has to as well
+            if (fork) CK(cudaEventRecord(g.chunk_done, g.stream));
+            // The batch runs as a PIPELINE of parts of `pipe` views: set-up + binning of part p+1 (main stream, high
+            // priority, small latency-bound launches) overlap the tile / shading kernels of part p (auxiliary streams),
+            // which fill the machine.  Within a part, tile + shading (+ the copy to the host) may be cut further into
+            // sub-chunks: sub-chunks are independent (per-view planes, read-only lists), they rotate over a few auxiliary
+            // streams so that the tail of one launch overlaps the next and their frames leave over PCIe (copy stream)
+            // while later sub-chunks render.
+            const bool serial = g.timing || dbg;
+            const int pipe = serial ? nv : std::min(nv, std::max(1, g.pipe_views));
             const int want_sub = !host_out ? g.dev_chunk : (host_async ? g.async_chunk : g.host_chunk);
-            const int sub = (g.timing || dbg || nv <= want_sub) ? nv : std::max(1, want_sub);
-            const bool multi = sub < nv;
-            if (multi) CK(cudaEventRecord(g.setup_done, g.stream));
+            const int n_aux = !host_out ? g.aux_dev : g.aux_host;
+            bool aux_used[Context::N_AUX] = {};
             int n_sub = 0;
-            for (int v0 = 0; v0 < nv; v0 += sub, ++n_sub) {
-                const int sv = std::min(sub, nv - v0);
-                cudaStream_t st = multi ? g.aux[n_sub % (!host_out ? g.aux_dev : g.aux_host)] : g.stream;
-                if (multi) CK(cudaStreamWaitEvent(st, g.setup_done, 0));
-                k_raster<<<(unsigned)sv * (unsigned)n_tiles, RASTER_THREADS, 0, st>>>(S, dviews, Fr, sc->tris.p,
-                                                                                   sc->quads.p, E, B, O, v0, sv);
+            for (int p0 = 0; p0 < nv; p0 += pipe) {
+                const int pv = std::min(pipe, nv - p0);
+                if (F > 0) {
+                    cudaStream_t ts = g.stream;
+                    if (fork) {
+                        CK(cudaStreamWaitEvent(g.fork_stream, g.chunk_done, 0));
+                        ts = g.fork_stream;
+                    }
+                    k_tri_setup<<<dim3((F + 127) / 128, pv), 128, 0, ts>>>(S, dviews, Fr, sc->tris.p, sc->boxes.p, status,
+                                                                           coop_count, sc->coop_list.p, p0);
+                    k_tri_count<<<dim3(std::max(1, std::min((F + 7) / 8, g.sm_count * 2)), pv), 256, 0, ts>>>(
+                        S, dviews, sc->tris.p, sc->boxes.p, status, coop_count, sc->coop_list.p, p0);
+                    g.launches += 2;
+                    if (fork) CK(cudaEventRecord(g.tri_done, ts));
+                }
+                stage_mark(g, "tri_setup");
+                const int quad_blocks = std::max(1, std::min((sc->n_edges + 63) / 64, g.sm_count * 4));
+                k_quad_setup<<<dim3(quad_blocks, pv), 64, 0, g.stream>>>(sc->sil.p, sc->counters.p, dviews, Fr, sc->quads.p, E, p0);
                 ++g.launches;
-                stage_mark(g, "raster");
-                k_shade<<<dim3((W + 31) / 32, (rows + B2R_SHADE_THREADS / 32 - 1) / (B2R_SHADE_THREADS / 32), sv),
-                          B2R_SHADE_THREADS, 0, st>>>(S, dviews, Fr, sc->tris.p, sc->winner.p, sc->stencil.p, rgb_dev, v0,
-                                                      want_f32 ? sc->frame_f32.p : nullptr, bg_packed);
-                ++g.launches;
-                stage_mark(g, "shade");
-                cudaEvent_t done = g.aux_done[n_sub % 16];
-                if (multi || host_out) CK(cudaEventRecord(done, st));
-                if (multi) CK(cudaStreamWaitEvent(g.stream, done, 0));  // the batch is complete on the main stream
-                if (host_out) {  // these frames travel on the copy stream while the next sub-chunk renders
-                    CK(cudaStreamWaitEvent(g.copy_stream, done, 0));
-                    const size_t band_off = (size_t)(H - row_end) * W * 3, band_bytes = (size_t)(row_end - row_begin) * W * 3;
-                    uint8_t* src = rgb_dev + (size_t)v0 * npx * 3;
-                    uint8_t* dst = out_rgb + (size_t)(first + v0) * npx * 3;
-                    if (band_bytes == npx * 3) {
-                        CK(cudaMemcpyAsync(dst, src, (size_t)sv * npx * 3, kind, g.copy_stream));
+                stage_mark(g, "quad_setup");
+                if (fork) CK(cudaStreamWaitEvent(g.stream, g.tri_done, 0));
+                const int bin_blocks = g.bin_blocks ? g.bin_blocks : g.sm_count * 2;
+                k_bin<false><<<dim3(bin_blocks, pv), 256, 0, g.stream>>>(Fr, sc->boxes.p, sc->quads.p, sc->counters.p, E, B, p0);
+                k_scan<<<dim3(pv, 2), 1024, 0, g.stream>>>(Fr, B, flags + 2 * first, sticky, p0, sc->counters.p, E, need_sil_flag);
+                k_order<<<pv, 1024, 0, g.stream>>>(Fr, B, p0);
+                k_bin<true><<<dim3(bin_blocks, pv), 256, 0, g.stream>>>(Fr, sc->boxes.p, sc->quads.p, sc->counters.p, E, B, p0);
+                g.launches += 4;
+                stage_mark(g, "bin");
+                const int sub = (serial || pv <= want_sub) ? pv : std::max(1, want_sub);
+                const bool multi = !serial && (sub < pv || pipe < nv);   // tile / shading leave the main stream
+                if (multi) CK(cudaEventRecord(g.setup_done, g.stream));
+                for (int v0 = p0; v0 < p0 + pv; v0 += sub, ++n_sub) {
+                    const int sv = std::min(sub, p0 + pv - v0);
+                    const int ai = n_sub % n_aux;
+                    cudaStream_t st = multi ? g.aux[ai] : g.stream;
+                    if (multi) { CK(cudaStreamWaitEvent(st, g.setup_done, 0)); aux_used[ai] = true; }
+                    if (fused) {
+                        k_tile<true><<<(unsigned)sv * (unsigned)n_tiles, RASTER_THREADS, 0, st>>>(
+                            S, dviews, Fr, sc->tris.p, sc->quads.p, E, B, T, v0, sv);
+                        ++g.launches;
+                        stage_mark(g, "tile");
                     } else {
-                        for (int i = 0; i < sv; ++i)
-                            CK(cudaMemcpyAsync(dst + (size_t)i * npx * 3 + band_off, src + (size_t)i * npx * 3 + band_off,
-                                               band_bytes, kind, g.copy_stream));
+                        k_tile<false><<<(unsigned)sv * (unsigned)n_tiles, RASTER_THREADS, 0, st>>>(
+                            S, dviews, Fr, sc->tris.p, sc->quads.p, E, B, T, v0, sv);
+                        ++g.launches;
+                        stage_mark(g, "raster");
+                        k_shade_packed<<<(unsigned)sv * (unsigned)n_tiles, RASTER_THREADS, 0, st>>>(
+                            S, dviews, Fr, sc->tris.p, B, T, v0, sv);
+                        ++g.launches;
+                        stage_mark(g, "shade");
+                    }
+                    cudaEvent_t done = g.aux_done[n_sub % 16];
+                    if (multi || host_out) CK(cudaEventRecord(done, st));
+                    if (multi) CK(cudaEventRecord(g.aux_last[ai], st));
+                    if (host_out) {  // these frames travel on the copy stream while the next sub-chunk renders
+                        CK(cudaStreamWaitEvent(g.copy_stream, done, 0));
+                        const size_t band_off = (size_t)(H - row_end) * W * 3, band_bytes = (size_t)(row_end - row_begin) * W * 3;
+                        uint8_t* src = rgb_dev + (size_t)v0 * npx * 3;
+                        uint8_t* dst = out_rgb + (size_t)(first + v0) * npx * 3;
+                        if (band_bytes == npx * 3) {
+                            CK(cudaMemcpyAsync(dst, src, (size_t)sv * npx * 3, kind, g.copy_stream));
+                        } else {
+                            for (int i = 0; i < sv; ++i)
+                                CK(cudaMemcpyAsync(dst + (size_t)i * npx * 3 + band_off, src + (size_t)i * npx * 3 + band_off,
+                                                   band_bytes, kind, g.copy_stream));
+                        }
                     }
                 }
             }
+            for (int ai = 0; ai < Context::N_AUX; ++ai)      // the batch is complete on the main stream
+                if (aux_used[ai]) CK(cudaStreamWaitEvent(g.stream, g.aux_last[ai], 0));
             if (want_status) {
                 const size_t ns = (size_t)nv * F;
                 k_status_resolve<<<(unsigned)((ns + 255) / 256), 256, 0, g.stream>>>(status, ns);
@@ -1039,9 +1098,10 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
         CK(cudaStreamSynchronize(g.copy_stream));
         int need_tri = 0, need_quad = 0;
         for (int i = 0; i < n_views; ++i) { need_tri = std::max(need_tri, flags[2 * i]); need_quad = std::max(need_quad, flags[2 * i + 1]); }
-        if (!need_tri && !need_quad) return *err_flag ? fail_index() : 0;
-        if (need_tri) { sc->tri_cap = need_tri + need_tri / 4; sc->tri_list.release(); }
-        if (need_quad) { sc->quad_cap = need_quad + need_quad / 4; sc->quad_list.release(); sc->pair_list.release(); }
+        const int need_sil = *need_sil_flag;
+        if (!need_tri && !need_quad && !need_sil) return *err_flag ? fail_index() : 0;
+        b2r_scene_grow_lists(sc, need_tri, need_quad, need_sil);
+        *need_sil_flag = 0;
     }
     return fail("tile list capacity overflow");
 }

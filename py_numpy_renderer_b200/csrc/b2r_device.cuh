@@ -50,6 +50,8 @@ struct MaterialDev {
     double Ns;
     int map_Kd, map_Ks, norm;
     int ns_int;  // Ns if it is a small non-negative integer (pow by squaring), else -1
+    int ns_log2; // k if Ns == 2^k (k squarings), else -1
+    int pad;
 };
 
 struct TextureDev {
@@ -112,6 +114,14 @@ struct TriRec {  // 128 B (8-byte aligned on purpose: staged copies in shared me
     short bx0, bx1, by0, by1;           // pixel box [bx0,bx1) x [by0,by1)               8
     int flags;                          //                                               4
     int pad;                            //                                               4
+};
+
+// What binning needs of a face, 16 B instead of the 128-byte record (with a million faces per view k_bin is bound by
+// the bytes it reads): written by k_tri_setup for EVERY face, flags == 0 for faces that are culled / empty / clipped.
+struct __align__(16) TriBox {
+    short bx0, bx1, by0, by1;
+    int flags;  // TR_*
+    int pad;
 };
 
 // ---- shadow volume quads -------------------------------------------------------------------------------------------

@@ -11,18 +11,27 @@
 //   k_bin<FILL>     per primitive    tile lists (count / fill): thread per face, warp per quad with the exact
 //                                    corner classification of every (quad, tile) pair
 //   k_scan          per view         exclusive scan of the tile counts
-//   k_raster        per 32x32 tile   (1) depth: staged triangle lists, dense (triangle,pixel) dealing, 64-bit keyed
+//   k_tile<FUSED>   per 32x32 tile   (1) depth: staged triangle lists, dense (triangle,pixel) dealing, 64-bit keyed
 //                                    smem atomics  (2) stencil: depth-range classification, exact row spans, dense
 //                                    pixel dealing  (3) winner: verified last-improver, full pass only on ties
+//                                    (4) one packed word per pixel (winner | lit << 31) -- or, FUSED, the shading itself
 //                                                                          (triangular.py:78-118, 341-368)
-//   k_shade         per pixel        Phong + textures + tangent normal maps + skybox + tonemap, warp-packed stores
+//   k_shade_packed  per 32x32 tile   Phong + textures + tangent normal maps + skybox + tonemap, warp-packed stores;
+//                                    tiles without primitives are recognised from their empty lists
 //                                                                          (triangular.py:135-171, core.py:138-228,640; cube_map.py:63-101)
 #pragma once
 #include "b2r_device.cuh"
 
 namespace b2r {
 
-__constant__ float c_lut[2][256];  // [B2R_TEX_UNORM | B2R_TEX_SNORM][u8] -> the reference's float32 texel
+// The reference's float32 texel from the uint8 source (core.py:96-104): f32(u8/255) or f32(u8/255*2-1), float64
+// intermediates.  Closed forms that are bit-identical for all 256 inputs (checked exhaustively in
+// tests/test_host_api.py::test_texel_decode_closed_forms): a per-lane table lookup in constant memory serialises on
+// every distinct index of the warp, these are four instructions.
+__device__ __forceinline__ float texel_decode(unsigned u8, int snorm) {
+    const double u = (double)u8;
+    return snorm ? (float)(u * (2.0 / 255.0) - 1.0) : (float)(u * (1.0 / 255.0));
+}
 
 // optional work counters (build with -DB2R_STATS; read with b2r_debug_stats) -- never in the production library
 __device__ unsigned long long g_stats[16];
@@ -37,6 +46,7 @@ struct SceneDev {
     const double2* uv;       // (Ttot) u, v
     const double* nrm;       // (Ntot,3)
     const FaceStatic* faces; // (F)
+    const int4* face_vf;     // (F) v0, v1, v2, FS_* flags: what the per-view set-up needs of a face, 16 B
     const ShadeStatic* shade; // (F) gathered per-face shading inputs
     const MaterialDev* mats;
     const TextureDev* tex;
@@ -79,17 +89,19 @@ __global__ void k_facing(SceneDev S, LightDev L, uint8_t* __restrict__ facing) {
 
 // One thread per undirected edge: replay the set toggles of shadow_volumes() in face order, then extrude.
 // state: 0 absent, 1 present as (lo,hi), 2 present as (hi,lo); `persist` != nullptr carries it across renders.
-__global__ void k_silhouette(SceneDev S, LightDev L, const uint8_t* __restrict__ facing, int8_t* persist,
-                             SilEdge* __restrict__ out, int* __restrict__ out_count, int* __restrict__ per_model_count,
-                             const int* __restrict__ edge_model) {
+__global__ void k_silhouette(SceneDev S, LightDev L, const uint8_t* __restrict__ facing, int8_t* persist, int toggle,
+                             SilEdge* __restrict__ out, int out_cap, int* __restrict__ out_count,
+                             int* __restrict__ per_model_count, const int* __restrict__ edge_model) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= S.n_edges) return;
     int state = persist ? persist[e] : 0;
-    for (int i = S.edge_ptr[e]; i < S.edge_ptr[e + 1]; ++i) {
-        const int inc = S.edge_inc[i];
-        if (facing[inc >> 1]) state = state ? 0 : 1 + (inc & 1);
+    if (toggle || !persist) {   // toggle == 0: a retry after a capacity overflow, the persistent state is already final
+        for (int i = S.edge_ptr[e]; i < S.edge_ptr[e + 1]; ++i) {
+            const int inc = S.edge_inc[i];
+            if (facing[inc >> 1]) state = state ? 0 : 1 + (inc & 1);
+        }
+        if (persist) persist[e] = (int8_t)state;
     }
-    if (persist) persist[e] = (int8_t)state;
     if (!state) return;
     const int2 ev = S.edge_v[e];
     const double4 A4 = S.pos[state == 1 ? ev.x : ev.y], B4 = S.pos[state == 1 ? ev.y : ev.x];
@@ -116,6 +128,7 @@ __global__ void k_silhouette(SceneDev S, LightDev L, const uint8_t* __restrict__
     }
     const int slot = atomicAdd(out_count, 1);
     atomicAdd(per_model_count + edge_model[e], 1);
+    if (slot >= out_cap) return;   // capacity overflow: the count keeps growing, the host raises the capacity and retries
     SilEdge& o = out[slot];
 #pragma unroll
     for (int k = 0; k < 4; ++k) { o.q[k] = A[k]; o.q[4 + k] = B[k]; o.q[8 + k] = Dd[k]; o.q[12 + k] = Cc[k]; }
@@ -148,119 +161,131 @@ __device__ __forceinline__ bool tri_pixel_in(const TriRec& r, const double* cc, 
 
 constexpr int COV_SERIAL_MAX = 128;  // boxes up to this many pixels are counted by the owning thread
 
-__global__ void k_tri_setup(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, TriRec* __restrict__ recs,
-                            uint8_t* __restrict__ status) {
-    const int view = blockIdx.y;
+// One thread per (face, view).  The common path keeps no clip coordinates alive (the per-pixel clip test is elided for
+// faces well inside both frusta): 3 x (2 vec.mat, 1/w, viewport) -> cull -> box -> float32
+// constants -> N == 1 count over the (small) box.  Faces that need the per-pixel clip test for the count, or whose
+// box is large, are queued for k_tri_count (a warp per face).  Every face writes its 16-byte TriBox; only valid faces
+// touch their 128-byte record.
+__global__ void __launch_bounds__(128, 8)
+k_tri_setup(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, TriRec* __restrict__ recs,
+            TriBox* __restrict__ boxes, uint8_t* __restrict__ status, int* __restrict__ coop_count,
+            int* __restrict__ coop_list, int view0) {
+    const int view = blockIdx.y + view0;
     const ViewDev& V = views[view];
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    TriRec* my = nullptr;
+    if (f >= S.n_faces) return;
+    const int4 fv = S.face_vf[f];   // v0, v1, v2, FS_* flags
+    const int vidx[3] = {fv.x, fv.y, fv.z};
+    TriRec r;
+    double sx[3], sy[3], sz[3];
+    bool inside = true;   // all three vertices well inside both frusta: the per-pixel clip test cannot fail
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {  // triangular.py:36-45
+        const double4 p = S.pos[vidx[i]];
+        const double w[4] = {p.x, p.y, p.z, p.w};
+        double c[4];
+        vec4_mat4(w, V.mvp, c);
+        if (fv.w & FS_CLIP) {
+            double cd[4];
+            vec4_mat4(w, V.mvp_dbg, cd);
+            const double m = 1.0 - 1e-9;
+            const double wc = c[3] * m, wd = cd[3] * m;
+            inside = inside && wc > 0 && wd > 0 && fabs(c[0]) < wc && fabs(c[1]) < wc && fabs(c[2]) < wc &&
+                     fabs(cd[0]) < wd && fabs(cd[1]) < wd && fabs(cd[2]) < wd;
+        }
+        const double dpt = 1.0 / c[3];
+        const double t[4] = {c[0] * dpt, c[1] * dpt, c[2] * dpt, c[3] * dpt};
+        double s4[4];
+        vec4_mat4(t, V.viewport, s4);
+        sx[i] = s4[0]; sy[i] = s4[1]; sz[i] = s4[2];
+        r.d[i] = dpt;
+    }
+    int st = -1;
     bool need_coop = false;
-    FaceStatic fs;
-    double cc[CLIP_DOUBLES];
-    if (f < S.n_faces) {
-        fs = S.faces[f];
-        load_clip_coords(S, V, fs, cc);
-        TriRec r;
-        double sx[3], sy[3], sz[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {  // triangular.py:42-45
-            const double* ci = cc + i * 4;
-            const double dpt = 1.0 / ci[3];
-            const double t[4] = {ci[0] * dpt, ci[1] * dpt, ci[2] * dpt, ci[3] * dpt};
-            double s[4];
-            vec4_mat4(t, V.viewport, s);
-            sx[i] = s[0]; sy[i] = s[1]; sz[i] = s[2];
-            r.d[i] = dpt;
-        }
-        int st = -1;
-        if (V.backface) {  // normalize(cross(b-a, c-a))[2] < 0 on screen xyz (triangular.py:47, core.py:132-136)
-            const double e0x = sx[1] - sx[0], e0y = sy[1] - sy[0], e0z = sz[1] - sz[0];
-            const double e1x = sx[2] - sx[0], e1y = sy[2] - sy[0], e1z = sz[2] - sz[0];
-            double n[3] = {e0y * e1z - e0z * e1y, e0z * e1x - e0x * e1z, e0x * e1y - e0y * e1x};
-            normalize3(n);
-            if (n[2] < 0) st = B2R_FACE_BACK_FACE_CULLING;
-        }
-        if (st < 0) {  // bound_box (transformation.py:35-43)
-            double mnx = fmin(fmin(sx[0], sx[1]), sx[2]), mxx = fmax(fmax(sx[0], sx[1]), sx[2]);
-            double mny = fmin(fmin(sy[0], sy[1]), sy[2]), mxy = fmax(fmax(sy[0], sy[1]), sy[2]);
-            mnx = mnx < 0 ? 0 : mnx; mxx = mxx > Fr.W ? (double)Fr.W : mxx;
-            mny = mny < 0 ? 0 : mny; mxy = mxy > Fr.H ? (double)Fr.H : mxy;
-            if (mnx > mxx || mny > mxy || !(mnx == mnx) || !(mxx == mxx) || !(mny == mny) || !(mxy == mxy)) {
-                st = B2R_FACE_EMPTY_Z;
-            } else {
-                r.bx0 = (short)(int)ceil(mnx); r.bx1 = (short)(int)ceil(mxx);
-                r.by0 = (short)(int)ceil(mny); r.by1 = (short)(int)ceil(mxy);
-            }
-        }
-        if (st < 0) {  // barycentric constants (transformation.py:16-28)
-            r.ax = sx[0]; r.ay = sy[0];
-            r.v0x = sx[1] - sx[0]; r.v0y = sy[1] - sy[0];
-            r.v1x = sx[2] - sx[0]; r.v1y = sy[2] - sy[0];
-            r.d00 = (float)seq2(r.v0x, r.v0y, r.v0x, r.v0y);
-            r.d01 = (float)seq2(r.v0x, r.v0y, r.v1x, r.v1y);
-            r.d11 = (float)seq2(r.v1x, r.v1y, r.v1x, r.v1y);
-            const float den = __fsub_rn(__fmul_rn(r.d00, r.d11), __fmul_rn(r.d01, r.d01));
-            if (den == 0.0f) st = B2R_FACE_EMPTY_B;
-            else r.inv = __fdiv_rn(1.0f, den);
-        }
-        if (st < 0) {
-            const int nx = r.bx1 > r.bx0 ? r.bx1 - r.bx0 : 0, ny = r.by1 > r.by0 ? r.by1 - r.by0 : 0;
-            const int n_box = nx * ny;
-            if (n_box == 0) st = B2R_FACE_CLIPPED;
-            else {
-                r.flags = TR_VALID | (n_box == 1 ? TR_BOX_ONE : 0) | ((fs.flags & FS_NO_ZWRITE) ? TR_NO_ZWRITE : 0);
-#pragma unroll
-                for (int i = 0; i < 3; ++i) r.zl[i] = linearize_z(sz[i], V);
-                if (fs.flags & FS_CLIP) {
-                    // The per-pixel clip test passes for every covered pixel when all three vertices are inside
-                    // both frusta with a relative margin >> 6 ulp (DESIGN.md "clip test elision").
-                    bool inside = true;
-                    const double m = 1.0 - 1e-9;
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        const double* c = cc + i * 4;
-                        const double* cd = cc + 12 + i * 4;
-                        const double w = c[3] * m, wd = cd[3] * m;
-                        inside = inside && w > 0 && wd > 0 && fabs(c[0]) < w && fabs(c[1]) < w && fabs(c[2]) < w &&
-                                 fabs(cd[0]) < wd && fabs(cd[1]) < wd && fabs(cd[2]) < wd;
-                    }
-                    if (!inside) r.flags |= TR_NEEDS_CLIP;
-                }
-                r.pad = 0;
-                // N of `bar_screen[Bi]` decides the evaluation order of the z interpolation: count covered &
-                // unclipped pixels, stopping at 2.
-                if (n_box <= COV_SERIAL_MAX) {
-                    int cnt = 0, px = r.bx0, py = r.by0;
-                    for (int i = 0; i < n_box && cnt < 2; ++i) {
-                        float bu, bv, bw;
-                        cnt += tri_pixel_in(r, cc, px, py, bu, bv, bw) ? 1 : 0;
-                        if (++py == r.by1) { py = r.by0; ++px; }
-                    }
-                    if (cnt == 1) r.flags |= TR_COV_ONE;
-                    if (cnt == 0) { st = B2R_FACE_CLIPPED; r.flags = 0; }
-                } else {
-                    need_coop = true;
-                }
-                my = recs + (size_t)view * S.n_faces + f;
-                *my = r;
-            }
-        }
-        if (st >= 0) {
-            recs[(size_t)view * S.n_faces + f].flags = 0;
-            if (status) status[(size_t)view * S.n_faces + f] = (uint8_t)st;
-        } else if (status) {
-            status[(size_t)view * S.n_faces + f] = 0xE0;  // pending: raster ORs coverage / z / lit bits into the low bits
+    if (V.backface) {  // normalize(cross(b-a, c-a))[2] < 0 on screen xyz (triangular.py:47, core.py:132-136)
+        const double e0x = sx[1] - sx[0], e0y = sy[1] - sy[0], e0z = sz[1] - sz[0];
+        const double e1x = sx[2] - sx[0], e1y = sy[2] - sy[0], e1z = sz[2] - sz[0];
+        double n[3] = {e0y * e1z - e0z * e1y, e0z * e1x - e0x * e1z, e0x * e1y - e0y * e1x};
+        normalize3(n);
+        if (n[2] < 0) st = B2R_FACE_BACK_FACE_CULLING;
+    }
+    if (st < 0) {  // bound_box (transformation.py:35-43)
+        double mnx = fmin(fmin(sx[0], sx[1]), sx[2]), mxx = fmax(fmax(sx[0], sx[1]), sx[2]);
+        double mny = fmin(fmin(sy[0], sy[1]), sy[2]), mxy = fmax(fmax(sy[0], sy[1]), sy[2]);
+        mnx = mnx < 0 ? 0 : mnx; mxx = mxx > Fr.W ? (double)Fr.W : mxx;
+        mny = mny < 0 ? 0 : mny; mxy = mxy > Fr.H ? (double)Fr.H : mxy;
+        if (mnx > mxx || mny > mxy || !(mnx == mnx) || !(mxx == mxx) || !(mny == mny) || !(mxy == mxy)) {
+            st = B2R_FACE_EMPTY_Z;
+        } else {
+            r.bx0 = (short)(int)ceil(mnx); r.bx1 = (short)(int)ceil(mxx);
+            r.by0 = (short)(int)ceil(mny); r.by1 = (short)(int)ceil(mxy);
         }
     }
-    // warp-cooperative count for large boxes (ballot queue): lanes stride over the box, stop at 2 hits
-    unsigned queue = __ballot_sync(0xffffffffu, need_coop);
-    while (queue) {
-        const int src = __ffs(queue) - 1;
-        queue &= queue - 1;
-        const int sf = __shfl_sync(0xffffffffu, f, src);
-        __syncwarp();
-        const TriRec r = recs[(size_t)view * S.n_faces + sf];
+    if (st < 0) {  // barycentric constants (transformation.py:16-28)
+        r.ax = sx[0]; r.ay = sy[0];
+        r.v0x = sx[1] - sx[0]; r.v0y = sy[1] - sy[0];
+        r.v1x = sx[2] - sx[0]; r.v1y = sy[2] - sy[0];
+        r.d00 = (float)seq2(r.v0x, r.v0y, r.v0x, r.v0y);
+        r.d01 = (float)seq2(r.v0x, r.v0y, r.v1x, r.v1y);
+        r.d11 = (float)seq2(r.v1x, r.v1y, r.v1x, r.v1y);
+        const float den = __fsub_rn(__fmul_rn(r.d00, r.d11), __fmul_rn(r.d01, r.d01));
+        if (den == 0.0f) st = B2R_FACE_EMPTY_B;
+        else r.inv = __fdiv_rn(1.0f, den);
+    }
+    if (st < 0) {
+        const int nx = r.bx1 > r.bx0 ? r.bx1 - r.bx0 : 0, ny = r.by1 > r.by0 ? r.by1 - r.by0 : 0;
+        const int n_box = nx * ny;
+        if (n_box == 0) st = B2R_FACE_CLIPPED;
+        else {
+            r.flags = TR_VALID | (n_box == 1 ? TR_BOX_ONE : 0) | ((fv.w & FS_NO_ZWRITE) ? TR_NO_ZWRITE : 0) |
+                      (((fv.w & FS_CLIP) && !inside) ? TR_NEEDS_CLIP : 0);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) r.zl[i] = linearize_z(sz[i], V);
+            r.pad = 0;
+            // N of `bar_screen[Bi]` decides the evaluation order of the z interpolation: count covered & unclipped
+            // pixels, stopping at 2.  Small boxes without a clip test are counted right here.
+            if (n_box <= COV_SERIAL_MAX && !(r.flags & TR_NEEDS_CLIP)) {
+                int cnt = 0, px = r.bx0, py = r.by0;
+                for (int i = 0; i < n_box && cnt < 2; ++i) {
+                    float bu, bv, bw;
+                    cnt += tri_bary(r, px, py, bu, bv, bw) ? 1 : 0;
+                    if (++py == r.by1) { py = r.by0; ++px; }
+                }
+                if (cnt == 1) r.flags |= TR_COV_ONE;
+                if (cnt == 0) { st = B2R_FACE_CLIPPED; r.flags = 0; }
+            } else {
+                need_coop = true;
+            }
+            if (st < 0) recs[(size_t)view * S.n_faces + f] = r;
+        }
+    }
+    TriBox bx;
+    bx.pad = 0;
+    if (st >= 0) {   // culled / empty / clipped: the 128-byte record is not touched at all
+        bx.bx0 = bx.bx1 = bx.by0 = bx.by1 = 0; bx.flags = 0;
+        if (status) status[(size_t)view * S.n_faces + f] = (uint8_t)st;
+    } else {
+        bx.bx0 = r.bx0; bx.bx1 = r.bx1; bx.by0 = r.by0; bx.by1 = r.by1; bx.flags = r.flags;
+        if (status) status[(size_t)view * S.n_faces + f] = 0xE0;  // pending: the tile kernel ORs coverage / z / lit bits in
+    }
+    boxes[(size_t)view * S.n_faces + f] = bx;
+    if (need_coop) coop_list[(size_t)view * S.n_faces + atomicAdd(coop_count + view, 1)] = f;
+}
+
+// N == 1 count of the faces k_tri_setup queued (large boxes, faces that need the per-pixel clip test): a warp per face,
+// lanes stride over the box in a scattered order and stop at two hits.
+__global__ void k_tri_count(SceneDev S, const ViewDev* __restrict__ views, TriRec* __restrict__ recs,
+                            TriBox* __restrict__ boxes, uint8_t* __restrict__ status, const int* __restrict__ coop_count,
+                            const int* __restrict__ coop_list, int view0) {
+    const int view = blockIdx.y + view0;
+    const ViewDev& V = views[view];
+    const int lane = threadIdx.x & 31;
+    const int n_queued = coop_count[view];
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; qi < n_queued; qi += warps) {
+        const int sf = coop_list[(size_t)view * S.n_faces + qi];
+        TriRec* my = recs + (size_t)view * S.n_faces + sf;
+        const TriRec r = *my;
         double c2[CLIP_DOUBLES];
         if (r.flags & TR_NEEDS_CLIP) load_clip_coords(S, V, S.faces[sf], c2);
         const int ny = r.by1 - r.by0, n_box = (r.bx1 - r.bx0) * ny;
@@ -283,9 +308,13 @@ __global__ void k_tri_setup(SceneDev S, const ViewDev* __restrict__ views, Frame
             if (j >= n_box) j -= n_box;
             cnt += __popc(__ballot_sync(0xffffffffu, in));
         }
-        if (lane == src) {
-            if (cnt == 1) my->flags |= TR_COV_ONE;
-            if (cnt == 0) { my->flags = 0; if (status) status[(size_t)view * S.n_faces + f] = B2R_FACE_CLIPPED; }
+        if (lane == 0) {
+            if (cnt == 1) { my->flags = r.flags | TR_COV_ONE; boxes[(size_t)view * S.n_faces + sf].flags = r.flags | TR_COV_ONE; }
+            if (cnt == 0) {
+                my->flags = 0;
+                boxes[(size_t)view * S.n_faces + sf].flags = 0;
+                if (status) status[(size_t)view * S.n_faces + sf] = B2R_FACE_CLIPPED;
+            }
         }
     }
 }
@@ -294,10 +323,11 @@ __global__ void k_tri_setup(SceneDev S, const ViewDev* __restrict__ views, Frame
 // then projection and plane set-up of resterize_quadrangle (triangular.py:325-340).  One thread per quad.
 __device__ void quad_setup_one(const SilEdge& sil, const ViewDev& V, const FrameDev& Fr, QuadRec& R);
 __global__ void k_quad_setup(const SilEdge* __restrict__ sil, const int* __restrict__ sil_count,
-                             const ViewDev* __restrict__ views, FrameDev Fr, QuadRec* __restrict__ recs, int rec_stride) {
-    const int view = blockIdx.y;
+                             const ViewDev* __restrict__ views, FrameDev Fr, QuadRec* __restrict__ recs, int rec_stride,
+                             int view0) {
+    const int view = blockIdx.y + view0;
     const ViewDev& V = views[view];
-    const int n_quads = *sil_count;
+    const int n_quads = min(*sil_count, rec_stride);   // rec_stride = capacity of the silhouette / quad records
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n_quads; q += gridDim.x * blockDim.x)
         quad_setup_one(sil[q], V, Fr, recs[(size_t)view * rec_stride + q]);
 }
@@ -380,6 +410,7 @@ __device__ __forceinline__ double edge_fn(double px, double py, double x0, doubl
 // roundings, so its extremes over the rectangle are attained, EXACTLY, at corners:
 //   0 = no pixel of the rectangle can be inside,  1 = some may be,  2 = every pixel of the rectangle is inside.
 constexpr int QUAD_FULL_BIT = 1 << 30;  // flag in a tile-list entry: the quad covers every pixel of the tile
+constexpr int TRI_CLIP_BIT = 1 << 30;   // flag in a triangle tile-list entry: the face needs the per-pixel clip test
 __device__ __forceinline__ int quad_tile_class(const QuadRec& R, int x0, int x1, int y0, int y1) {
     bool full = true;
     for (int i = 0; i < R.n; ++i) {
@@ -425,12 +456,12 @@ constexpr int BIN_HUGE = 256, BIN_HUGE_CAP = 64;
 constexpr int BIN_PAIR_BUF = 128;  // per-warp shared-memory run of (quad, tile) pairs between two global appends
 constexpr int BIN_SUPER = 4;  // quads: tiles are classified in blocks of BIN_SUPER x BIN_SUPER first
 template <bool FILL>
-__global__ void k_bin(FrameDev Fr, const TriRec* __restrict__ tris, const QuadRec* __restrict__ quads,
-                      const int* __restrict__ sil_count, int quad_stride, BinDev B) {
-    const int view = blockIdx.y;
+__global__ void k_bin(FrameDev Fr, const TriBox* __restrict__ boxes, const QuadRec* __restrict__ quads,
+                      const int* __restrict__ sil_count, int quad_stride, BinDev B, int view0) {
+    const int view = blockIdx.y + view0;
     const int lane = threadIdx.x & 31;
     const int n_tiles = Fr.tiles_x * Fr.tiles_y;
-    const int n_quads = *sil_count;
+    const int n_quads = min(*sil_count, quad_stride);   // quad_stride = capacity of the silhouette / quad records
     const int band_y0 = Fr.row_begin, band_y1 = Fr.row_end;
     if (FILL && (B.overflow[view * 2] | B.overflow[view * 2 + 1])) return;
     const int stride = gridDim.x * blockDim.x;
@@ -444,9 +475,11 @@ __global__ void k_bin(FrameDev Fr, const TriRec* __restrict__ tris, const QuadRe
         const int slot = base + lane;
         int bx0 = 0, bx1 = 0, by0 = 0, by1 = 0;
         bool valid = false;
+        int entry = slot;   // tile-list entry: face index, TRI_CLIP_BIT set when the face needs the per-pixel clip test
         if (slot < Fr.n_faces) {
-            const TriRec& r = tris[(size_t)view * Fr.n_faces + slot];
+            const TriBox r = boxes[(size_t)view * Fr.n_faces + slot];   // one 16-byte load
             if (r.flags & TR_VALID) { valid = true; bx0 = r.bx0; bx1 = r.bx1; by0 = r.by0; by1 = r.by1; }
+            if (r.flags & TR_NEEDS_CLIP) entry |= TRI_CLIP_BIT;
         }
         by0 = max(by0, band_y0); by1 = min(by1, band_y1);
         valid = valid && by0 < by1 && bx0 < bx1;
@@ -473,7 +506,7 @@ __global__ void k_bin(FrameDev Fr, const TriRec* __restrict__ tris, const QuadRe
                 if (lane == leader) base = atomicAdd(tri_count + t, __popc(peers));
                 if (FILL) {
                     base = __shfl_sync(peers, base, leader);
-                    tri_list[tri_off[t] + base + __popc(peers & ((1u << lane) - 1))] = slot;
+                    tri_list[tri_off[t] + base + __popc(peers & ((1u << lane) - 1))] = entry;
                 }
             }
         }
@@ -483,6 +516,7 @@ __global__ void k_bin(FrameDev Fr, const TriRec* __restrict__ tris, const QuadRe
             queue &= queue - 1;
             const int s_tx0 = __shfl_sync(0xffffffffu, tx0, src), s_ty0 = __shfl_sync(0xffffffffu, ty0, src);
             const int s_tw = __shfl_sync(0xffffffffu, tw, src), s_nt = __shfl_sync(0xffffffffu, nt, src);
+            const int s_entry = __shfl_sync(0xffffffffu, entry, src);
             if (s_nt > BIN_HUGE) {
                 // A screen-filling triangle: thousands of list inserts, each waiting for its atomic, would make this
                 // one warp the critical path of the fill pass.  The count pass (fire-and-forget atomics) notes the
@@ -501,7 +535,7 @@ __global__ void k_bin(FrameDev Fr, const TriRec* __restrict__ tris, const QuadRe
             }
             for (int i = lane; i < s_nt; i += 32) {
                 const int t = (s_ty0 + i / s_tw - Fr.tile_row0) * Fr.tiles_x + s_tx0 + i % s_tw;
-                if (FILL) tri_list[tri_off[t] + atomicAdd(tri_count + t, 1)] = base + src;
+                if (FILL) tri_list[tri_off[t] + atomicAdd(tri_count + t, 1)] = s_entry;
                 else atomicAdd(tri_count + t, 1);
             }
         }
@@ -513,13 +547,14 @@ __global__ void k_bin(FrameDev Fr, const TriRec* __restrict__ tris, const QuadRe
         const int nh = min(B.huge_count[view], BIN_HUGE_CAP);
         for (int h = 0; h < nh; ++h) {   // the noted screen-filling faces: one tile per thread of the grid
             const int face = B.huge_list[view * BIN_HUGE_CAP + h];
-            const TriRec& r = tris[(size_t)view * Fr.n_faces + face];
+            const TriBox r = boxes[(size_t)view * Fr.n_faces + face];
+            const int h_entry = face | ((r.flags & TR_NEEDS_CLIP) ? TRI_CLIP_BIT : 0);
             const int bx0 = r.bx0, bx1 = r.bx1, by0 = max((int)r.by0, band_y0), by1 = min((int)r.by1, band_y1);
             const int tx0 = bx0 / TILE_W, ty0 = by0 / TILE_H, tw = (bx1 - 1) / TILE_W - tx0 + 1;
             const int nt = tw * ((by1 - 1) / TILE_H - ty0 + 1);
             for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nt; i += stride) {
                 const int t = (ty0 + i / tw - Fr.tile_row0) * Fr.tiles_x + tx0 + i % tw;
-                tri_list[tri_off[t] + atomicAdd(tri_count + t, 1)] = face;
+                tri_list[tri_off[t] + atomicAdd(tri_count + t, 1)] = h_entry;
             }
         }
         // the count pass left the surviving (quad, tile) pairs behind: the fill pass only scatters them
@@ -612,8 +647,9 @@ __global__ void k_bin(FrameDev Fr, const TriRec* __restrict__ tris, const QuadRe
 
 // exclusive scan of the tile counts of one (view, kind); resets the counts to 0 so k_bin<true> can reuse them
 // as cursors.  One CTA of 1024 threads.
-__global__ void k_scan(FrameDev Fr, BinDev B, int* __restrict__ host_flags, int* sticky) {  // both: mapped pinned memory
-    const int view = blockIdx.x, kind = blockIdx.y;
+__global__ void k_scan(FrameDev Fr, BinDev B, int* __restrict__ host_flags, int* sticky, int view0,
+                       const int* __restrict__ sil_count, int sil_cap, int* need_sil) {  // flags: mapped pinned memory
+    const int view = blockIdx.x + view0, kind = blockIdx.y;
     const int n_tiles = Fr.tiles_x * Fr.tiles_y;
     int* count = (kind ? B.quad_count : B.tri_count) + (size_t)view * n_tiles;
     int* off = (kind ? B.quad_off : B.tri_off) + (size_t)view * (n_tiles + 1);
@@ -651,6 +687,10 @@ __global__ void k_scan(FrameDev Fr, BinDev B, int* __restrict__ host_flags, int*
         // device-resident renders: overflow of ANY call since the last b2r_sync must survive later, fitting calls.
         // Racing views all store a sufficient-or-retried size (the host grows the list and the caller renders again).
         if (sticky && carry > cap) sticky[kind] = carry;
+        if (kind == 1 && *sil_count > sil_cap) {   // the silhouette did not fit its records (same for every view)
+            *need_sil = *sil_count;
+            if (sticky) sticky[3] = *sil_count;
+        }
     }
 }
 
@@ -663,8 +703,8 @@ __device__ __forceinline__ int tile_cost_class(int n_tri, int n_quad) {
     const int cost = 4 * n_quad + n_tri;
     return cost >= 1024 ? 0 : cost >= 256 ? 1 : cost >= 64 ? 2 : cost >= 16 ? 3 : cost > 0 ? 4 : 5;
 }
-__global__ void k_order(FrameDev Fr, BinDev B) {
-    const int view = blockIdx.x;
+__global__ void k_order(FrameDev Fr, BinDev B, int view0) {
+    const int view = blockIdx.x + view0;
     const int n_tiles = Fr.tiles_x * Fr.tiles_y;
     const int* tri_off = B.tri_off + (size_t)view * (n_tiles + 1);
     const int* quad_off = B.quad_off + (size_t)view * (n_tiles + 1);
@@ -689,13 +729,6 @@ __global__ void k_order(FrameDev Fr, BinDev B) {
 // =====================================================================================================================
 // tile raster: z -> stencil -> winner, all in shared memory
 // =====================================================================================================================
-struct RasterOut {
-    int* winner;        // (views, H, W)  buffer rows
-    short* stencil;     // (views, H, W)
-    double* z;          // optional
-    uint8_t* status;    // optional (views, F)
-};
-
 // Can any pixel of the rectangle [x0,x1] x [y0,y1] (inclusive) pass the float32 coverage test of `tri_bary`?
 // The computed barycentrics are, up to float32 rounding, affine functions of the pixel: b_i = t_i(p) + eps_i with
 //   t_v = (d11*D20 - d01*D21)*inv,  t_w = (d00*D21 - d01*D20)*inv,  t_u = 1 - t_v - t_w   (real arithmetic on the
@@ -737,422 +770,6 @@ constexpr int STAGE_CLIP = 16;   // of which at most this many need the per-pixe
 constexpr int REC_DOUBLES = 17;  // 128-byte record + 8 bytes of padding: consecutive records start on different banks
 static_assert(sizeof(TriRec) == 128, "TriRec layout");
 
-struct RasterSmem {
-    unsigned long long z[TILE_PX];          // order-preserving keys of the float64 z-buffer      8 KB
-    int id[TILE_PX];                        // winner face                                        4 KB
-    int st[TILE_PX];                        // stencil count                                      4 KB
-    double tri[STAGE_TRIS][REC_DOUBLES];    // staged per-tile triangle list                      4.25 KB
-    double clip[STAGE_CLIP][CLIP_DOUBLES];  // clip coordinates of the staged triangles that need them   3 KB
-    int face[STAGE_TRIS];
-    int start[STAGE_TRIS + 1];              // exclusive scan of the pixel counts of the staged triangles
-    int geo[STAGE_TRIS];                    // box inside the tile: x0 | y0 << 8 | width << 16
-    signed char clip_slot[STAGE_TRIS];
-    unsigned long long red_min[RASTER_WARPS], red_max[RASTER_WARPS];
-    int n_round;
-    int next_quad;
-    int uniform;
-    int need_full;                          // the fast winner resolution is not provably right: run the full pass
-};
-
-// One pass over the tile's triangle list.
-//   PASS 1: zbuf = min (RH) / max (LH) of z over covered, unclipped pixels (triangular.py:96-118), remembering the
-//           face that last improved each pixel; an exact tie between two faces raises `need_full`.
-//   PASS 3: winner = greatest face index whose z equals the final zbuf (the reference lets later faces overwrite).
-// Work split: the (triangle, pixel) pairs of a staged round are flattened into one dense list (exclusive scan of the
-// per-triangle pixel counts) and dealt 32 at a time, so a warp is full whether the tile holds a thousand one-pixel
-// triangles or a single triangle covering all of it.
-template <int PASS>
-__device__ __forceinline__ void raster_tris(RasterSmem& sm, const SceneDev& S, const ViewDev& V, const FrameDev& Fr,
-                                            const TriRec* __restrict__ vtris, const int* __restrict__ tri_list,
-                                            int t_beg, int t_end, int X0, int Y0, int X1, int Yb0, int Y1, bool rh,
-                                            uint8_t* status_view) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int n = 0;
-    for (int base = t_beg; base < t_end; base += n) {
-        __syncthreads();  // previous round fully consumed
-        if (wid == 0) {   // choose the round: up to 32 triangles, at most STAGE_CLIP of them with a clip test
-            const int cand = min(STAGE_TRIS, t_end - base);
-            const int face = lane < cand ? tri_list[base + lane] : -1;
-            const bool clip = face >= 0 && (vtris[face].flags & TR_NEEDS_CLIP);
-            const unsigned mask = __ballot_sync(0xffffffffu, clip);
-            const int take = __popc(mask) > STAGE_CLIP ? (int)__fns(mask, 0, STAGE_CLIP + 1) : cand;
-            if (lane < take) {
-                sm.face[lane] = face;
-                sm.clip_slot[lane] = clip ? (signed char)__popc(mask & ((1u << lane) - 1)) : (signed char)-1;
-            }
-            if (lane == 0) sm.n_round = take;
-        }
-        __syncthreads();
-        n = sm.n_round;
-        for (int u = threadIdx.x; u < n * 16; u += RASTER_THREADS) {  // records: coalesced 8-byte pieces
-            const int t = u >> 4, part = u & 15;
-            reinterpret_cast<unsigned long long*>(sm.tri[t])[part] =
-                __ldg(reinterpret_cast<const unsigned long long*>(vtris + sm.face[t]) + part);
-        }
-        for (int u = threadIdx.x; u < n * CLIP_DOUBLES; u += RASTER_THREADS) {  // clip coordinates, 4 FMAs each
-            const int t = u / CLIP_DOUBLES, j = u - t * CLIP_DOUBLES;
-            const int slot = sm.clip_slot[t];
-            if (slot < 0) continue;
-            const int cam = j / 12, vtx = (j % 12) >> 2, k = j & 3;
-            const double4 p = S.pos[S.faces[sm.face[t]].v[vtx]];
-            const double* M = cam ? V.mvp_dbg : V.mvp;
-            sm.clip[slot][j] = fma(p.w, M[12 + k], fma(p.z, M[8 + k], fma(p.y, M[4 + k], p.x * M[k])));
-        }
-        __syncthreads();
-        if (wid == 0) {   // boxes inside the tile and the exclusive scan of their pixel counts
-            int npx = 0;
-            if (lane < n) {
-                const TriRec& r = *reinterpret_cast<const TriRec*>(sm.tri[lane]);
-                const int x0 = max((int)r.bx0, X0), x1 = min((int)r.bx1, X1), y0 = max((int)r.by0, Yb0), y1 = min((int)r.by1, Y1);
-                const int w = max(x1 - x0, 0), h = max(y1 - y0, 0);
-                npx = w * h;
-                if (npx >= BIG_BOX_PX && tri_misses_rect(r, x0, x1 - 1, y0, y1 - 1)) npx = 0;  // provably no covered pixel
-                sm.geo[lane] = (x0 - X0) | ((y0 - Y0) << 8) | (w << 16);
-            }
-            int incl = npx;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-            sm.start[lane + 1] = incl;
-            if (lane == 0) sm.start[0] = 0;
-        }
-        __syncthreads();
-        const int total = sm.start[n];
-        for (int k0 = wid * 32; k0 < total; k0 += RASTER_THREADS) {
-            const int k = k0 + lane;
-            if (k >= total) continue;
-            int t = 0;  // largest t with start[t] <= k
-#pragma unroll
-            for (int step = 16; step; step >>= 1) if (t + step < n && sm.start[t + step] <= k) t += step;
-            const int i = k - sm.start[t], geo = sm.geo[t];
-            const int w = geo >> 16;
-            // i / w for i < 1024, w <= 32: (i + 0.5) / w stays >= 1/64 away from an integer
-            const int yy = __float2int_rd(((float)i + 0.5f) * (1.0f / (float)w));
-            const int px = X0 + (geo & 0xff) + i - yy * w, py = Y0 + ((geo >> 8) & 0xff) + yy;
-            const TriRec& r = *reinterpret_cast<const TriRec*>(sm.tri[t]);
-            const int slot = sm.clip_slot[t];
-            const double* cc = sm.clip[slot < 0 ? 0 : slot];
-            float bu, bv, bw;
-            if (PASS == 1) B2R_STAT(12, 1);
-            if (!tri_pixel_in(r, cc, px, py, bu, bv, bw)) continue;
-            if (PASS == 1) B2R_STAT(13, 1);
-            const double b0 = (double)bu, b1 = (double)bv, b2 = (double)bw;
-            const double z = (r.flags & TR_COV_ONE) ? seq3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2])
-                                                    : gemv3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2]);
-            unsigned bits = 1;
-            const int face = sm.face[t];
-            if (z == z) {
-                const int p = (py - Y0) * TILE_W + (px - X0);
-                const unsigned long long key = zkey(z);
-                if (PASS == 1) {
-                    // a face of a Model(depth_test=False) never writes z (triangular.py:117); it may still colour the
-                    // pixel, which only the full winner pass resolves
-                    if (r.flags & TR_NO_ZWRITE) { sm.need_full = 1; continue; }
-                    const unsigned long long old = rh ? atomicMin(&sm.z[p], key) : atomicMax(&sm.z[p], key);
-                    if (old == key) sm.need_full = 1;                       // exact tie: the greatest face index wins
-                    else if (rh ? (key < old) : (key > old)) store_relaxed_smem(&sm.id[p], face);  // last improver (verified afterwards)
-                } else {
-                    // writing faces colour where they ARE the z-buffer; non-writing ones wherever they pass the test
-                    // against the final z-buffer (zbuf >= z for RH, <= for LH)
-                    const unsigned long long kb = sm.z[p];
-                    const bool pass = (r.flags & TR_NO_ZWRITE) ? (rh ? (kb >= key) : (kb <= key)) : (key == kb);
-                    if (pass) {
-                        atomicMax(&sm.id[p], face);
-                        bits |= 2 | (sm.st[p] == 0 ? 4 : 0);
-                    }
-                }
-            }
-            if (PASS == 3 && status_view) {
-                uint8_t* sp = status_view + face;
-                unsigned* wp = (unsigned*)((uintptr_t)sp & ~(uintptr_t)3);
-                atomicOr(wp, bits << (8 * ((uintptr_t)sp & 3)));
-            }
-        }
-    }
-}
-
-#ifndef B2R_RASTER_MINB
-#define B2R_RASTER_MINB 9
-#endif
-__global__ void __launch_bounds__(RASTER_THREADS, B2R_RASTER_MINB)
-k_raster(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec* __restrict__ tris,
-         const QuadRec* __restrict__ quads, int quad_stride, BinDev B, RasterOut O, int view0, int n_sub) {
-    __shared__ RasterSmem sm;
-    // grid = n_sub views x n_tiles, the views of the sub-chunk interleaved, tiles in k_order's heaviest-first order
-    const int view = (int)(blockIdx.x % (unsigned)n_sub) + view0;  // view0: first view of this sub-chunk within the batch
-    const ViewDev& V = views[view];
-    const int n_tiles = Fr.tiles_x * Fr.tiles_y;
-    const int tile = B.order[(size_t)view * n_tiles + blockIdx.x / (unsigned)n_sub];
-    const int tx = tile % Fr.tiles_x, ty = tile / Fr.tiles_x + Fr.tile_row0;
-    const int X0 = tx * TILE_W, Y0 = ty * TILE_H;
-    const int X1 = min(X0 + TILE_W, Fr.W), Y1 = min(min(Y0 + TILE_H, Fr.H), Fr.row_end);
-    const int Yb0 = max(Y0, Fr.row_begin);
-    const bool rh = V.system == 1;
-    const int* tri_off = B.tri_off + (size_t)view * (n_tiles + 1);
-    const int* quad_off = B.quad_off + (size_t)view * (n_tiles + 1);
-    // lists that did not fit (capacity overflow, reported to the host) are treated as empty: never read past them
-    const bool lists_ok = (B.overflow[view * 2] | B.overflow[view * 2 + 1]) == 0;
-    const int t_beg = lists_ok ? tri_off[tile] : 0, t_end = lists_ok ? tri_off[tile + 1] : 0;
-    const int q_beg = lists_ok ? quad_off[tile] : 0, q_end = lists_ok ? quad_off[tile + 1] : 0;
-    const size_t plane = (size_t)view * Fr.H * Fr.W;
-    const double z_bg = rh ? __longlong_as_double(0x7FF0000000000000ll) : __longlong_as_double(0xFFF0000000000000ll);
-
-    if (t_beg == t_end && (q_beg == q_end || !Fr.full_stencil)) {
-        // no face can win here, so the stencil count is never read by the shader: background tile
-        for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) {
-            const int px = X0 + (i & (TILE_W - 1)), py = Y0 + i / TILE_W;
-            if (px < X1 && py >= Yb0 && py < Y1) {
-                const size_t g = plane + (size_t)py * Fr.W + px;
-                O.winner[g] = -1;
-                O.stencil[g] = 0;
-                if (O.z) O.z[g] = z_bg;
-            }
-        }
-        return;
-    }
-
-    if (threadIdx.x == 0) { B2R_STAT(11, 1); B2R_STAT(14, q_end - q_beg); B2R_STAT(15, t_end - t_beg); }
-    const unsigned long long z_init = zkey(z_bg);
-    for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) { sm.z[i] = z_init; sm.id[i] = -1; sm.st[i] = 0; }
-    if (threadIdx.x == 0) { sm.uniform = 0; sm.need_full = 0; sm.next_quad = 0; }
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const TriRec* vtris = tris + (size_t)view * Fr.n_faces;
-    const int* tri_list = B.tri_list + (size_t)view * B.tri_cap;
-    uint8_t* status_view = O.status ? O.status + (size_t)view * Fr.n_faces : nullptr;
-
-    raster_tris<1>(sm, S, V, Fr, vtris, tri_list, t_beg, t_end, X0, Y0, X1, Yb0, Y1, rh, status_view);
-    __syncthreads();
-
-    // ---- stencil: one warp per quad  (triangular.py:341-368) ----
-    // Outside debug mode the count is only read under a face, so background pixels are skipped, and a whole
-    // (quad, tile) pair is skipped when the quad lies behind every covered pixel of the tile: the depth of the quad
-    // plane as the reference evaluates it is a composition of monotone roundings in px and py, hence its extremes
-    // over a pixel rectangle are attained exactly at the corners (as long as the linearisation has no pole inside).
-    const bool skip_bg = !Fr.full_stencil;
-    unsigned long long kb_min = ~0ull, kb_max = 0ull;
-    if (skip_bg && q_beg < q_end) {
-        // depth range of the covered pixels of the tile (keys; empty = min > max)
-        for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) {
-            const unsigned long long k = sm.z[i];
-            if (k != z_init) { kb_min = min(kb_min, k); kb_max = max(kb_max, k); }
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            kb_min = min(kb_min, __shfl_xor_sync(0xffffffffu, kb_min, o));
-            kb_max = max(kb_max, __shfl_xor_sync(0xffffffffu, kb_max, o));
-        }
-        if (lane == 0) { sm.red_min[wid] = kb_min; sm.red_max[wid] = kb_max; }
-        __syncthreads();
-#pragma unroll
-        for (int w = 0; w < RASTER_WARPS; ++w) { kb_min = min(kb_min, sm.red_min[w]); kb_max = max(kb_max, sm.red_max[w]); }
-    }
-    const bool any_cov = kb_min <= kb_max;
-    int uniform = 0;  // stencil increments that apply to every covered pixel of the tile
-    if (!skip_bg || any_cov) {
-        const int* quad_list = B.quad_list + (size_t)view * B.quad_cap;
-        const QuadRec* vquads = quads + (size_t)view * quad_stride;
-        // (quad, tile) pairs are handed out dynamically, eight at a time (their cost differs by orders of magnitude: a
-        // warp that finishes cheap ones grabs more instead of idling at the barrier).  The eight pairs are classified
-        // together -- lane -> pair lane/4, rectangle corner lane%4 -- so a rejected pair costs a few instructions;
-        // the survivors are then processed one after the other by the whole warp.
-        for (;;) {
-            int t0 = 0;
-            if (lane == 0) t0 = q_beg + atomicAdd(&sm.next_quad, 8);
-            t0 = __shfl_sync(0xffffffffu, t0, 0);
-            if (t0 >= q_end) break;
-            const int tg = t0 + (lane >> 2);
-            int g_entry = 0, g_state = 0;  // 0 skip, 1 process, 2 process and every covered pixel passes the z test
-            double g_z = 0.0;
-            int g_code = 3;                // sign class of the linearisation denominator at this corner, 3 = irregular
-            if (tg < q_end) {
-                g_entry = quad_list[tg];
-                const QuadRec& G = vquads[g_entry & (QUAD_FULL_BIT - 1)];
-                const int gx0 = max((int)G.bx0, X0), gx1 = min((int)G.bx1, X1) - 1;
-                const int gy0 = max((int)G.by0, Yb0), gy1 = min((int)G.by1, Y1) - 1;
-                if (gx0 <= gx1 && gy0 <= gy1) {
-                    g_state = 1;
-                    if (skip_bg) {  // depth of the quad plane at one corner of the rectangle, as the reference rounds it
-                        const int cx = (lane & 1) ? gx1 : gx0, cy = (lane & 2) ? gy1 : gy0;
-                        const double z = -(G.nx * (double)cx + G.ny * (double)cy + G.D) / G.nz;
-                        const double den = V.zl_sum - z * V.zl_diff;
-                        g_z = V.zl_num / den;
-                        g_code = (g_z == g_z) ? (den > 0 ? 1 : (den < 0 ? 2 : 3)) : 3;
-                    }
-                }
-            }
-            if (skip_bg) {  // reduce over the four corners of each pair (lanes 4g .. 4g+3)
-                unsigned long long kmin = zkey(g_z), kmax = kmin;
-#pragma unroll
-                for (int o = 1; o <= 2; o <<= 1) {
-                    const int other = __shfl_xor_sync(0xffffffffu, g_code, o);
-                    g_code = (g_code == other) ? g_code : 3;
-                    kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
-                    kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
-                }
-                if (g_state && g_code != 3) {  // no pole inside: the corner depths bound the depth over the rectangle
-                    if (rh ? (kmin > kb_max) : (kmax < kb_min)) g_state = 0;         // fails everywhere it matters
-                    else if (rh ? (kmax <= kb_min) : (kmin >= kb_max)) g_state = 2;  // passes on every covered pixel
-                }
-            }
-            if ((lane & 3) == 0 && tg < q_end) { B2R_STAT(0, 1); if (g_state == 0) B2R_STAT(1, 1); if (g_state == 2) B2R_STAT(6, 1); }
-            unsigned todo = __ballot_sync(0xffffffffu, (lane & 3) == 0 && g_state != 0);
-            while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int entry = __shfl_sync(0xffffffffu, g_entry, src);
-            const bool all_pass = __shfl_sync(0xffffffffu, g_state, src) == 2;
-            const bool full = (entry & QUAD_FULL_BIT) != 0;  // every pixel of the tile is inside the quad
-            const QuadRec& R = vquads[entry & (QUAD_FULL_BIT - 1)];
-            const int rx0 = max((int)R.bx0, X0), rx1 = min((int)R.bx1, X1) - 1;
-            const int ry0 = max((int)R.by0, Yb0), ry1 = min((int)R.by1, Y1) - 1;
-            if (all_pass && full) {  // one count for every covered pixel of the tile: no per-pixel work at all
-                uniform += R.front ? 1 : -1;
-                if (lane == 0) B2R_STAT(4, 1);
-                continue;
-            }
-            auto quad_depth = [&](int px, int py, double& den) {
-                const double z = -(R.nx * (double)px + R.ny * (double)py + R.D) / R.nz;
-                den = V.zl_sum - z * V.zl_diff;
-                return V.zl_num / den;
-            };
-            // exact span of row py = Y0 + lane: every edge function is monotone in px, so each edge cuts the
-            // candidate interval from one side; the cut is located by bisection on the exact predicate
-            const int py = Y0 + lane;
-            int lo = rx0, hi = rx1;
-            if (py < ry0 || py > ry1) hi = lo - 1;
-            const bool front = R.front != 0;
-            const int nv = full ? 0 : R.n;  // a fully covered tile needs no span search
-            if (full && lane == 0) B2R_STAT(5, 1);
-            for (int e = 0; e < nv; ++e) {
-                const int j = (e + 1 == nv) ? 0 : e + 1;
-                const double xi = R.x[e], yi = R.y[e];
-                const double ex = R.x[j] - xi, ey = R.y[j] - yi;
-                // (warp-uniform) an edge whose worst corner of the rectangle is already inside constrains no row
-                {
-                    const double fworst = front ? edge_fn(ey >= 0 ? rx0 : rx1, ex <= 0 ? ry0 : ry1, xi, yi, ex, ey)
-                                                : edge_fn(ey >= 0 ? rx1 : rx0, ex <= 0 ? ry1 : ry0, xi, yi, ex, ey);
-                    if (front ? (fworst > 0) : (fworst < 0)) continue;
-                }
-                if (lo > hi) continue;
-                const double c = ((double)py - yi) * ex;
-                auto pred = [&](int px) {  // front ? f > 0 : f < 0 with f = (px - xi)*ey - c  (triangular.py:305-311)
-                    const double f = ((double)px - xi) * ey - c;
-                    return front ? (f > 0) : (f < 0);
-                };
-                const bool up = front ? (ey > 0) : (ey < 0);  // the true set is upward closed in px
-                if (ey == 0 || !(ey == ey)) {
-                    if (!pred(lo)) hi = lo - 1;
-                    continue;
-                }
-                // The boundary is where f changes sign: px* = xi + c/ey.  Start from that estimate and walk to the
-                // exact first/last pixel satisfying the EXACT predicate (monotone in px): normally zero or one step.
-                const double est = xi + c / ey;
-                if (up) {          // smallest px in [lo,hi] with pred
-                    if (!pred(hi)) { hi = lo - 1; continue; }
-                    int k = est >= (double)hi ? hi : (est <= (double)lo ? lo : (int)ceil(est));  // NaN falls to lo
-                    if (!(est == est)) k = lo;
-                    while (k > lo && pred(k - 1)) --k;
-                    while (!pred(k)) ++k;                 // terminates: pred(hi) holds
-                    lo = k;
-                } else {           // largest px in [lo,hi] with pred
-                    if (!pred(lo)) { hi = lo - 1; continue; }
-                    int k = est >= (double)hi ? hi : (est <= (double)lo ? lo : (int)floor(est));
-                    if (!(est == est)) k = hi;
-                    while (k < hi && pred(k + 1)) ++k;
-                    while (!pred(k)) --k;                 // terminates: pred(lo) holds
-                    hi = k;
-                }
-            }
-            const int delta = front ? 1 : -1;
-            // The spans of the 32 rows are flattened into one dense pixel list and dealt to the lanes, so every lane
-            // works whatever the shape of the quad: pixel k lies in the row r with start[r] <= k < start[r+1]
-            // (inclusive scan over the lanes, then a 5-step bisection through shuffles).  Two pixels per lane and
-            // iteration, written as straight-line code: their depth evaluations (two dependent float64 divisions
-            // each) are independent and overlap in the pipeline.
-            const int len = max(hi - lo + 1, 0);
-            int incl = len;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
-            if (lane == 0) { B2R_STAT(2, 1); B2R_STAT(3, total); }
-            auto locate = [&](int k, int& px, int& qy) {  // every lane takes part in the shuffles
-                int r = 0;  // smallest lane with incl[r] > k
-#pragma unroll
-                for (int step = 16; step; step >>= 1) {
-                    const int probe = __shfl_sync(0xffffffffu, incl, r + step - 1);
-                    if (probe <= k) r += step;
-                }
-                const int row_incl = __shfl_sync(0xffffffffu, incl, r), row_len = __shfl_sync(0xffffffffu, len, r);
-                px = __shfl_sync(0xffffffffu, lo, r) + (k - (row_incl - row_len));
-                qy = Y0 + r;
-            };
-            for (int k = lane; k < ((total + 63) & ~63); k += 64) {
-                int pxa, qya, pxb, qyb;
-                locate(k, pxa, qya);
-                locate(k + 32, pxb, qyb);
-                const bool va = k < total, vb = k + 32 < total;
-                const int pa = va ? (qya - Y0) * TILE_W + (pxa - X0) : 0, pb = vb ? (qyb - Y0) * TILE_W + (pxb - X0) : 0;
-                const unsigned long long kba = sm.z[pa], kbb = sm.z[pb];
-                bool hit_a = va && !(skip_bg && kba == z_init), hit_b = vb && !(skip_bg && kbb == z_init);
-                if (!all_pass) {
-                    double dena, denb;
-                    const double za = quad_depth(pxa, qya, dena), zb = quad_depth(pxb, qyb, denb);
-                    const unsigned long long kza = zkey(za), kzb = zkey(zb);
-                    hit_a = hit_a && za == za && (rh ? (kba >= kza) : (kba <= kza));
-                    hit_b = hit_b && zb == zb && (rh ? (kbb >= kzb) : (kbb <= kzb));
-                }
-                if (hit_a) atomicAdd(&sm.st[pa], delta);
-                if (hit_b) atomicAdd(&sm.st[pb], delta);
-            }
-            }  // survivors of this batch
-        }
-    }
-    if (skip_bg) {  // fold the tile-uniform increments into the per-pixel counts
-        if (lane == 0 && uniform) atomicAdd(&sm.uniform, uniform);
-    }
-    __syncthreads();
-    if (skip_bg && sm.uniform) {
-        const int u = sm.uniform;
-        for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) if (sm.z[i] != z_init) sm.st[i] += u;
-        __syncthreads();
-    }
-
-    // ---- winner.  Fast path: the face that last improved a pixel is its winner if its depth is the final zbuf
-    // there and no exact tie was seen in the tile; it is checked by re-evaluating that one face per pixel.  Anything
-    // else (ties, a late store losing a race, status requested) falls back to the full pass over the lists. ----
-    if (!status_view && !sm.need_full) {
-        for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) {
-            const int f = sm.id[i];
-            const unsigned long long kb = sm.z[i];
-            if (f < 0) { if (kb != z_init) sm.need_full = 1; continue; }
-            const TriRec& r = vtris[f];
-            float bu, bv, bw;
-            tri_bary(r, X0 + (i & (TILE_W - 1)), Y0 + i / TILE_W, bu, bv, bw);
-            const double b0 = (double)bu, b1 = (double)bv, b2 = (double)bw;
-            const double z = (r.flags & TR_COV_ONE) ? seq3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2])
-                                                    : gemv3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2]);
-            if (!(z == z) || zkey(z) != kb) sm.need_full = 1;
-        }
-    }
-    __syncthreads();
-    if (status_view || sm.need_full) {
-        if (threadIdx.x == 0) B2R_STAT(7, 1);
-        for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) sm.id[i] = -1;
-        raster_tris<3>(sm, S, V, Fr, vtris, tri_list, t_beg, t_end, X0, Y0, X1, Yb0, Y1, rh, status_view);
-        __syncthreads();
-    }
-
-    // ---- write-back (coalesced rows) ----
-    for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) {
-        const int px = X0 + (i & (TILE_W - 1)), py = Y0 + i / TILE_W;
-        if (px < X1 && py >= Yb0 && py < Y1) {
-            const size_t g = plane + (size_t)py * Fr.W + px;
-            O.winner[g] = sm.id[i];
-            O.stencil[g] = (short)sm.st[i];
-            if (O.z) O.z[g] = zkey_decode(sm.z[i]);
-        }
-    }
-}
-
 // =====================================================================================================================
 // shading
 // =====================================================================================================================
@@ -1174,23 +791,38 @@ __device__ __forceinline__ bool texel_fetch(const TextureDev& T, const double P[
     if (col < 0 || col >= T.width) { col = 0; ok = false; }
     if (row < 0 || row >= T.height) { row = 0; ok = false; }
     const uchar4 t = __ldg(T.texels + (size_t)row * T.width + col);
-    const float* lut = c_lut[T.decode];
-    out[0] = lut[t.x]; out[1] = lut[t.y]; out[2] = lut[t.z];
+    out[0] = texel_decode(t.x, T.decode); out[1] = texel_decode(t.y, T.decode); out[2] = texel_decode(t.z, T.decode);
     return ok;
 }
 
 // normalize() for shading vectors: x * rsqrt(|x|^2).  Within an ulp or two of the reference's x / sqrt(.) -- far
 // below what survives the uint8 quantisation (the exact form is kept wherever a comparison depends on it).
+__device__ __forceinline__ double fast_rsqrt(double s) {
+    // float32 hardware estimate (2^-22) polished by two Newton steps in float64: relative error ~1e-16 like rsqrt(),
+    // without its special-case branches; shading vectors are O(1), anything outside float range takes the library path
+    if (!(s > 1e-30 && s < 1e30)) return rsqrt(s);
+    double y = (double)rsqrtf((float)s);
+    const double h = 0.5 * s;
+    y = y * fma(-h * y, y, 1.5);
+    y = y * fma(-h * y, y, 1.5);
+    return y;
+}
 __device__ __forceinline__ void shade_norm3(double v[3]) {
     const double s = (v[0] * v[0] + v[1] * v[1]) + v[2] * v[2];
     if (s > 0) {
-        const double r = rsqrt(s);
+        const double r = fast_rsqrt(s);
         v[0] *= r; v[1] *= r; v[2] *= r;
     }
 }
 
 __device__ __forceinline__ double pow_ns(double x, const MaterialDev& M) {
-    if (M.ns_int >= 0) {  // exponentiation by squaring for the usual integer shininess (64, 32, ...)
+    if (M.ns_log2 >= 0) {  // Ns = 2^k (the default 64, 32, ...): k squarings
+        double r = x;
+        if (M.ns_log2 == 6) { r *= r; r *= r; r *= r; r *= r; r *= r; r *= r; return r; }   // the reference's default Ns = 64
+        for (int i = 0; i < M.ns_log2; ++i) r *= r;
+        return r;
+    }
+    if (M.ns_int >= 0) {  // exponentiation by squaring for any other small integer shininess
         double r = 1.0, b = x;
         int e = M.ns_int;
         while (e) { if (e & 1) r *= b; b *= b; e >>= 1; }
@@ -1421,68 +1053,573 @@ __device__ __forceinline__ bool skybox_pixel(const SceneDev& S, const ViewDev& V
         if (i0 < 0 || i0 >= sky_size) i0 = 0;
         if (i1 < 0 || i1 >= sky_size) i1 = 0;
         const uchar4 tx = __ldg(S.sky + ((size_t)side * sky_size + i0) * sky_size + i1);
-        out[0] = c_lut[0][tx.x]; out[1] = c_lut[0][tx.y]; out[2] = c_lut[0][tx.z];
+        out[0] = texel_decode(tx.x, 0); out[1] = texel_decode(tx.y, 0); out[2] = texel_decode(tx.z, 0);
         return true;
     }
     return false;
 }
 
-// One thread per pixel; a warp covers 32 consecutive pixels of one buffer row and packs its 96 output bytes into
-// 24 aligned 32-bit stores.  Output row = H-1-py (core.py:640).
-#ifndef B2R_SHADE_THREADS
-#define B2R_SHADE_THREADS 128
-#endif
 #ifndef B2R_SHADE_MINB
 #define B2R_SHADE_MINB 12
 #endif
-__global__ void __launch_bounds__(B2R_SHADE_THREADS, B2R_SHADE_MINB)
-k_shade(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec* __restrict__ tris,
-        const int* __restrict__ winner, const short* __restrict__ stencil, uint8_t* __restrict__ out_rgb, int view0,
-        float* __restrict__ out_f32, const unsigned* __restrict__ bg_packed) {
-    const int view = blockIdx.z + view0;
-    const ViewDev& V = views[view];
-    const int lane = threadIdx.x & 31;
-    const int px = blockIdx.x * 32 + lane;
-    const int py = Fr.row_begin + blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (py >= Fr.row_end) return;  // whole warp
-    float c[3] = {0.f, 0.f, 0.f};
-    bool const_bg = false;
-    if (px < Fr.W) {
-        const size_t g = (size_t)view * Fr.H * Fr.W + (size_t)py * Fr.W + px;
-        const int face = winner[g];
-        if (face >= 0) {
-            if (!shade_face_pixel(S, V, Fr.light, tris[(size_t)view * Fr.n_faces + face], face, px, py, stencil[g] == 0, c))
-                *Fr.err_flag = 1;  // mapped pinned memory: the host raises IndexError like the reference
-        } else if (Fr.bg_mode == B2R_BG_CUBEMAP) {
-            skybox_pixel(S, V, Fr.sky_size, px, py, c);
-        } else {
-            c[0] = Fr.background[0]; c[1] = Fr.background[1]; c[2] = Fr.background[2];
-            const_bg = true;
+
+// =====================================================================================================================
+// k_tile<FUSED>: depth -> stencil -> winner (-> SHADING when FUSED) of one 32x32 tile; z-buffer, winner and stencil count
+// live in shared memory (swizzled: pixel (x, y) sits at (y << 5) | (x ^ y), so lanes sharing a column do not pile up on
+// one bank).
+//   FUSED = false (production): the kernel ends by writing ONE packed word per pixel (winner | lit << 31) for
+//     k_shade_packed; tiles without primitives write nothing.  Round 1 wrote winner (4 B) + stencil (2 B) for every
+//     pixel of the screen.
+//   FUSED = true (B2R_FUSED=1, kept as the measured alternative): shading runs at the end of this kernel straight from
+//     the shared planes, nothing but the finished pixels reaches HBM.  Measured on the B200 (diablo, 64 views): 5.19 ms
+//     against 2.66 + 1.55 ms for the two-kernel form -- the fused kernel's instruction footprint (~100 KB against a
+//     32 KB L1.5 instruction cache, CTAs of one SM in different phases) and its 64 registers / 8 CTAs per SM cost more
+//     than the 4 bytes per covered pixel of HBM traffic it saves.
+// Exactness of the shortcuts: the quad edge function and the quad plane depth, as the reference
+// rounds them, are compositions of monotone roundings in px and py, so their extremes over a pixel rectangle sit
+// exactly at its corners -- depth-range rejection / acceptance of a (quad, tile) pair, the per-row span search and the
+// edge skipping below are exact, not merely conservative.
+// Also tried this round and measured slower, hence not kept: (triangle, row, 8-pixel segment) items with incremental
+// barycentrics in the depth pass and lane-owned rows / columns or 4-pixel segments in the stencil pass -- fewer
+// instructions per pixel, but 25 instead of 30 active lanes per instruction and a longer closing barrier (2.94 ms
+// against 2.66 ms for the dense (primitive, pixel) dealing below); rounds of 62 staged triangles in the depth pass (the
+// second 30 records in the memory of the still unused stencil plane): +3 % on diablo, no gain on the 1M-triangle torus,
+// whose tile time is its 17.8 k shadow quads, not the rounds.
+// =====================================================================================================================
+__device__ __forceinline__ int tpix(int x, int y) { return (y << 5) | ((x ^ y) & 31); }  // x, y in [0, 32)
+
+constexpr unsigned PACKED_LIT = 0x80000000u;   // bit 31 of the packed winner word: stencil == 0
+constexpr unsigned PACKED_NONE = 0x7fffffffu;  // no face (background)
+
+struct TileOut {
+    uint8_t* rgb;          // FUSED: (views, H, W, 3) final image rows
+    float* f32;            // FUSED, optional: float frame before tonemap, buffer rows
+    const unsigned* bg_packed;
+    unsigned* packed;      // !FUSED: (views, H, W) winner | lit << 31, buffer rows (background tiles are NOT written:
+                           // k_shade_packed recognises them from the empty tile lists)
+    int* winner;           // optional debug planes (views, H, W), buffer rows
+    short* stencil;
+    double* z;
+    uint8_t* status;       // optional (views, F)
+};
+
+struct TileSmem {
+    unsigned long long z[TILE_PX];          // order-preserving keys of the float64 z-buffer (swizzled)   8 KB
+    int id[TILE_PX];                        // winner face                                                4 KB
+    int st[TILE_PX];                        // stencil count                                              4 KB
+    double tri[STAGE_TRIS][REC_DOUBLES];    // staged per-tile triangle list                              4.25 KB
+    double clip[STAGE_CLIP][CLIP_DOUBLES];  // clip coordinates of the staged triangles that need them    3 KB
+    int face[STAGE_TRIS];
+    int start[STAGE_TRIS + 1];              // exclusive scan of the pixel counts of the staged triangles
+    int geo[STAGE_TRIS];                    // box inside the tile: x0 | y0 << 8 | width << 16
+    signed char clip_slot[STAGE_TRIS];
+    unsigned long long red_min[RASTER_WARPS], red_max[RASTER_WARPS];
+    int n_round;
+    int next_quad;
+    int uniform;
+    int need_full;
+};
+// One pass over the tile's triangle list.  PASS 1: zbuf + last improver, PASS 3: full winner pass (+ status bits).
+template <int PASS>
+__device__ __noinline__ void tile_tris(TileSmem& sm, const SceneDev& S, const ViewDev& V,
+                                       const TriRec* __restrict__ vtris, const int* __restrict__ tri_list,
+                                       int t_beg, int t_end, int X0, int Y0, int X1, int Yb0, int Y1, bool rh,
+                                       uint8_t* status_view) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int n = 0;
+    for (int base = t_beg; base < t_end; base += n) {
+        __syncthreads();  // previous round fully consumed
+        if (wid == 0) {   // choose the round: up to 32 triangles, at most STAGE_CLIP of them with a clip test (the tile-list
+                          // entry carries that flag: no dependent load of the record here)
+            const int cand = min(STAGE_TRIS, t_end - base);
+            const int e0 = lane < cand ? tri_list[base + lane] : 0;
+            const bool clip = (e0 & TRI_CLIP_BIT) != 0;
+            const unsigned mask = __ballot_sync(0xffffffffu, clip);
+            const int take = __popc(mask) > STAGE_CLIP ? (int)__fns(mask, 0, STAGE_CLIP + 1) : cand;
+            if (lane < take) {
+                sm.face[lane] = e0 & (TRI_CLIP_BIT - 1);
+                sm.clip_slot[lane] = clip ? (signed char)__popc(mask & ((1u << lane) - 1)) : (signed char)-1;
+            }
+            if (lane == 0) sm.n_round = take;
+        }
+        __syncthreads();
+        n = sm.n_round;
+        for (int u = threadIdx.x; u < n * 16; u += RASTER_THREADS) {  // records: coalesced 8-byte pieces
+            const int t = u >> 4, part = u & 15;
+            reinterpret_cast<unsigned long long*>(sm.tri[t])[part] =
+                __ldg(reinterpret_cast<const unsigned long long*>(vtris + sm.face[t]) + part);
+        }
+        for (int u = threadIdx.x; u < n * CLIP_DOUBLES; u += RASTER_THREADS) {  // clip coordinates, 4 FMAs each
+            const int t = u / CLIP_DOUBLES, j = u - t * CLIP_DOUBLES;
+            const int slot = sm.clip_slot[t];
+            if (slot < 0) continue;
+            const int cam = j / 12, vtx = (j % 12) >> 2, k = j & 3;
+            const double4 p = S.pos[S.faces[sm.face[t]].v[vtx]];
+            const double* M = cam ? V.mvp_dbg : V.mvp;
+            sm.clip[slot][j] = fma(p.w, M[12 + k], fma(p.z, M[8 + k], fma(p.y, M[4 + k], p.x * M[k])));
+        }
+        __syncthreads();
+        if (wid == 0) {   // boxes inside the tile and the exclusive scan of their pixel counts
+            int npx = 0;
+            if (lane < n) {
+                const TriRec& r = *reinterpret_cast<const TriRec*>(sm.tri[lane]);
+                const int x0 = max((int)r.bx0, X0), x1 = min((int)r.bx1, X1), y0 = max((int)r.by0, Yb0), y1 = min((int)r.by1, Y1);
+                const int w = max(x1 - x0, 0), h = max(y1 - y0, 0);
+                npx = w * h;
+                if (npx >= BIG_BOX_PX && tri_misses_rect(r, x0, x1 - 1, y0, y1 - 1)) npx = 0;  // provably no covered pixel
+                sm.geo[lane] = (x0 - X0) | ((y0 - Y0) << 8) | (w << 16);
+            }
+            int incl = npx;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            sm.start[lane + 1] = incl;
+            if (lane == 0) sm.start[0] = 0;
+        }
+        __syncthreads();
+        // the (triangle, pixel) pairs of the round, flattened into one dense list and dealt 128 at a time: a warp is full
+        // whether the tile holds a thousand one-pixel triangles or a single triangle covering all of it
+        const int total = sm.start[n];
+        for (int k0 = wid * 32; k0 < total; k0 += RASTER_THREADS) {
+            const int k = k0 + lane;
+            if (k >= total) continue;
+            int t = 0;  // largest t with start[t] <= k
+#pragma unroll
+            for (int step = 16; step; step >>= 1) if (t + step < n && sm.start[t + step] <= k) t += step;
+            const int i = k - sm.start[t], geo = sm.geo[t];
+            const int w = geo >> 16;
+            // i / w for i < 1024, w <= 32: (i + 0.5) / w stays >= 1/64 away from an integer
+            const int yy = __float2int_rd(((float)i + 0.5f) * (1.0f / (float)w));
+            const int lx = (geo & 0xff) + i - yy * w, ly = ((geo >> 8) & 0xff) + yy;
+            const int px = X0 + lx, py = Y0 + ly;
+            const TriRec& r = *reinterpret_cast<const TriRec*>(sm.tri[t]);
+            const int slot = sm.clip_slot[t];
+            const double* cc = sm.clip[slot < 0 ? 0 : slot];
+            float bu, bv, bw;
+            if (PASS == 1) B2R_STAT(12, 1);
+            if (!tri_pixel_in(r, cc, px, py, bu, bv, bw)) continue;
+            if (PASS == 1) B2R_STAT(13, 1);
+            const double b0 = (double)bu, b1 = (double)bv, b2 = (double)bw;
+            const double z = (r.flags & TR_COV_ONE) ? seq3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2])
+                                                    : gemv3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2]);
+            unsigned bits = 1;
+            const int face = sm.face[t];
+            if (z == z) {
+                const int p = tpix(lx, ly);
+                const unsigned long long key = zkey(z);
+                if (PASS == 1) {
+                    // a face of a Model(depth_test=False) never writes z (triangular.py:117); it may still colour the
+                    // pixel, which only the full winner pass resolves
+                    if (r.flags & TR_NO_ZWRITE) { sm.need_full = 1; continue; }
+                    const unsigned long long old = rh ? atomicMin(&sm.z[p], key) : atomicMax(&sm.z[p], key);
+                    if (old == key) sm.need_full = 1;                                               // exact tie
+                    else if (rh ? (key < old) : (key > old)) store_relaxed_smem(&sm.id[p], face);   // last improver
+                } else {
+                    // writing faces colour where they ARE the z-buffer; non-writing ones wherever they pass the test
+                    // against the final z-buffer (zbuf >= z for RH, <= for LH)
+                    const unsigned long long kb = sm.z[p];
+                    const bool pass = (r.flags & TR_NO_ZWRITE) ? (rh ? (kb >= key) : (kb <= key)) : (key == kb);
+                    if (pass) {
+                        atomicMax(&sm.id[p], face);
+                        bits |= 2 | (sm.st[p] == 0 ? 4 : 0);
+                    }
+                }
+            }
+            if (PASS == 3 && status_view) {
+                uint8_t* sp = status_view + face;
+                unsigned* wp = (unsigned*)((uintptr_t)sp & ~(uintptr_t)3);
+                atomicOr(wp, bits << (8 * ((uintptr_t)sp & 3)));
+            }
         }
     }
-    if (out_f32 && px < Fr.W) {  // debug plane: the float frame of core.py:588, buffer row order
-        float* o = out_f32 + (((size_t)view * Fr.H + py) * Fr.W + px) * 3;
-        o[0] = c[0]; o[1] = c[1]; o[2] = c[2];
-    }
-    // (frame ** 0.8 * 255).astype(uint8) in float32; the constant background was tonemapped once by k_frame_consts
-    const unsigned packed = const_bg ? __ldg(bg_packed) : tonemap_pack(c);
+}
+
+// One 32-pixel row segment of finished pixels -> 96 bytes of the uint8 frame (row H-1-py), packed into 24 word stores.
+__device__ __forceinline__ void store_row(const FrameDev& Fr, uint8_t* __restrict__ out_rgb, int view, int x_base, int py,
+                                          unsigned packed, bool valid, int lane) {
     uint8_t* row = out_rgb + ((size_t)view * Fr.H + (size_t)(Fr.H - 1 - py)) * Fr.W * 3;
-    const int x_base = blockIdx.x * 32;
     if (x_base + 32 <= Fr.W && (((size_t)Fr.W * 3) & 3) == 0) {
-        // lane j < 24 assembles bytes 4j..4j+3 of the warp's 96-byte run: they belong to the pixels k = 4j/3 and
-        // k+1, whose 24-bit values overlap the word at a shift of 8*(j%3) bits
         const int k = (4 * lane) / 3, s = 8 * (lane - 3 * (lane / 3));
         const unsigned a = __shfl_sync(0xffffffffu, packed, k & 31), b = __shfl_sync(0xffffffffu, packed, (k + 1) & 31);
         const unsigned word = (a >> s) | (b << (24 - s));
         if (lane < 24) reinterpret_cast<unsigned*>(row + (size_t)x_base * 3)[lane] = word;
-    } else if (px < Fr.W) {
+    } else if (valid) {
+        const int px = x_base + lane;
         row[(size_t)px * 3 + 0] = (uint8_t)(packed & 0xff);
         row[(size_t)px * 3 + 1] = (uint8_t)((packed >> 8) & 0xff);
         row[(size_t)px * 3 + 2] = (uint8_t)((packed >> 16) & 0xff);
     }
 }
 
-// pass-3 status of every face (core.py:624-636): pending faces carry coverage / z / lit bits ORed in by k_raster
+#ifndef B2R_TILE_MINB
+#define B2R_TILE_MINB 8
+#endif
+#ifndef B2R_TILE_MINB_UNFUSED
+#define B2R_TILE_MINB_UNFUSED 9
+#endif
+template <bool FUSED>
+__global__ void __launch_bounds__(RASTER_THREADS, FUSED ? B2R_TILE_MINB : B2R_TILE_MINB_UNFUSED)
+k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec* __restrict__ tris,
+       const QuadRec* __restrict__ quads, int quad_stride, BinDev B, TileOut O, int view0, int n_sub) {
+    __shared__ TileSmem sm;
+    const int view = (int)(blockIdx.x % (unsigned)n_sub) + view0;
+    const ViewDev& V = views[view];
+    const int n_tiles = Fr.tiles_x * Fr.tiles_y;
+    const int tile = B.order[(size_t)view * n_tiles + blockIdx.x / (unsigned)n_sub];
+    const int tx = tile % Fr.tiles_x, ty = tile / Fr.tiles_x + Fr.tile_row0;
+    const int X0 = tx * TILE_W, Y0 = ty * TILE_H;
+    const int X1 = min(X0 + TILE_W, Fr.W), Y1 = min(min(Y0 + TILE_H, Fr.H), Fr.row_end);
+    const int Yb0 = max(Y0, Fr.row_begin);
+    const bool rh = V.system == 1;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int* tri_off = B.tri_off + (size_t)view * (n_tiles + 1);
+    const int* quad_off = B.quad_off + (size_t)view * (n_tiles + 1);
+    const bool lists_ok = (B.overflow[view * 2] | B.overflow[view * 2 + 1]) == 0;
+    const int t_beg = lists_ok ? tri_off[tile] : 0, t_end = lists_ok ? tri_off[tile + 1] : 0;
+    const int q_beg = lists_ok ? quad_off[tile] : 0, q_end = lists_ok ? quad_off[tile + 1] : 0;
+    const size_t plane = (size_t)view * Fr.H * Fr.W;
+    const double z_bg = rh ? __longlong_as_double(0x7FF0000000000000ll) : __longlong_as_double(0xFFF0000000000000ll);
+
+    if (t_beg == t_end && (q_beg == q_end || !Fr.full_stencil)) {
+        // no face can win here: background tile
+        if (!FUSED && !(O.winner || O.stencil || O.z)) return;   // k_shade_packed sees the empty lists itself
+        const unsigned bg = (!FUSED || Fr.bg_mode == B2R_BG_CUBEMAP) ? 0u : __ldg(O.bg_packed);
+        for (int row = wid; row < TILE_H; row += RASTER_WARPS) {
+            const int py = Y0 + row, px = X0 + lane;
+            if (py < Yb0 || py >= Y1) continue;
+            unsigned packed = bg;
+            float c[3] = {Fr.background[0], Fr.background[1], Fr.background[2]};
+            if (FUSED && Fr.bg_mode == B2R_BG_CUBEMAP) {
+                c[0] = c[1] = c[2] = 0.f;
+                if (px < X1) skybox_pixel(S, V, Fr.sky_size, px, py, c);
+                packed = tonemap_pack(c);
+            }
+            if (px < X1) {
+                const size_t g = plane + (size_t)py * Fr.W + px;
+                if (FUSED && O.f32) { float* o = O.f32 + g * 3; o[0] = c[0]; o[1] = c[1]; o[2] = c[2]; }
+                if (O.winner) O.winner[g] = -1;
+                if (O.stencil) O.stencil[g] = 0;
+                if (O.z) O.z[g] = z_bg;
+            }
+            if (FUSED) store_row(Fr, O.rgb, view, X0, py, packed, px < X1, lane);
+        }
+        return;
+    }
+
+    if (threadIdx.x == 0) { B2R_STAT(11, 1); B2R_STAT(14, q_end - q_beg); B2R_STAT(15, t_end - t_beg); }
+    const unsigned long long z_init = zkey(z_bg);
+    for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) { sm.z[i] = z_init; sm.id[i] = -1; sm.st[i] = 0; }
+    if (threadIdx.x == 0) { sm.uniform = 0; sm.need_full = 0; sm.next_quad = 0; }
+    const TriRec* vtris = tris + (size_t)view * Fr.n_faces;
+    const int* tri_list = B.tri_list + (size_t)view * B.tri_cap;
+    uint8_t* status_view = O.status ? O.status + (size_t)view * Fr.n_faces : nullptr;
+
+    tile_tris<1>(sm, S, V, vtris, tri_list, t_beg, t_end, X0, Y0, X1, Yb0, Y1, rh, status_view);
+    __syncthreads();
+
+    // ---- stencil (triangular.py:341-368) ----
+    const bool skip_bg = !Fr.full_stencil;
+    unsigned long long kb_min = ~0ull, kb_max = 0ull;
+    if (skip_bg && q_beg < q_end) {
+        for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) {
+            const unsigned long long k = sm.z[i];
+            if (k != z_init) { kb_min = min(kb_min, k); kb_max = max(kb_max, k); }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            kb_min = min(kb_min, __shfl_xor_sync(0xffffffffu, kb_min, o));
+            kb_max = max(kb_max, __shfl_xor_sync(0xffffffffu, kb_max, o));
+        }
+        if (lane == 0) { sm.red_min[wid] = kb_min; sm.red_max[wid] = kb_max; }
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < RASTER_WARPS; ++w) { kb_min = min(kb_min, sm.red_min[w]); kb_max = max(kb_max, sm.red_max[w]); }
+    }
+    const bool any_cov = kb_min <= kb_max;
+    int uniform = 0;
+    if (!skip_bg || any_cov) {
+        const int* quad_list = B.quad_list + (size_t)view * B.quad_cap;
+        const QuadRec* vquads = quads + (size_t)view * quad_stride;
+        const int n_pairs = q_end - q_beg;
+        for (;;) {
+            // guided self-scheduling: eight pairs per grab while the list is long, fewer towards its end, so the
+            // warps reach the closing barrier together
+            int t0 = 0, grab = 0;
+            if (lane == 0) {
+                const int seen = sm.next_quad;  // a stale value only changes the grab size
+                grab = max(1, min(8, (n_pairs - seen) / (2 * RASTER_WARPS)));
+                t0 = q_beg + atomicAdd(&sm.next_quad, grab);
+            }
+            t0 = __shfl_sync(0xffffffffu, t0, 0);
+            grab = __shfl_sync(0xffffffffu, grab, 0);
+            if (t0 >= q_end) break;
+            const int t_hi = min(t0 + grab, q_end);
+            const int tg = t0 + (lane >> 2);
+            int g_entry = 0, g_state = 0;  // 0 skip, 1 process, 2 process and every covered pixel passes the z test
+            double g_z = 0.0;
+            int g_code = 3;
+            if (tg < t_hi) {
+                g_entry = quad_list[tg];
+                const QuadRec& G = vquads[g_entry & (QUAD_FULL_BIT - 1)];
+                const int gx0 = max((int)G.bx0, X0), gx1 = min((int)G.bx1, X1) - 1;
+                const int gy0 = max((int)G.by0, Yb0), gy1 = min((int)G.by1, Y1) - 1;
+                if (gx0 <= gx1 && gy0 <= gy1) {
+                    g_state = 1;
+                    if (skip_bg) {
+                        const int cx = (lane & 1) ? gx1 : gx0, cy = (lane & 2) ? gy1 : gy0;
+                        const double z = -(G.nx * (double)cx + G.ny * (double)cy + G.D) / G.nz;
+                        const double den = V.zl_sum - z * V.zl_diff;
+                        g_z = V.zl_num / den;
+                        g_code = (g_z == g_z) ? (den > 0 ? 1 : (den < 0 ? 2 : 3)) : 3;
+                    }
+                }
+            }
+            if (skip_bg) {
+                unsigned long long kmin = zkey(g_z), kmax = kmin;
+#pragma unroll
+                for (int o = 1; o <= 2; o <<= 1) {
+                    const int other = __shfl_xor_sync(0xffffffffu, g_code, o);
+                    g_code = (g_code == other) ? g_code : 3;
+                    kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+                    kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+                }
+                if (g_state && g_code != 3) {
+                    if (rh ? (kmin > kb_max) : (kmax < kb_min)) g_state = 0;
+                    else if (rh ? (kmax <= kb_min) : (kmin >= kb_max)) g_state = 2;
+                }
+            }
+            if ((lane & 3) == 0 && tg < t_hi) { B2R_STAT(0, 1); if (g_state == 0) B2R_STAT(1, 1); if (g_state == 2) B2R_STAT(6, 1); }
+            unsigned todo = __ballot_sync(0xffffffffu, (lane & 3) == 0 && g_state != 0);
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int entry = __shfl_sync(0xffffffffu, g_entry, src);
+                const bool all_pass = __shfl_sync(0xffffffffu, g_state, src) == 2;
+                const bool full = (entry & QUAD_FULL_BIT) != 0;
+                const QuadRec& R = vquads[entry & (QUAD_FULL_BIT - 1)];
+                const bool front = R.front != 0;
+                if (all_pass && full) {
+                    uniform += front ? 1 : -1;
+                    if (lane == 0) B2R_STAT(4, 1);
+                    continue;
+                }
+                const int rx0 = max((int)R.bx0, X0), rx1 = min((int)R.bx1, X1) - 1;
+                const int ry0 = max((int)R.by0, Yb0), ry1 = min((int)R.by1, Y1) - 1;
+                // exact span of row py = Y0 + lane: every edge function is monotone in px
+                const int py = Y0 + lane;
+                int lo = rx0, hi = rx1;
+                if (py < ry0 || py > ry1) hi = lo - 1;
+                const int nv = full ? 0 : R.n;
+                if (full && lane == 0) B2R_STAT(5, 1);
+                for (int e = 0; e < nv; ++e) {
+                    const int j = (e + 1 == nv) ? 0 : e + 1;
+                    const double xi = R.x[e], yi = R.y[e];
+                    const double ex = R.x[j] - xi, ey = R.y[j] - yi;
+                    {   // (warp-uniform) an edge whose worst corner of the rectangle is already inside constrains no row
+                        const double fworst = front ? edge_fn(ey >= 0 ? rx0 : rx1, ex <= 0 ? ry0 : ry1, xi, yi, ex, ey)
+                                                    : edge_fn(ey >= 0 ? rx1 : rx0, ex <= 0 ? ry1 : ry0, xi, yi, ex, ey);
+                        if (front ? (fworst > 0) : (fworst < 0)) continue;
+                    }
+                    if (lo > hi) continue;
+                    const double c = ((double)py - yi) * ex;
+                    auto pred = [&](int px) {  // front ? f > 0 : f < 0 with f = (px - xi)*ey - c  (triangular.py:305-311)
+                        const double f = ((double)px - xi) * ey - c;
+                        return front ? (f > 0) : (f < 0);
+                    };
+                    const bool up = front ? (ey > 0) : (ey < 0);  // the true set is upward closed in px
+                    if (ey == 0 || !(ey == ey)) {
+                        if (!pred(lo)) hi = lo - 1;
+                        continue;
+                    }
+                    const double est = xi + c / ey;   // where f changes sign; then walk to the exact cut
+                    if (up) {
+                        if (!pred(hi)) { hi = lo - 1; continue; }
+                        int k = est >= (double)hi ? hi : (est <= (double)lo ? lo : (int)ceil(est));
+                        if (!(est == est)) k = lo;
+                        while (k > lo && pred(k - 1)) --k;
+                        while (!pred(k)) ++k;
+                        lo = k;
+                    } else {
+                        if (!pred(lo)) { hi = lo - 1; continue; }
+                        int k = est >= (double)hi ? hi : (est <= (double)lo ? lo : (int)floor(est));
+                        if (!(est == est)) k = hi;
+                        while (k < hi && pred(k + 1)) ++k;
+                        while (!pred(k)) --k;
+                        hi = k;
+                    }
+                }
+                const int delta = front ? 1 : -1;
+                // The spans of the 32 rows are flattened into one dense pixel list and dealt to the lanes, so every lane
+                // works whatever the shape of the quad: pixel k lies in the row r with start[r] <= k < start[r+1]
+                // (inclusive scan over the lanes, then a 5-step bisection through shuffles).  Two pixels per lane and
+                // iteration, written as straight-line code: their depth evaluations (two dependent float64 divisions
+                // each) are independent and overlap in the pipeline.
+                const int len = max(hi - lo + 1, 0);
+                int incl = len;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                if (lane == 0) { B2R_STAT(2, 1); B2R_STAT(3, total); }
+                auto locate = [&](int k, int& lx, int& r) {  // every lane takes part in the shuffles
+                    r = 0;  // smallest lane with incl[r] > k
+#pragma unroll
+                    for (int step = 16; step; step >>= 1) {
+                        const int probe = __shfl_sync(0xffffffffu, incl, r + step - 1);
+                        if (probe <= k) r += step;
+                    }
+                    const int row_incl = __shfl_sync(0xffffffffu, incl, r), row_len = __shfl_sync(0xffffffffu, len, r);
+                    lx = __shfl_sync(0xffffffffu, lo, r) + (k - (row_incl - row_len)) - X0;
+                };
+                auto quad_depth = [&](int px, int qy) {  // z = -(nx*px + ny*py + D)/nz, linearised (triangular.py:352-354)
+                    const double z = -(R.nx * (double)px + R.ny * (double)qy + R.D) / R.nz;
+                    return V.zl_num / (V.zl_sum - z * V.zl_diff);
+                };
+                for (int k = lane; k < ((total + 63) & ~63); k += 64) {
+                    int lxa, ra, lxb, rb;
+                    locate(k, lxa, ra);
+                    locate(k + 32, lxb, rb);
+                    const bool va = k < total, vb = k + 32 < total;
+                    const int pa = va ? tpix(lxa, ra) : 0, pb = vb ? tpix(lxb, rb) : 0;
+                    const unsigned long long kba = sm.z[pa], kbb = sm.z[pb];
+                    bool hit_a = va && !(skip_bg && kba == z_init), hit_b = vb && !(skip_bg && kbb == z_init);
+                    if (!all_pass) {
+                        const double za = quad_depth(X0 + lxa, Y0 + ra), zb = quad_depth(X0 + lxb, Y0 + rb);
+                        const unsigned long long kza = zkey(za), kzb = zkey(zb);
+                        hit_a = hit_a && za == za && (rh ? (kba >= kza) : (kba <= kza));
+                        hit_b = hit_b && zb == zb && (rh ? (kbb >= kzb) : (kbb <= kzb));
+                    }
+                    if (hit_a) atomicAdd(&sm.st[pa], delta);
+                    if (hit_b) atomicAdd(&sm.st[pb], delta);
+                }
+            }  // survivors of this grab
+        }
+    }
+    if (skip_bg && lane == 0 && uniform) atomicAdd(&sm.uniform, uniform);
+    __syncthreads();
+    if (skip_bg && sm.uniform) {
+        const int uadd = sm.uniform;
+        for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) if (sm.z[i] != z_init) sm.st[i] += uadd;
+        __syncthreads();
+    }
+
+    // ---- winner: verified last improver, full pass on ties / lost races / status requests ----
+    if (!status_view && !sm.need_full) {
+        for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) {
+            const int ly = i >> 5, lx = i & 31;
+            const int p = tpix(lx, ly);
+            const int f = sm.id[p];
+            const unsigned long long kb = sm.z[p];
+            if (f < 0) { if (kb != z_init) sm.need_full = 1; continue; }
+            const TriRec& r = vtris[f];
+            float bu, bv, bw;
+            tri_bary(r, X0 + lx, Y0 + ly, bu, bv, bw);
+            const double b0 = (double)bu, b1 = (double)bv, b2 = (double)bw;
+            const double z = (r.flags & TR_COV_ONE) ? seq3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2])
+                                                    : gemv3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2]);
+            if (!(z == z) || zkey(z) != kb) sm.need_full = 1;
+        }
+    }
+    __syncthreads();
+    if (status_view || sm.need_full) {
+        if (threadIdx.x == 0) B2R_STAT(7, 1);
+        for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) sm.id[i] = -1;
+        tile_tris<3>(sm, S, V, vtris, tri_list, t_beg, t_end, X0, Y0, X1, Yb0, Y1, rh, status_view);
+        __syncthreads();
+    }
+
+    // ---- output: a warp per tile row ----
+    const bool dbg_planes = O.winner || O.stencil || O.z;
+    for (int row = wid; row < TILE_H; row += RASTER_WARPS) {
+        const int py = Y0 + row, px = X0 + lane;
+        if (py < Yb0 || py >= Y1) continue;  // whole warp
+        const int p = tpix(lane, row);
+        const int face = sm.id[p], stc = sm.st[p];
+        const size_t g = plane + (size_t)py * Fr.W + px;
+        if (dbg_planes && px < X1) {
+            if (O.winner) O.winner[g] = face;
+            if (O.stencil) O.stencil[g] = (short)stc;
+            if (O.z) O.z[g] = zkey_decode(sm.z[p]);
+        }
+        if (!FUSED) {   // one packed word per pixel for k_shade_packed
+            if (px < X1) O.packed[g] = face < 0 ? PACKED_NONE : ((unsigned)face | (stc == 0 ? PACKED_LIT : 0u));
+            continue;
+        }
+        // shading straight from the shared planes (triangular.py:135-171, core.py:640)
+        float c[3] = {0.f, 0.f, 0.f};
+        bool const_bg = false;
+        if (px < X1) {
+            if (face >= 0) {
+                if (!shade_face_pixel(S, V, Fr.light, vtris[face], face, px, py, stc == 0, c)) *Fr.err_flag = 1;
+            } else if (Fr.bg_mode == B2R_BG_CUBEMAP) {
+                skybox_pixel(S, V, Fr.sky_size, px, py, c);
+            } else {
+                c[0] = Fr.background[0]; c[1] = Fr.background[1]; c[2] = Fr.background[2];
+                const_bg = true;
+            }
+            if (O.f32) { float* o = O.f32 + g * 3; o[0] = c[0]; o[1] = c[1]; o[2] = c[2]; }
+        }
+        const unsigned packed = const_bg ? __ldg(O.bg_packed) : tonemap_pack(c);
+        store_row(Fr, O.rgb, view, X0, py, packed, px < X1, lane);
+    }
+}
+
+// Shading pass of the unfused path: one CTA of 128 threads per 32x32 tile (a warp per row), reading the packed winner
+// word k_tile<false> left behind.  Tiles whose lists are empty were never written: they are recognised here.
+__global__ void __launch_bounds__(RASTER_THREADS, B2R_SHADE_MINB)
+k_shade_packed(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec* __restrict__ tris, BinDev B,
+               TileOut O, int view0, int n_sub) {
+    const int view = (int)(blockIdx.x % (unsigned)n_sub) + view0;
+    const ViewDev& V = views[view];
+    const int n_tiles = Fr.tiles_x * Fr.tiles_y;
+    const int tile = B.order[(size_t)view * n_tiles + blockIdx.x / (unsigned)n_sub];
+    const int tx = tile % Fr.tiles_x, ty = tile / Fr.tiles_x + Fr.tile_row0;
+    const int X0 = tx * TILE_W, Y0 = ty * TILE_H;
+    const int X1 = min(X0 + TILE_W, Fr.W), Y1 = min(min(Y0 + TILE_H, Fr.H), Fr.row_end);
+    const int Yb0 = max(Y0, Fr.row_begin);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int* tri_off = B.tri_off + (size_t)view * (n_tiles + 1);
+    const int* quad_off = B.quad_off + (size_t)view * (n_tiles + 1);
+    const bool lists_ok = (B.overflow[view * 2] | B.overflow[view * 2 + 1]) == 0;
+    const bool empty = !lists_ok || (tri_off[tile] == tri_off[tile + 1] &&
+                                     (quad_off[tile] == quad_off[tile + 1] || !Fr.full_stencil));
+    const size_t plane = (size_t)view * Fr.H * Fr.W;
+    const TriRec* vtris = tris + (size_t)view * Fr.n_faces;
+    const unsigned bg = __ldg(O.bg_packed);
+    // a row segment that is constant background everywhere (all of an empty tile, most rows of a partly covered one):
+    // lane j < 24 stores bytes 4j .. 4j+3 of the repeating R,G,B pattern, no shuffles, no tonemap
+    const bool fast_bg = Fr.bg_mode != B2R_BG_CUBEMAP && !O.f32 && X0 + 32 <= Fr.W && (((size_t)Fr.W * 3) & 3) == 0;
+    unsigned bg_word = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bg_word |= ((bg >> (8 * ((4 * lane + i) % 3))) & 0xffu) << (8 * i);
+    for (int row = wid; row < TILE_H; row += RASTER_WARPS) {
+        const int py = Y0 + row, px = X0 + lane;
+        if (py < Yb0 || py >= Y1) continue;  // whole warp
+        const size_t g = plane + (size_t)py * Fr.W + px;
+        const unsigned w = (empty || px >= X1) ? PACKED_NONE : O.packed[g];
+        if (fast_bg && __all_sync(0xffffffffu, w == PACKED_NONE)) {
+            if (lane < 24)
+                reinterpret_cast<unsigned*>(O.rgb + ((size_t)view * Fr.H + (size_t)(Fr.H - 1 - py)) * Fr.W * 3 + (size_t)X0 * 3)[lane] = bg_word;
+            continue;
+        }
+        float c[3] = {0.f, 0.f, 0.f};
+        bool const_bg = false;
+        if (px < X1) {
+            if (w != PACKED_NONE) {
+                const int face = (int)(w & ~PACKED_LIT);
+                if (!shade_face_pixel(S, V, Fr.light, vtris[face], face, px, py, (w & PACKED_LIT) != 0, c)) *Fr.err_flag = 1;
+            } else if (Fr.bg_mode == B2R_BG_CUBEMAP) {
+                skybox_pixel(S, V, Fr.sky_size, px, py, c);
+            } else {
+                c[0] = Fr.background[0]; c[1] = Fr.background[1]; c[2] = Fr.background[2];
+                const_bg = true;
+            }
+            if (O.f32) { float* o = O.f32 + g * 3; o[0] = c[0]; o[1] = c[1]; o[2] = c[2]; }
+        }
+        const unsigned packed = const_bg ? bg : tonemap_pack(c);
+        store_row(Fr, O.rgb, view, X0, py, packed, px < X1, lane);
+    }
+}
+
+// pass-3 status of every face (core.py:624-636): pending faces carry coverage / z / lit bits ORed in by k_tile
 __global__ void k_status_resolve(uint8_t* __restrict__ status, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

@@ -4,8 +4,12 @@
 Bar (BASELINE.json north star): z-buffer (float64), stencil counts, z-test winners and per-face status bit-exact;
 uint8 RGB within 1 LSB on >= 99.9 % of the pixels.  All run on the B200 box:  pytest -m gpu
 """
+import os
+
 import numpy as np
 import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 import golden_util as gu
 import scenes
@@ -315,3 +319,31 @@ def test_async_pipeline_many_views_matches_single_frames():
         scene.camera, scene.debug_camera = cams[k], dcams[k]
         scene.persist_silhouette = False
         assert np.array_equal(scene.render(), host[k])
+
+
+@pytest.mark.gpu
+def test_fused_tile_kernel_alternative_stays_bit_exact():
+    """B2R_FUSED=1 (shading inside the tile kernel; measured slower, kept as the documented alternative) is selected when
+    the library initialises, hence a child process: three fixtures, z / stencil / winner bit-exact, RGB identical to the
+    production path's bytes."""
+    import subprocess
+    import sys
+    code = r'''
+import sys
+sys.path[:0] = [%r, %r + "/tests", %r + "/oracle"]
+import numpy as np
+import golden_util as gu, oracle as orc
+for name in ("g2_diablo_floor_point", "g6_skybox_orthographic", "g12_depth_test_false"):
+    scene, exp, meta = gu.load(name)
+    scene.persist_silhouette = False
+    ref = gu.oracle_frame(orc, scene)
+    dbg = {}
+    rgb = scene.render(debug=dbg)
+    rep = gu.compare_planes(dict(rgb=rgb, z=dbg["z"], stencil=dbg["stencil"], winner=dbg["winner"]), ref)
+    assert rep["z_mismatch"] == 0 and rep["stencil_mismatch"] == 0 and rep["winner_mismatch"] == 0 and rep["rgb_px_gt1"] == 0, (name, rep)
+    assert np.array_equal(scene.render(), rgb), name
+    print("FUSED-OK", name, rep)
+''' % (ROOT, ROOT, ROOT)
+    res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, B2R_FUSED="1"), capture_output=True, text=True,
+                         timeout=600)
+    assert res.returncode == 0 and res.stdout.count("FUSED-OK") == 3, res.stdout[-2000:] + res.stderr[-2000:]

@@ -270,3 +270,12 @@ def test_model_faces_match_the_reference_when_it_is_importable():
     I, N = np.array([[0.3, -0.8, 0.5], [1.0, 2.0, 3.0]]), np.array([[0.0, 1.0, 0.0], [0.6, 0.0, 0.8]])
     import py_numpy_renderer_b200 as b2r
     assert np.array_equal(b2r.Light.reflect(I, N), ref.Light.reflect(I, N))
+
+
+def test_texel_decode_closed_forms():
+    """csrc texel_decode(): (float)((double)u8 * (1/255)) and (float)((double)u8 * (2/255) - 1) are bit-identical to the
+    reference's f32(u8 / 255) and f32(u8 / 255 * 2 - 1) (core.py:96-104) for every uint8 value."""
+    i = np.arange(256)
+    assert np.array_equal((i.astype(np.float64) * (np.float64(1) / 255)).astype(np.float32), (i / 255).astype(np.float32))
+    assert np.array_equal((i.astype(np.float64) * (np.float64(2) / 255) - 1).astype(np.float32),
+                          (i / 255 * 2 - 1).astype(np.float32))

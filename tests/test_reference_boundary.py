@@ -162,3 +162,17 @@ def test_uv_below_minus_one_raises_index_error_on_the_gpu():
     # a scene that stays inside its maps is unaffected
     ok = scenes.c3_synthetic((60, 80), tex=64, nu=16, nv=8)
     ok.render()
+
+
+@pytest.mark.parametrize("name", ["g7_cube_mtl_rh_directx", "g13_depth_test_false_rh"])
+def test_product_scene_converted_to_reference_objects_reproduces_the_fixture(name):
+    """oracle/refboot.to_reference_scene (what bench.py's NumPy-reference arm renders) is the same scene: the unmodified
+    reference renders the committed fixture bit for bit from the product-side Scene description."""
+    _, refboot = _ref()
+    import contextlib
+    import io
+    import golden_util as gu
+    scene, exp, _ = gu.load(name)
+    with contextlib.redirect_stdout(io.StringIO()):
+        rgb = refboot.to_reference_scene(scene).render()
+    assert np.array_equal(rgb, exp['rgb'])

@@ -1,31 +1,29 @@
 """Per-source-line instruction and stall-sample shares from an ncu report captured with --import-source on.
-    ncu -i rep.ncu-rep --page source --csv --print-source cuda,sass > src.csv ; python tools/ncu_source_lines.py src.csv [launch] [top]"""
+    ncu -i rep.ncu-rep --page source --csv --print-source cuda,sass > src.csv
+    python tools/ncu_source_lines.py src.csv <kernel name substring> [top]
+Launches of the same kernel are summed."""
 import csv
 import sys
 from collections import defaultdict
 
 path = sys.argv[1]
-want = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+want = sys.argv[2] if len(sys.argv) > 2 else ""
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-rows = list(csv.reader(open(path)))
-launch, cur_file, hdr, first_file = -1, "?", None, None
+cur_file, cur_fn, hdr = "?", "", None
 agg = defaultdict(lambda: [0, 0, ""])  # (file, line) -> [inst, samples, text]
-for r in rows:
+for r in csv.reader(open(path)):
     if not r:
         continue
-    if r[0] == "File Path":  # one block per source file; the first file showing up again starts the next launch
+    if r[0] == "File Path":
         cur_file = r[1].split("/")[-1]
-        if first_file is None:
-            first_file = cur_file
-        if cur_file == first_file:
-            launch += 1
         continue
     if r[0] == "Function Name":
+        cur_fn = r[1]
         continue
     if r[0] == "Line No":
         hdr = {n: i for i, n in enumerate(r)}
         continue
-    if launch != want or hdr is None:
+    if hdr is None or want not in cur_fn:
         continue
     if r[0]:  # a CUDA source line: aggregated metrics of its SASS
         try:  # a source line holding inline asm with quotes breaks the csv fields: skip it
@@ -38,6 +36,6 @@ for r in rows:
         agg[key][2] = r[1].strip()
 ti = sum(v[0] for v in agg.values()) or 1
 ts = sum(v[1] for v in agg.values()) or 1
-print(f"launch {want}: {ti} warp instructions, {ts} samples, {len(agg)} source lines")
+print(f"kernel *{want}*: {ti} warp instructions, {ts} samples, {len(agg)} source lines")
 for (f, l), v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
     print(f"{100 * v[1] / ts:5.1f}% smp {100 * v[0] / ti:5.1f}% inst  {f}:{l:<5d} {v[2][:110]}")
