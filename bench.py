@@ -37,6 +37,13 @@ import sys
 import threading
 import time
 
+# --impl reference with several worker processes: one BLAS thread per worker (the thread count is fixed when NumPy loads
+# its BLAS, i.e. before the arguments are parsed).  A single worker (--ref-procs 1) keeps the library's own default, which
+# is how the reference runs when a user starts it.
+if "reference" in sys.argv and not ("--ref-procs" in sys.argv and sys.argv[sys.argv.index("--ref-procs") + 1:][:1] == ["1"]):
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ.setdefault(_v, "1")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
@@ -252,8 +259,6 @@ def numpy_reference_sample(workload, res, n_frames, procs, radius):
     threaded: P processes render P different frames).  -> (frames/s, wall s, per-frame seconds)"""
     import multiprocessing as mp
     ctx = mp.get_context("fork")
-    os.environ.setdefault("OMP_NUM_THREADS", "1")          # inherited: one BLAS thread per worker
-    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
     procs = max(1, min(procs, n_frames))
     shards = [list(range(p, n_frames, procs)) for p in range(procs)]
     barrier, queue = ctx.Barrier(procs + 1), ctx.Queue()
@@ -315,6 +320,14 @@ def run_reference(args, rank, world):
     base = {"value": fps, "unit": UNIT, "cores": cores,
             "kind": "reference" if kind == "numpy" else "port"}
     if kind == "numpy":
+        try:   # the C restatement on the same cores, for comparison (one short pass)
+            cams = scenes.orbit_cameras(n_frames, radius=radius, start=0.123)
+            dcams = scenes.orbit_cameras(n_frames, radius=radius, start=0.123, fovy=90, near=0.05, far=20)
+            cpu_port_sample(scene, cams[:1], dcams[:1], 1)
+            base["port_fps_same_cores"] = cpu_port_sample(scene, cams, dcams, procs)[0]
+        except Exception as exc:  # noqa: BLE001
+            base["port_fps_same_cores"] = f"unavailable: {exc}"[:120]
+        base["blas_threads_per_process"] = os.environ.get("OPENBLAS_NUM_THREADS", "library default")
         base["sample"] = (f"{n_frames} orbit frames per step over {min(procs, n_frames)} processes (one frame each, "
                           f"fresh Models per frame), the UNMODIFIED NumPy reference (Scene.render, obj/core.py:587-640) "
                           f"imported from baseline/_ref/ref_src.zip; median single-frame time "

@@ -187,6 +187,12 @@ int b2r_wait(int64_t ticket);
 int b2r_sync(void);
 void* b2r_stream(void); /* the cudaStream_t the library launches on */
 
+/* Page-locked host memory for frame buffers (cudaHostAlloc / cudaFreeHost): a device-to-host copy into pageable memory is
+ * staged by the driver at a fraction of the PCIe rate.  The Python API keeps a small pool of these behind the arrays
+ * `Scene.render()` returns. */
+int b2r_host_alloc(int64_t bytes, void** host_ptr);
+int b2r_host_free(void* host_ptr);
+
 /* Number of kernel launches issued by this library since init (bench.py `gpu_launches`). */
 int64_t b2r_launch_count(void);
 

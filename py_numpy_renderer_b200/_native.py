@@ -56,6 +56,8 @@ _SYMBOLS = {
     "b2r_window_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "b2r_window_close": (C.c_int, [C.c_void_p]),
     "b2r_window_destroy": (C.c_int, [C.c_void_p]),
+    "b2r_host_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
+    "b2r_host_free": (C.c_int, [C.c_void_p]),
     "b2r_obj_load": (C.c_int, [C.c_char_p, C.c_void_p]),
     "b2r_obj_free": (None, [C.c_void_p]),
 }
@@ -191,6 +193,56 @@ def _dev_ptr(t):
     return C.c_void_p(int(t.data_ptr()) if hasattr(t, "data_ptr") else int(t))
 
 
+class _PinnedPool:
+    """Page-locked buffers behind the arrays `Scene.render()` / `render_batch()` hand out when the caller passes no
+    `out`: the device-to-host copy of a frame runs at the PCIe rate instead of being staged through the driver's bounce
+    buffer, and a buffer returns to the pool when the last view of its array is garbage collected.  At most `limit`
+    buffers are outstanding or cached; beyond that ordinary (pageable) arrays are returned."""
+
+    def __init__(self, limit=12, max_bytes=1 << 30):
+        self.limit, self.max_bytes = limit, max_bytes
+        self.free = {}          # nbytes -> [ptr]
+        self.count = 0
+
+    def array(self, shape):
+        import weakref
+        n = int(np.prod(shape))
+        if n <= 0 or n > self.max_bytes:
+            return None
+        lib = init()
+        bucket = self.free.get(n)
+        if bucket:
+            ptr = bucket.pop()
+        else:
+            if self.count >= self.limit:
+                self._trim()
+                if self.count >= self.limit:
+                    return None
+            p = C.c_void_p()
+            if lib.b2r_host_alloc(n, C.byref(p)) != 0:
+                return None
+            ptr = p.value
+            self.count += 1
+        raw = (C.c_uint8 * n).from_address(ptr)
+        weakref.finalize(raw, self._release, n, ptr)     # runs when the last array viewing `raw` is gone
+        return np.ctypeslib.as_array(raw).reshape(shape)
+
+    def _release(self, n, ptr):
+        self.free.setdefault(n, []).append(ptr)
+
+    def _trim(self):
+        """Drop cached buffers (of sizes nobody asked for lately) to make room."""
+        lib = load_library()
+        for n in list(self.free):
+            while self.free[n]:
+                lib.b2r_host_free(C.c_void_p(self.free[n].pop()))
+                self.count -= 1
+            del self.free[n]
+
+
+_pinned_pool = _PinnedPool()
+
+
 class DeviceScene:
     """Device mirror of a list of host `Model`s (+ optional CubeMap)."""
 
@@ -288,7 +340,11 @@ class DeviceScene:
                     raise ValueError("out must be a C-contiguous uint8 array of shape (n, H, W, 3)")
                 frames = out
             else:
-                frames = np.zeros((n, H, W, 3), np.uint8) if band is not None else np.empty((n, H, W, 3), np.uint8)
+                frames = _pinned_pool.array((n, H, W, 3))       # page-locked when the pool has room
+                if frames is None:
+                    frames = np.empty((n, H, W, 3), np.uint8)
+                if band is not None:
+                    frames[...] = 0
             target = C.c_void_p(frames.ctypes.data)
         mode = 1 if on_device else (0 if (wait or want_debug) else 2)
         _check(self.lib.b2r_render(self.handle, C.byref(fp), C.cast(views, C.c_void_p), n, target,
@@ -369,8 +425,8 @@ def status_report(models, face_status):
     start = 0
     for m in models:
         n = len(m._faces)
-        st = np.asarray(face_status[start:start + n])
+        hist = np.bincount(np.asarray(face_status[start:start + n], dtype=np.uint8), minlength=32)
         start += n
-        counts = {err: int((st == err.value).sum()) for err in Errors}
-        lines += [f"Total faces {n}", f"Face rendered {int((st == 0).sum())}", f"Discarded {counts}"]
+        counts = {err: int(hist[err.value]) for err in Errors}
+        lines += [f"Total faces {n}", f"Face rendered {int(hist[0])}", f"Discarded {counts}"]
     return lines

@@ -177,6 +177,9 @@ struct b2r_scene {
     DevBuf<ViewDev> views;
     DevBuf<TriRec> tris;
     DevBuf<TriBox> boxes;     // (views, F) what binning needs of a face
+    DevBuf<double4> vrec;     // (views, V) per-vertex screen x, y, z and 1/w (k_vertex)
+    DevBuf<uint8_t> vinside;  // (views, V) vertex well inside both frusta
+    int n_vertices = 0;
     DevBuf<int> coop_list;    // (views, F) faces queued for k_tri_count; their counts sit behind the tile counters
     DevBuf<QuadRec> quads;
     DevBuf<int> tile_counts, tile_offs, tri_list, quad_list, overflow, tile_order;
@@ -393,6 +396,18 @@ int b2r_debug_stats(unsigned long long* out16, int reset) {
     if (reset) { unsigned long long z[16] = {0}; CK(cudaMemcpyToSymbol(g_stats, z, sizeof(z))); }
     return 0;
 }
+int b2r_host_alloc(int64_t bytes, void** host_ptr) {
+    CTX_OR_FAIL();
+    if (bytes <= 0 || !host_ptr) return fail("b2r_host_alloc: bad arguments");
+    CK(cudaSetDevice(g.device));
+    CK(cudaHostAlloc(host_ptr, (size_t)bytes, cudaHostAllocPortable));
+    return 0;
+}
+int b2r_host_free(void* host_ptr) {
+    if (!host_ptr) return 0;
+    CK(cudaFreeHost(host_ptr));
+    return 0;
+}
 // ---- multi-GPU output window: CUDA IPC export / import of the assembling rank's frame buffer ----
 int b2r_window_create(int64_t bytes, void** dev_ptr, void* handle_out) {
     CTX_OR_FAIL();
@@ -550,6 +565,7 @@ int b2r_scene_create(const b2r_model_desc* models, int32_t n_models, const b2r_t
     }
     edge_ptr.push_back((int)half.size());
     sc->n_faces = (int)nf;
+    sc->n_vertices = (int)nv;
     sc->n_edges = (int)edge_v.size();
 
 #define UP(buf, vec)                                                                                          \
@@ -635,7 +651,7 @@ int b2r_scene_destroy(b2r_scene* sc) {
     for (uchar4* d : sc->tex_data) cudaFree(d);
     sc->sky.release(); sc->edge_v.release(); sc->edge_ptr.release(); sc->edge_inc.release(); sc->edge_model.release();
     sc->sil_state.release(); sc->facing.release(); sc->sil.release(); sc->counters.release(); sc->views.release();
-    sc->tris.release(); sc->boxes.release(); sc->coop_list.release(); sc->quads.release(); sc->tile_counts.release(); sc->tile_offs.release(); sc->tri_list.release();
+    sc->tris.release(); sc->boxes.release(); sc->coop_list.release(); sc->vrec.release(); sc->vinside.release(); sc->quads.release(); sc->tile_counts.release(); sc->tile_offs.release(); sc->tri_list.release();
     sc->quad_list.release(); sc->pair_list.release(); sc->overflow.release(); sc->tile_order.release(); sc->winner.release(); sc->packed.release(); sc->stencil.release(); sc->zplane.release();
     sc->status.release(); sc->frame_f32.release(); sc->rgb[0].release(); sc->rgb[1].release();
     delete sc;
@@ -817,7 +833,7 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
     // same as "pixels whose z-buffer was written": count everywhere then
     Fr.full_stencil = ((dbg && dbg->stencil) || sc->has_no_zwrite) ? 1 : 0;
     const int n_tiles = Fr.tiles_x * Fr.tiles_y;
-    const int F = sc->n_faces;
+    const int F = sc->n_faces, NV = std::max(1, sc->n_vertices);
     // Silhouette / quad records: far fewer edges are extruded at once than the mesh has (diablo 1 381 of 7 533, the 1M-
     // triangle torus ~3 000 of 1.5 M), so the records are sized by a capacity that grows on overflow like the tile lists
     if (sc->sil_cap == 0) sc->sil_cap = std::min(std::max(1, sc->n_edges), std::max(16384, sc->n_edges / 16));
@@ -829,7 +845,7 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
     // chunks, so that the D2H copy of chunk i (copy stream) overlaps the kernels of chunk i+1 (compute stream).
     const bool fused = g.fused != 0;
     const bool want_planes = dbg && (dbg->winner || dbg->stencil);  // debug winner / stencil planes in HBM
-    const size_t per_view = (size_t)F * (sizeof(TriRec) + sizeof(TriBox) + sizeof(int)) + (size_t)E * sizeof(QuadRec) + (want_planes ? npx * 6 : 0) +
+    const size_t per_view = (size_t)F * (sizeof(TriRec) + sizeof(TriBox) + sizeof(int)) + (size_t)NV * 33 + (size_t)E * sizeof(QuadRec) + (want_planes ? npx * 6 : 0) +
                             (fused ? 0 : npx * 4) + (want_z ? npx * 8 : 0) + (want_f32 ? npx * 12 : 0);
     int VB = (int)std::max<size_t>(1, std::min<size_t>(n_views, ((size_t)6 << 30) / std::max<size_t>(per_view, 1)));
     VB = std::min(VB, 64);
@@ -930,6 +946,8 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
 
         CK(sc->tris.reserve((size_t)VB * F));
         CK(sc->boxes.reserve((size_t)VB * F));
+        CK(sc->vrec.reserve((size_t)VB * NV));
+        CK(sc->vinside.reserve((size_t)VB * NV + 8));
         CK(sc->quads.reserve((size_t)VB * E));
         CK(sc->tile_counts.reserve((size_t)VB * n_tiles * 2 + (size_t)VB * (3 + BIN_HUGE_CAP)));  // + pair / huge-face / queued-face counters and lists
         CK(sc->coop_list.reserve((size_t)VB * F));
@@ -998,8 +1016,11 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
                         CK(cudaStreamWaitEvent(g.fork_stream, g.chunk_done, 0));
                         ts = g.fork_stream;
                     }
-                    k_tri_setup<<<dim3((F + 127) / 128, pv), 128, 0, ts>>>(S, dviews, Fr, sc->tris.p, sc->boxes.p, status,
-                                                                           coop_count, sc->coop_list.p, p0);
+                    k_vertex<<<dim3((NV + 127) / 128, pv), 128, 0, ts>>>(S, NV, dviews, sc->vrec.p, sc->vinside.p, p0);
+                    ++g.launches;
+                    k_tri_setup<<<dim3((F + 127) / 128, pv), 128, 0, ts>>>(S, NV, dviews, Fr, sc->vrec.p, sc->vinside.p,
+                                                                           sc->tris.p, sc->boxes.p, status, coop_count,
+                                                                           sc->coop_list.p, p0);
                     k_tri_count<<<dim3(std::max(1, std::min((F + 7) / 8, g.sm_count * 2)), pv), 256, 0, ts>>>(
                         S, dviews, sc->tris.p, sc->boxes.p, status, coop_count, sc->coop_list.p, p0);
                     g.launches += 2;

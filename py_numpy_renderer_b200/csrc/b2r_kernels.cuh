@@ -161,13 +161,41 @@ __device__ __forceinline__ bool tri_pixel_in(const TriRec& r, const double* cc, 
 
 constexpr int COV_SERIAL_MAX = 128;  // boxes up to this many pixels are counted by the owning thread
 
+// One thread per (vertex, view): the vertex stage of rasterize() (triangular.py:36-45) evaluated once per vertex
+// instead of once per corner of every incident face (a vertex of a closed mesh has ~6 of them).  The operations and
+// their order are exactly those of the per-face form, so the records are the same bits.
+//   rec = (screen x, screen y, screen z (viewport), 1/w)      inside = all of |x|,|y|,|z| < w(1-1e-9) in BOTH frusta
+__global__ void k_vertex(SceneDev S, int n_vertices, const ViewDev* __restrict__ views, double4* __restrict__ vrec,
+                         uint8_t* __restrict__ vinside, int view0) {
+    const int view = blockIdx.y + view0;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_vertices) return;
+    const ViewDev& V = views[view];
+    const double4 p = S.pos[v];
+    const double w[4] = {p.x, p.y, p.z, p.w};
+    double c[4], cd[4];
+    vec4_mat4(w, V.mvp, c);
+    vec4_mat4(w, V.mvp_dbg, cd);
+    const double m = 1.0 - 1e-9;
+    const double wc = c[3] * m, wd = cd[3] * m;
+    const bool inside = wc > 0 && wd > 0 && fabs(c[0]) < wc && fabs(c[1]) < wc && fabs(c[2]) < wc &&
+                        fabs(cd[0]) < wd && fabs(cd[1]) < wd && fabs(cd[2]) < wd;
+    const double dpt = 1.0 / c[3];
+    const double t[4] = {c[0] * dpt, c[1] * dpt, c[2] * dpt, c[3] * dpt};
+    double s4[4];
+    vec4_mat4(t, V.viewport, s4);
+    vrec[(size_t)view * n_vertices + v] = make_double4(s4[0], s4[1], s4[2], dpt);
+    vinside[(size_t)view * n_vertices + v] = inside ? 1 : 0;
+}
+
 // One thread per (face, view).  The common path keeps no clip coordinates alive (the per-pixel clip test is elided for
 // faces well inside both frusta): 3 x (2 vec.mat, 1/w, viewport) -> cull -> box -> float32
 // constants -> N == 1 count over the (small) box.  Faces that need the per-pixel clip test for the count, or whose
 // box is large, are queued for k_tri_count (a warp per face).  Every face writes its 16-byte TriBox; only valid faces
 // touch their 128-byte record.
 __global__ void __launch_bounds__(128, 8)
-k_tri_setup(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, TriRec* __restrict__ recs,
+k_tri_setup(SceneDev S, int n_vertices, const ViewDev* __restrict__ views, FrameDev Fr,
+            const double4* __restrict__ vrec, const uint8_t* __restrict__ vinside, TriRec* __restrict__ recs,
             TriBox* __restrict__ boxes, uint8_t* __restrict__ status, int* __restrict__ coop_count,
             int* __restrict__ coop_list, int view0) {
     const int view = blockIdx.y + view0;
@@ -180,25 +208,11 @@ k_tri_setup(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, TriRec* 
     double sx[3], sy[3], sz[3];
     bool inside = true;   // all three vertices well inside both frusta: the per-pixel clip test cannot fail
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {  // triangular.py:36-45
-        const double4 p = S.pos[vidx[i]];
-        const double w[4] = {p.x, p.y, p.z, p.w};
-        double c[4];
-        vec4_mat4(w, V.mvp, c);
-        if (fv.w & FS_CLIP) {
-            double cd[4];
-            vec4_mat4(w, V.mvp_dbg, cd);
-            const double m = 1.0 - 1e-9;
-            const double wc = c[3] * m, wd = cd[3] * m;
-            inside = inside && wc > 0 && wd > 0 && fabs(c[0]) < wc && fabs(c[1]) < wc && fabs(c[2]) < wc &&
-                     fabs(cd[0]) < wd && fabs(cd[1]) < wd && fabs(cd[2]) < wd;
-        }
-        const double dpt = 1.0 / c[3];
-        const double t[4] = {c[0] * dpt, c[1] * dpt, c[2] * dpt, c[3] * dpt};
-        double s4[4];
-        vec4_mat4(t, V.viewport, s4);
-        sx[i] = s4[0]; sy[i] = s4[1]; sz[i] = s4[2];
-        r.d[i] = dpt;
+    for (int i = 0; i < 3; ++i) {  // the vertex stage (triangular.py:36-45) was evaluated per vertex by k_vertex
+        const double4 q = vrec[(size_t)view * n_vertices + vidx[i]];
+        sx[i] = q.x; sy[i] = q.y; sz[i] = q.z;
+        r.d[i] = q.w;
+        inside = inside && vinside[(size_t)view * n_vertices + vidx[i]] != 0;
     }
     int st = -1;
     bool need_coop = false;
@@ -266,7 +280,7 @@ k_tri_setup(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, TriRec* 
         if (status) status[(size_t)view * S.n_faces + f] = (uint8_t)st;
     } else {
         bx.bx0 = r.bx0; bx.bx1 = r.bx1; bx.by0 = r.by0; bx.by1 = r.by1; bx.flags = r.flags;
-        if (status) status[(size_t)view * S.n_faces + f] = 0xE0;  // pending: the tile kernel ORs coverage / z / lit bits in
+        if (status) status[(size_t)view * S.n_faces + f] = 0xE1;  // pending + covered: the tile kernel ORs the z / lit bits in
     }
     boxes[(size_t)view * S.n_faces + f] = bx;
     if (need_coop) coop_list[(size_t)view * S.n_faces + atomicAdd(coop_count + view, 1)] = f;
@@ -411,11 +425,17 @@ __device__ __forceinline__ double edge_fn(double px, double py, double x0, doubl
 //   0 = no pixel of the rectangle can be inside,  1 = some may be,  2 = every pixel of the rectangle is inside.
 constexpr int QUAD_FULL_BIT = 1 << 30;  // flag in a tile-list entry: the quad covers every pixel of the tile
 constexpr int TRI_CLIP_BIT = 1 << 30;   // flag in a triangle tile-list entry: the face needs the per-pixel clip test
-__device__ __forceinline__ int quad_tile_class(const QuadRec& R, int x0, int x1, int y0, int y1) {
+// The polygon of the quad a warp is classifying, staged once in shared memory together with its edge vectors: the
+// classification of hundreds of (quad, tile) pairs then reads broadcast shared-memory words instead of the 256-byte
+// global record, and the edge subtraction is done once per quad.
+struct QuadEdges {
+    double x[B2R_MAX_POLY], y[B2R_MAX_POLY], ex[B2R_MAX_POLY], ey[B2R_MAX_POLY];
+    int n, front;
+};
+__device__ __forceinline__ int quad_tile_class(const QuadEdges& R, int x0, int x1, int y0, int y1) {
     bool full = true;
     for (int i = 0; i < R.n; ++i) {
-        const int j = (i + 1 == R.n) ? 0 : i + 1;
-        const double ex = R.x[j] - R.x[i], ey = R.y[j] - R.y[i];
+        const double ex = R.ex[i], ey = R.ey[i];
         // corner maximising f = (px-xi)*ey - (py-yi)*ex, and the opposite corner minimising it
         const double fmax = edge_fn(ey >= 0 ? x1 : x0, ex <= 0 ? y1 : y0, R.x[i], R.y[i], ex, ey);
         const double fmin = edge_fn(ey >= 0 ? x0 : x1, ex <= 0 ? y0 : y1, R.x[i], R.y[i], ex, ey);
@@ -571,7 +591,9 @@ __global__ void k_bin(FrameDev Fr, const TriBox* __restrict__ boxes, const QuadR
     // blocks of the box).  Surviving pairs collect in a per-warp shared-memory run and reach the per-view pair list
     // with one global atomic per run.
     __shared__ int2 pair_buf[8][BIN_PAIR_BUF];
+    __shared__ QuadEdges edges[8];
     int2* const my_buf = pair_buf[threadIdx.x >> 5];
+    QuadEdges& QE = edges[threadIdx.x >> 5];
     int2* const pair_list = B.pair_list + (size_t)view * B.quad_cap;
     int n_buf = 0;  // warp-uniform
     auto flush = [&]() {
@@ -589,9 +611,19 @@ __global__ void k_bin(FrameDev Fr, const TriBox* __restrict__ boxes, const QuadR
     const int part = warp_id % share;
     for (int prim = warp_id / share; prim < n_quads; prim += total_warps / share) {
         const QuadRec* Q = quads + (size_t)view * quad_stride + prim;
-        if (Q->n == 0) continue;
+        const int qn = Q->n;
+        if (qn == 0) continue;
         const int bx0 = Q->bx0, bx1 = Q->bx1, by0 = max((int)Q->by0, band_y0), by1 = min((int)Q->by1, band_y1);
         if (by0 >= by1 || bx0 >= bx1) continue;
+        __syncwarp();   // the previous quad's edges are no longer read
+        if (lane < qn) { QE.x[lane] = Q->x[lane]; QE.y[lane] = Q->y[lane]; }
+        if (lane == 0) { QE.n = qn; QE.front = Q->front; }
+        __syncwarp();
+        if (lane < qn) {
+            const int j = (lane + 1 == qn) ? 0 : lane + 1;
+            QE.ex[lane] = QE.x[j] - QE.x[lane]; QE.ey[lane] = QE.y[j] - QE.y[lane];
+        }
+        __syncwarp();
         // Two levels.  The box of a shadow quad (a long diagonal sliver) holds many more tiles than the quad touches,
         // so blocks of BIN_SUPER x BIN_SUPER tiles are classified first with the same exact corner test: a rejected
         // block rejects its tiles, a block that is inside everywhere makes its tiles "full" without further tests
@@ -606,7 +638,7 @@ __global__ void k_bin(FrameDev Fr, const TriBox* __restrict__ boxes, const QuadR
                 sty = sy0 + si / sw; stx = sx0 + si % sw;
                 const int ta = max(tx0, stx * BIN_SUPER), tb = min(tx1, (stx + 1) * BIN_SUPER);
                 const int tc = max(ty0, sty * BIN_SUPER), td = min(ty1, (sty + 1) * BIN_SUPER);
-                s_cls = quad_tile_class(*Q, max(bx0, ta * TILE_W), min(bx1, tb * TILE_W) - 1,
+                s_cls = quad_tile_class(QE, max(bx0, ta * TILE_W), min(bx1, tb * TILE_W) - 1,
                                         max(by0, tc * TILE_H), min(by1, td * TILE_H) - 1);
             }
             unsigned alive = __ballot_sync(0xffffffffu, s_cls != 0);
@@ -627,7 +659,7 @@ __global__ void k_bin(FrameDev Fr, const TriBox* __restrict__ boxes, const QuadR
                 if (src >= 0 && tx >= tx0 && tx < tx1 && ty >= ty0 && ty < ty1) {
                     const int x0 = max(bx0, tx * TILE_W), x1 = min(bx1, (tx + 1) * TILE_W) - 1;
                     const int y0 = max(by0, ty * TILE_H), y1 = min(by1, (ty + 1) * TILE_H) - 1;
-                    cls = b_cls == 2 ? 2 : quad_tile_class(*Q, x0, x1, y0, y1);
+                    cls = b_cls == 2 ? 2 : quad_tile_class(QE, x0, x1, y0, y1);
                     // "full" only counts when the rectangle is the whole tile (clipped to the screen and the band)
                     if (cls == 2 && x0 == tx * TILE_W && x1 == min(Fr.W, (tx + 1) * TILE_W) - 1 &&
                         y0 == max(band_y0, ty * TILE_H) && y1 == min(min(Fr.H, band_y1), (ty + 1) * TILE_H) - 1)
@@ -766,7 +798,10 @@ __device__ __forceinline__ void store_relaxed_smem(int* p, int v) {
 
 constexpr int RASTER_WARPS = RASTER_THREADS / 32;
 constexpr int STAGE_TRIS = 32;   // triangle records staged in shared memory per round
-constexpr int STAGE_CLIP = 16;   // of which at most this many need the per-pixel clip test (clip coordinates staged too)
+#ifndef B2R_STAGE_CLIP
+#define B2R_STAGE_CLIP 16
+#endif
+constexpr int STAGE_CLIP = B2R_STAGE_CLIP;   // of which at most this many need the per-pixel clip test (clip coordinates staged too)
 constexpr int REC_DOUBLES = 17;  // 128-byte record + 8 bytes of padding: consecutive records start on different banks
 static_assert(sizeof(TriRec) == 128, "TriRec layout");
 
@@ -1501,8 +1536,8 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
         __syncthreads();
     }
 
-    // ---- winner: verified last improver, full pass on ties / lost races / status requests ----
-    if (!status_view && !sm.need_full) {
+    // ---- winner: verified last improver, full pass on ties / lost races ----
+    if (!sm.need_full) {
         for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) {
             const int ly = i >> 5, lx = i & 31;
             const int p = tpix(lx, ly);
@@ -1519,11 +1554,24 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
         }
     }
     __syncthreads();
-    if (status_view || sm.need_full) {
+    if (sm.need_full) {
         if (threadIdx.x == 0) B2R_STAT(7, 1);
         for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) sm.id[i] = -1;
         tile_tris<3>(sm, S, V, vtris, tri_list, t_beg, t_end, X0, Y0, X1, Yb0, Y1, rh, status_view);
         __syncthreads();
+    } else if (status_view) {
+        // Pass-3 status (core.py:624-636) without the full pass: no exact tie was seen in this tile, so the faces that pass
+        // the z-test here are exactly the verified winners, and a face is "rendered" iff it wins a pixel whose stencil
+        // count is 0 (every face that reached the lists covers a pixel: k_tri_setup set the covered bit).  A face's
+        // byte is read first: the atomic is issued once per face and tile, not once per pixel.
+        for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) {
+            const int f = sm.id[i];
+            if (f < 0 || sm.st[i] != 0) continue;
+            uint8_t* sp = status_view + f;
+            if (*(volatile uint8_t*)sp & 4) continue;
+            unsigned* wp = (unsigned*)((uintptr_t)sp & ~(uintptr_t)3);
+            atomicOr(wp, (2u | 4u) << (8 * ((uintptr_t)sp & 3)));
+        }
     }
 
     // ---- output: a warp per tile row ----

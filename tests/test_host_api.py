@@ -279,3 +279,33 @@ def test_texel_decode_closed_forms():
     assert np.array_equal((i.astype(np.float64) * (np.float64(1) / 255)).astype(np.float32), (i / 255).astype(np.float32))
     assert np.array_equal((i.astype(np.float64) * (np.float64(2) / 255) - 1).astype(np.float32),
                           (i / 255 * 2 - 1).astype(np.float32))
+
+
+def test_overlay_fast_exit_never_hides_a_segment():
+    """overlay.segments() returns [] early when the camera frustum lies strictly inside the debug frustum; whenever it
+    does, the full clipping sequence of the reference (frustums.py:46-75) must come out empty as well."""
+    import scenes
+    from py_numpy_renderer_b200 import overlay
+    rng = np.random.default_rng(11)
+    sc = scenes.c3_synthetic((90, 160), tex=32, nu=8, nv=4)
+    fast_hits = 0
+    for k in range(150):
+        pos = rng.uniform(-3, 3, 3)
+        pos[1] = abs(pos[1]) + 0.2
+        center = rng.uniform(-0.5, 0.5, 3)
+        fovy, near, far = rng.uniform(30, 80), rng.uniform(0.05, 0.5), rng.uniform(4, 15)
+        cam = b2r.Camera(tuple(pos), center=center, fovy=fovy, near=near, far=far)
+        if k % 3 == 0:      # containing debug frustum (how every throughput scene is set up)
+            dcam = b2r.Camera(tuple(pos), center=center, fovy=fovy + rng.uniform(5, 40), near=near / 2, far=far * 2)
+        elif k % 3 == 1:    # unrelated debug camera
+            dcam = b2r.Camera(tuple(rng.uniform(-3, 3, 3)), center=rng.uniform(-0.5, 0.5, 3), fovy=rng.uniform(30, 100),
+                              near=rng.uniform(0.05, 1), far=rng.uniform(2, 20))
+        else:               # nearly identical frusta: the margin decides
+            dcam = b2r.Camera(tuple(pos), center=center, fovy=fovy + rng.uniform(-1e-3, 1e-3), near=near, far=far)
+        cam.scene = dcam.scene = sc
+        if overlay.camera_frustum_inside_debug_frustum(cam, dcam):
+            fast_hits += 1
+            assert overlay.segments_full(cam, dcam) == []
+        else:
+            assert len(overlay.segments(cam, dcam)) == len(overlay.segments_full(cam, dcam))
+    assert fast_hits >= 40
