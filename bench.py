@@ -700,7 +700,9 @@ def main():
                 assert int(tmp[j].max()) > int(tmp[j].min()), "re-rendered frame is constant"
         byte_check = {"frames_checked": checked, "frames_differing": bad,
                       "what": f"rank 0 re-rendered views {sample} of every rank's last step and compared bytes"}
-        assert bad == 0, byte_check
+    if world > 1:
+        dist.barrier()                   # nobody overwrites a window slot (stage pass below) while rank 0 still compares
+        assert byte_check is None or byte_check["frames_differing"] == 0, byte_check
 
     # per-stage CUDA-event timing (library stream) on a few more steps of the same workload, synchronised per step
     n_stage_steps = min(K, 5)
