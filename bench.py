@@ -342,7 +342,10 @@ def run_reference(args, rank, world):
             "vs_baseline": None, "dtype": "f64",
             "data": "reference assets" if workload == "diablo" else "synthetic",
             "mpix_per_s": fps * H * W / 1e6,
-            "config": {"workload": desc, "resolution": [H, W], "frames_per_step": n_frames},
+            "config": {"workload": desc, "resolution": [H, W], "frames_per_step_per_gpu": args.views,
+                       "split": args.split, "cpu_frames_per_timed_step": n_frames,
+                       "note": "same scene, resolution and orbit as the B200 arm; a CPU step is a bounded sample of "
+                               "cpu_frames_per_timed_step frames (one per worker), rates are per frame"},
             "cpu_baseline": base,
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))

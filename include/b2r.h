@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define B2R_ABI_VERSION 4
+#define B2R_ABI_VERSION 5
 #define B2R_MAX_POLY 12 /* a quad clipped by 6 planes has at most 10 vertices */
 
 /* Light kinds: obj/lightning.py:4-7 */
@@ -48,6 +48,11 @@ enum { B2R_LIGHT_DIRECTIONAL = 0, B2R_LIGHT_POINT = 1, B2R_LIGHT_SPOT = 2 };
 enum { B2R_TEX_UNORM = 0, B2R_TEX_SNORM = 1 };
 /* vertex storage of Model.vertices: float32 straight from the loader, float64 after an `@` chain (core.py:350-352) */
 enum { B2R_F32 = 0, B2R_F64 = 1 };
+/* Shading function applied at the call site of rasterize() (triangular.py:120-130).  The reference ships the call to
+ * general_shading and, commented out beside it, flat_shading / gouraud / pbr (triangular.py:174-263): selecting one of
+ * those reproduces what the reference renders with that line swapped in (both passes then write the same value, so
+ * the shadow stencil has no visible effect). */
+enum { B2R_SHADE_GENERAL = 0, B2R_SHADE_FLAT = 1, B2R_SHADE_GOURAUD = 2, B2R_SHADE_PBR = 3 };
 /* background: core.py:595-600 */
 enum { B2R_BG_COLOR = 0, B2R_BG_CUBEMAP = 1 };
 /* per-face status of pass 3, triangular.py:15-20 (bit values of the reference's `Errors` Flag; 0 = rendered) */
@@ -70,6 +75,8 @@ typedef struct b2r_material {
     int32_t map_Ks;
     int32_t norm;
     int32_t reserved;
+    double Pm, Pr;  /* metalness, roughness (materials.py:47-48), read by pbr() only */
+    double Ka[3];   /* ambient colour (materials.py:49), the `ao` of pbr() */
 } b2r_material;
 
 /* One `Model` (core.py:231-256).  faces is the reference's (F,3,4) int32 array: per corner [v, vt, vn, mtl]. */
@@ -129,7 +136,7 @@ typedef struct b2r_frame_params {
     int32_t row_begin, row_end; /* screen-row band [row_begin,row_end) in BUFFER rows (pre-flip); 0,height = all */
     int32_t persist_silhouette; /* 1: toggle the scene's persistent silhouette like core.py:605 (Appendix B-3);
                                    0: every view starts from an empty set (fresh-Model semantics) */
-    int32_t reserved;
+    int32_t shading;            /* B2R_SHADE_*; 0 = general_shading, what the reference's render() runs */
 } b2r_frame_params;
 
 /* Optional per-view debug planes, each NULL or n_views * height * width elements (device or host pointer as the

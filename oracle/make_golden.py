@@ -208,6 +208,14 @@ def fixtures(ref):
                           quadratic=0.002),
                models=lambda: [ref.Model.load_model(cube_path(5)) @ T.scale(0.5) @ T.rotate_xyz((20, 30, 10)),
                                decal(ref, -1.5, 1.0, -0.5, 1.2, 0.8), floor(ref), decal(ref, -0.5, 1.5, -0.9, 0.6, -0.6)])
+    # the shading functions whose calls are commented out next to general_shading (triangular.py:120-130, 174-263):
+    # what the reference renders with that line swapped in
+    for k, shading in enumerate(('flat', 'gouraud', 'pbr')):
+        yield dict(name=f'g{14 + k}_shading_{shading}', resolution=(120, 160), system='LH', subsystem='OPENGL',
+                   camera=cam_kwargs((0.0, 1.5, 2.9), fovy=60, near=0.1, far=10, backface_culling=True),
+                   debug_camera=cam_kwargs((0.0, 1.5, 2.9), fovy=90, near=0.05, far=20, backface_culling=True),
+                   light=LIGHT, skymap=[0.1, 0.2, 0.3], shading=shading,
+                   models=lambda: [ref.Model(*torus_arrays(64, 32)), diablo(ref, False)])
     yield dict(name='g9_diablo_transformed', resolution=(180, 240), system='LH', subsystem='OPENGL', camera=CAM,
                debug_camera=DCAM, light=dict(LIGHT, position=[-1.5, 2.5, 2.0]),
                models=lambda: [diablo(ref, True, 8) @ T.scale(0.8) @ T.translation((0.1, 0.0, -0.2))
@@ -266,6 +274,28 @@ def dump_model(prefix, m, out):
     return dict(groups=list(m.material_group), mats=mats, clip=bool(m.clip), depth_test=bool(m.depth_test))
 
 
+def render_with_shading(ref, scene, shading):
+    """instrumented render; for shading != 'general' the call of general_shading in rasterize() (triangular.py:127) is
+    replaced by the call the reference keeps commented out on the following lines (128-130)."""
+    if shading == 'general':
+        return refboot.instrumented_render(scene)
+    tri = ref.triangular
+    original = tri.general_shading
+
+    def swapped(face, bar, light, camera, frame, x, y, first_pass):
+        if shading == 'flat':
+            return tri.flat_shading(face, light, frame, x, y)
+        if shading == 'gouraud':
+            return tri.gouraud(face, light, frame, bar, x, y)
+        return tri.pbr(face, light, camera, frame, bar, x, y)
+    tri.general_shading = swapped
+    try:
+        with np.errstate(all='ignore'):
+            return refboot.instrumented_render(scene)
+    finally:
+        tri.general_shading = original
+
+
 def generate(spec, ref):
     t0 = time.time()
     models = spec['models']()
@@ -281,7 +311,7 @@ def generate(spec, ref):
     out = {}
     meta = dict(name=spec['name'], resolution=list(spec['resolution']), system=spec['system'],
                 subsystem=spec['subsystem'], camera=spec['camera'], debug_camera=spec['debug_camera'],
-                light=spec['light'], skymap=spec.get('skymap'), models=[])
+                light=spec['light'], skymap=spec.get('skymap'), shading=spec.get('shading', 'general'), models=[])
     for mi, m in enumerate(models):
         meta['models'].append(dump_model(f"m{mi}_", m, out))
     if sky is not None:
@@ -292,7 +322,7 @@ def generate(spec, ref):
     out['ref_mvp_dbg'] = np.array(dcam.MVP)
     out['ref_viewport'] = np.array(cam.viewport)
     out['ref_planes'] = np.array(cam.frustum_planes)
-    res = refboot.instrumented_render(scene)
+    res = render_with_shading(ref, scene, spec.get('shading', 'general'))
     out['rgb'], out['z'], out['stencil'] = res['rgb'], res['z'], res['stencil']
     out['winner1'], out['winner3'] = res['winner1'], res['winner3']
     meta['n_silhouette'] = [len(m.silhouette) for m in models]

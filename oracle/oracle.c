@@ -209,6 +209,95 @@ static void inv3(const double A[9], double out[9]) {
     }
 }
 
+/* The alternative shading functions whose call sites are commented out in rasterize() (triangular.py:120-130):
+ * flat_shading (174-177), gouraud (180-182), pbr (222-263).  `sv` = the face's SCREEN vertices as rasterize() leaves them
+ * in face.vertices when the shader runs (viewport x, y, linearised z): pbr() uses them as positions.  Values are written
+ * to the float32 frame like the reference does (flat / gouraud: up to 255, the tonemap then wraps in uint8). */
+static inline float clampf_d(double v, double lo, double hi) { return (float)(v < lo ? lo : (v > hi ? hi : v)); }
+static void normalize3f(const float a[3], float out[3]) { /* normalize() on a float32 array (transformation.py:46-49) */
+    float l = sqrtf((a[0] * a[0] + a[1] * a[1]) + a[2] * a[2]);
+    if (l == 0) l = 1;
+    out[0] = a[0] / l; out[1] = a[1] / l; out[2] = a[2] / l;
+}
+static void shade_alt(const ctx_t* C, const face_t* F, const float bar[3], const double sv[3][3], int n_one, float out[3]) {
+    const b2r_light* L = &C->fp->light;
+    const b2r_model_desc* m = F->m;
+    const int mode = C->fp->shading;
+    if (mode == B2R_SHADE_FLAT) {
+        double n[3];
+        unit_normal_world(F, n);
+        double it = dot_seq(n, L->direction, 3);          /* face.unit_normal_world_space @ light.direction */
+        it = it < 0.3 ? 0.3 : (it > 1.0 ? 1.0 : it);     /* NaN stays NaN through both comparisons */
+        out[0] = out[1] = out[2] = (float)(it * 255);
+        return;
+    }
+    double vn[3][3] = {{0}};
+    if (m->normals) for (int c = 0; c < 3; ++c) {
+        int32_t t = F->ni[c]; if (t < 0) t += m->n_normals;
+        for (int k = 0; k < 3; ++k) vn[c][k] = load_real(m->normals, m->normal_dtype, (int64_t)t * 3 + k);
+    }
+    /* bar @ face.normals: float32 @ float32 stays float32 (sgemm), float32 @ float64 is evaluated in float64 */
+    double nb[3];
+    if (m->normal_dtype == B2R_F32) {
+        for (int k = 0; k < 3; ++k) {
+            float acc = n_one ? fmaf(bar[2], (float)vn[2][k], fmaf(bar[0], (float)vn[0][k], bar[1] * (float)vn[1][k]))
+                              : fmaf(bar[2], (float)vn[2][k], fmaf(bar[1], (float)vn[1][k], bar[0] * (float)vn[0][k]));
+            nb[k] = (double)acc;
+        }
+    } else {
+        double b[3] = {(double)bar[0], (double)bar[1], (double)bar[2]};
+        for (int k = 0; k < 3; ++k) nb[k] = mat3(n_one, b, vn[0][k], vn[1][k], vn[2][k]);
+    }
+    if (mode == B2R_SHADE_GOURAUD) {
+        double it = (nb[0] * L->direction[0] + nb[1] * L->direction[1]) + nb[2] * L->direction[2];
+        it = it < 0.0 ? 0.0 : (it > 1.0 ? 1.0 : it);
+        out[0] = out[1] = out[2] = (float)(it * 255);
+        return;
+    }
+    /* pbr (triangular.py:222-263) */
+    const double PI = 3.141592653589793;
+    const double metallic = F->mat->Pm, roughness = F->mat->Pr;
+    double N[3];
+    if (m->normal_dtype == B2R_F32) {
+        float nf[3] = {(float)nb[0], (float)nb[1], (float)nb[2]}, nn[3];
+        normalize3f(nf, nn);
+        N[0] = nn[0]; N[1] = nn[1]; N[2] = nn[2];
+    } else normalize3(nb, N);
+    double b[3] = {(double)bar[0], (double)bar[1], (double)bar[2]}, pos[3];
+    for (int k = 0; k < 3; ++k) pos[k] = mat3(n_one, b, sv[0][k], sv[1][k], sv[2][k]);
+    double vv[3] = {C->view->cam_pos[0] - pos[0], C->view->cam_pos[1] - pos[1], C->view->cam_pos[2] - pos[2]}, Vd[3];
+    normalize3(vv, Vd);
+    const double F0 = 0.04 * (1 - metallic) + 1.0 * metallic;       /* mix(F0, albedo = 1, metallic) */
+    double lv[3] = {L->position[0] - pos[0], L->position[1] - pos[1], L->position[2] - pos[2]}, Ld[3];
+    normalize3(lv, Ld);
+    double hv[3] = {Vd[0] + Ld[0], Vd[1] + Ld[1], Vd[2] + Ld[2]}, Hd[3];
+    normalize3(hv, Hd);
+    const double distance = norm3(lv);
+    const double attenuation = 1.0 / (distance * distance);
+    /* DistributionGGX */
+    const double a = roughness * roughness, a2 = a * a;
+    double NdotH = dot3_nofma(N, Hd); if (NdotH < 0) NdotH = 0;
+    double den = NdotH * NdotH * (a2 - 1.0) + 1.0;
+    den = PI * den * den;
+    const double NDF = a2 / den;
+    /* GeometrySmith */
+    double NdotV = dot3_nofma(N, Vd); if (NdotV < 0) NdotV = 0;
+    double NdotL = dot3_nofma(N, Ld); if (NdotL < 0) NdotL = 0;
+    const double r1 = roughness + 1.0, kk = (r1 * r1) / 8.0;
+    const double G = (NdotL / (NdotL * (1.0 - kk) + kk)) * (NdotV / (NdotV * (1.0 - kk) + kk));
+    double HdotV = dot3_nofma(Hd, Vd); if (HdotV < 0) HdotV = 0;
+    const double Fr = F0 + (1.0 - F0) * pow(1 - HdotV, 5);
+    const double kD = (1.0 - Fr) * (1.0 - metallic);
+    const double specular = (NDF * G * Fr) / (4.0 * NdotV * NdotL + 0.0001);
+    for (int k = 0; k < 3; ++k) {
+        const double radiance = L->color[k] * attenuation;
+        const double Lo = (kD * 1.0 / PI + specular) * radiance * NdotL;
+        double color = 1.0 * F->mat->Ka[k] + Lo;
+        color = color / (color + 1.0);
+        out[k] = (float)pow(color, 1.0 / 2.2);
+    }
+}
+
 /* general_shading (triangular.py:135-171) for one pixel; bar = screen barycentrics (float32), d = 1/w per vertex */
 static void shade_pixel(const ctx_t* C, const face_t* F, const float bar[3], const double d[3], int first_pass,
                         int n_one, float out[3]) {
@@ -457,7 +546,11 @@ static int rasterize(ctx_t* C, const face_t* F, int face_global, int stencil_pas
             const int px = box[0] + (int)(o / ny), py = box[2] + (int)(o % ny);
             const int64_t pix = (int64_t)py * W + px;
             if (!stencil_pass && F->m->depth_test) C->z[pix] = zs[o];
-            shade_pixel(C, F, bars + o * 3, depth, !stencil_pass, pass_one, C->frame + pix * 3);
+            if (C->fp->shading != B2R_SHADE_GENERAL) {
+                const double sv[3][3] = {{v[0][0], v[0][1], zl[0]}, {v[1][0], v[1][1], zl[1]}, {v[2][0], v[2][1], zl[2]}};
+                shade_alt(C, F, bars + o * 3, sv, pass_one, C->frame + pix * 3);
+            } else
+                shade_pixel(C, F, bars + o * 3, depth, !stencil_pass, pass_one, C->frame + pix * 3);
             (stencil_pass ? C->winner3 : C->winner1)[pix] = face_global;
         }
         free(zs);

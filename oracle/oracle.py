@@ -67,7 +67,8 @@ def render_scene(scene, cameras=None, threads=1, planes=True, extra=False):
     cams = list(cameras) if cameras is not None else [scene.camera]
     sky = scene.skybox if isinstance(scene.skybox, CubeMap) else None
     packed = _abi.PackedScene(scene.models, sky)
-    fp = _abi.pack_frame_params(scene.light, scene.resolution, scene._background(), False)
+    fp = _abi.pack_frame_params(scene.light, scene.resolution, scene._background(), False,
+                                shading=getattr(scene, 'shading', 'general'))
     for cam in cams:
         cam.scene = scene
     views = (_abi.View * len(cams))(*[_abi.pack_view(c, scene.debug_camera, scene.system, sky is not None)

@@ -13,7 +13,7 @@ from .constants import SYSTEM
 from .lightning import Lightning
 from .materials import Texture
 
-B2R_ABI_VERSION = 4
+B2R_ABI_VERSION = 5
 B2R_ERR_INDEX = 2
 B2R_F32, B2R_F64 = 0, 1
 B2R_TEX_UNORM, B2R_TEX_SNORM = 0, 1
@@ -32,7 +32,7 @@ class TextureDesc(C.Structure):
 
 class MaterialDesc(C.Structure):
     _fields_ = [("Kd", _d * 3), ("Ks", _d * 3), ("Ns", _d), ("map_Kd", _i), ("map_Ks", _i), ("norm", _i),
-                ("reserved", _i)]
+                ("reserved", _i), ("Pm", _d), ("Pr", _d), ("Ka", _d * 3)]
 
 
 class ModelDesc(C.Structure):
@@ -60,7 +60,7 @@ class LightDesc(C.Structure):
 
 class FrameParams(C.Structure):
     _fields_ = [("light", LightDesc), ("background", C.c_float * 3), ("bg_mode", _i), ("height", _i), ("width", _i),
-                ("row_begin", _i), ("row_end", _i), ("persist_silhouette", _i), ("reserved", _i)]
+                ("row_begin", _i), ("row_end", _i), ("persist_silhouette", _i), ("shading", _i)]
 
 
 class DebugOut(C.Structure):
@@ -134,6 +134,8 @@ class PackedScene:
                 _vec3(mats[si].Kd, mat.Kd)
                 _vec3(mats[si].Ks, mat.Ks)
                 mats[si].Ns = float(mat.Ns)
+                mats[si].Pm, mats[si].Pr = float(getattr(mat, 'Pm', 0.5)), float(getattr(mat, 'Pr', 0.5))
+                _vec3(mats[si].Ka, getattr(mat, 'Ka', (0.3, 0, 0)))
                 mats[si].map_Kd = tex_id(getattr(mat, 'map_Kd', None))
                 mats[si].map_Ks = tex_id(getattr(mat, 'map_Ks', None))
                 mats[si].norm = tex_id(getattr(mat, 'norm', None))
@@ -221,8 +223,14 @@ def pack_light(light) -> LightDesc:
     return ld
 
 
-def pack_frame_params(light, resolution, background, persist_silhouette, band=None) -> FrameParams:
+SHADING = {'general': 0, 'flat': 1, 'gouraud': 2, 'pbr': 3}
+
+
+def pack_frame_params(light, resolution, background, persist_silhouette, band=None, shading='general') -> FrameParams:
     fp = FrameParams()
+    if shading not in SHADING:
+        raise ValueError(f"shading must be one of {sorted(SHADING)}")
+    fp.shading = SHADING[shading]
     fp.light = pack_light(light)
     mode, color = background
     fp.bg_mode = mode

@@ -298,16 +298,18 @@ class DeviceScene:
         arr = np.ascontiguousarray(np.array(pairs, np.int32).reshape(-1, 2))
         _check(self.lib.b2r_scene_set_silhouette(self.handle, arr.ctypes.data, len(arr)))
 
-    def pack(self, cameras, debug_cameras, light, resolution, system, background, persist_silhouette=False, band=None):
+    def pack(self, cameras, debug_cameras, light, resolution, system, background, persist_silhouette=False, band=None,
+             shading='general'):
         """Host-side evaluation of the per-view constants (the reference's NumPy camera maths) -> (fp, views)."""
-        n = len(cameras)
-        fp = pack_frame_params(light, (int(resolution[0]), int(resolution[1])), background, persist_silhouette, band)
+        fp = pack_frame_params(light, (int(resolution[0]), int(resolution[1])), background, persist_silhouette, band,
+                               shading)
         views = _abi.pack_views(cameras, debug_cameras, system, self.has_sky)
         return fp, views
 
     def render(self, cameras, debug_cameras, light, resolution, system, background, persist_silhouette=False,
-               want_debug=False, out=None, band=None):
-        fp, views = self.pack(cameras, debug_cameras, light, resolution, system, background, persist_silhouette, band)
+               want_debug=False, out=None, band=None, shading='general'):
+        fp, views = self.pack(cameras, debug_cameras, light, resolution, system, background, persist_silhouette, band,
+                              shading)
         return self.render_packed(fp, views, want_debug=want_debug, out=out)
 
     def render_packed(self, fp, views, want_debug=False, out=None, wait=True):

@@ -378,6 +378,10 @@ class Scene:
         # extensions (not in the reference)
         self.persist_silhouette = True   # Appendix B-3 behaviour; False = every render starts from an empty set
         self.verbose = True              # print the three per-model lines of core.py:634-636
+        # 'general' = general_shading, what the reference's render() runs.  'flat' / 'gouraud' / 'pbr' = the functions of
+        # triangular.py:174-263 whose calls sit commented out next to it (triangular.py:120-130): what the reference
+        # renders with that line swapped in
+        self.shading = 'general' 
         self._device = None
         self._persist_dirty = False      # the device scene holds a persistent silhouette the host has not seen
 
@@ -432,7 +436,8 @@ class Scene:
         lines = overlay.segments(self.camera, self.debug_camera)  # frustum overlay of core.py:638; [] = nothing drawn
         mode = 'overlay' if lines else (True if debug is not None else ('status' if self.verbose else False))
         frames, info = dev.render([self.camera], [self.debug_camera], self.light, self.resolution, self.system,
-                                  self._background(), persist_silhouette=self.persist_silhouette, want_debug=mode)
+                                  self._background(), persist_silhouette=self.persist_silhouette, want_debug=mode,
+                                  shading=self.shading)
         self._persist_dirty = self._persist_dirty or bool(self.persist_silhouette)
         if isinstance(self.skybox, CubeMap):
             # fill_frame_from_skybox zeroes the translation row of the *cached* camera.lookat in place
@@ -464,7 +469,8 @@ class Scene:
         for cam in cameras + dcams:
             cam.scene = self
         frames, info = dev.render(cameras, dcams, self.light, self.resolution, self.system, self._background(),
-                                  persist_silhouette=False, want_debug=debug is not None, out=out, band=band)
+                                  persist_silhouette=False, want_debug=debug is not None, out=out, band=band,
+                                  shading=self.shading)
         if debug is not None:
             debug.update(info)
         return frames
@@ -484,6 +490,6 @@ class Scene:
         if out is None:
             out = np.empty((len(cameras), int(self.resolution[0]), int(self.resolution[1]), 3), np.uint8)
         fp, views = dev.pack(cameras, dcams, self.light, self.resolution, self.system, self._background(),
-                             persist_silhouette=False, band=band)
+                             persist_silhouette=False, band=band, shading=self.shading)
         frames, info = dev.render_packed(fp, views, out=out, wait=False)
         return _native.PendingFrames(dev.lib, info.get('ticket'), frames, info.get('keep'))

@@ -515,11 +515,15 @@ int b2r_scene_create(const b2r_model_desc* models, int32_t n_models, const b2r_t
             M.norm = src.norm < n_textures ? src.norm : -1;
             M.ns_int = (src.Ns >= 0 && src.Ns <= 4096 && src.Ns == std::floor(src.Ns)) ? (int)src.Ns : -1;
             M.ns_log2 = -1; M.pad = 0;
+            M.Pm = (m.materials && s < m.n_materials) ? src.Pm : 0.5;
+            M.Pr = (m.materials && s < m.n_materials) ? src.Pr : 0.5;
+            for (int k = 0; k < 3; ++k) M.Ka[k] = (m.materials && s < m.n_materials) ? src.Ka[k] : (k == 0 ? 0.3 : 0.0);
             for (int k = 0; k <= 12; ++k) if (M.ns_int == (1 << k)) M.ns_log2 = k;
         }
         const int base_flags = (m.clip ? FS_CLIP : 0) | (m.vertex_dtype == B2R_F32 ? FS_VTX_F32 : 0) |
                                (m.uv ? FS_HAS_UV : 0) | (m.uv && m.uv_dtype == B2R_F32 ? FS_UV_F32 : 0) |
-                               (m.normals ? FS_HAS_NORMALS : 0) | (m.depth_test ? 0 : FS_NO_ZWRITE);
+                               (m.normals ? FS_HAS_NORMALS : 0) | (m.depth_test ? 0 : FS_NO_ZWRITE) |
+                               (m.normals && m.normal_dtype == B2R_F32 ? FS_NRM_F32 : 0);
         auto wrap = [](int idx, int n) { if (idx < 0) idx += n; return (idx < 0 || idx >= n) ? 0 : idx; };
         for (size_t f = 0; f < (size_t)m.n_faces; ++f) {
             const int32_t* r = m.faces + f * 12;
@@ -828,6 +832,8 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
     Fr.n_faces = sc->n_faces;
     Fr.sky_size = sc->sky_size;
     Fr.want_status = want_status;
+    Fr.shading = fp->shading;
+    if (Fr.shading < B2R_SHADE_GENERAL || Fr.shading > B2R_SHADE_PBR) return fail("unknown shading mode");
     Fr.err_flag = nullptr;  // set below, once the read-back region of this call is known
     // stencil counts are only needed under faces -- which, with a Model(depth_test=False) around, is no longer the
     // same as "pixels whose z-buffer was written": count everywhere then
@@ -843,7 +849,7 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
 
     // Chunking.  Device-resident output: as many views per launch as the scratch budget allows.  Host output: small
     // chunks, so that the D2H copy of chunk i (copy stream) overlaps the kernels of chunk i+1 (compute stream).
-    const bool fused = g.fused != 0;
+    const bool fused = g.fused != 0 && fp->shading == B2R_SHADE_GENERAL;   // the alternative shaders live in the shading pass
     const bool want_planes = dbg && (dbg->winner || dbg->stencil);  // debug winner / stencil planes in HBM
     const size_t per_view = (size_t)F * (sizeof(TriRec) + sizeof(TriBox) + sizeof(int)) + (size_t)NV * 33 + (size_t)E * sizeof(QuadRec) + (want_planes ? npx * 6 : 0) +
                             (fused ? 0 : npx * 4) + (want_z ? npx * 8 : 0) + (want_f32 ? npx * 12 : 0);
@@ -1057,8 +1063,12 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
                             S, dviews, Fr, sc->tris.p, sc->quads.p, E, B, T, v0, sv);
                         ++g.launches;
                         stage_mark(g, "raster");
-                        k_shade_packed<<<(unsigned)sv * (unsigned)n_tiles, RASTER_THREADS, 0, st>>>(
-                            S, dviews, Fr, sc->tris.p, B, T, v0, sv);
+                        if (Fr.shading == B2R_SHADE_GENERAL)
+                            k_shade_packed<false><<<(unsigned)sv * (unsigned)n_tiles, RASTER_THREADS, 0, st>>>(
+                                S, dviews, Fr, sc->tris.p, B, T, v0, sv);
+                        else
+                            k_shade_packed<true><<<(unsigned)sv * (unsigned)n_tiles, RASTER_THREADS, 0, st>>>(
+                                S, dviews, Fr, sc->tris.p, B, T, v0, sv);
                         ++g.launches;
                         stage_mark(g, "shade");
                     }

@@ -23,7 +23,8 @@ enum : int {
     FS_UV_F32 = 4,      // uv deltas of tangent_() evaluated in float32
     FS_HAS_UV = 8,
     FS_HAS_NORMALS = 16,
-    FS_NO_ZWRITE = 32,  // Model.depth_test == False: tested against z, never writes it (triangular.py:117)
+    FS_NO_ZWRITE = 32,
+    FS_NRM_F32 = 64,    // Model.normals is float32 (`bar @ face.normals` of gouraud / pbr stays in float32)  // Model.depth_test == False: tested against z, never writes it (triangular.py:117)
 };
 struct FaceStatic {  // 48 B, indices are GLOBAL (scene-level concatenated arrays)
     int v[3];
@@ -52,6 +53,7 @@ struct MaterialDev {
     int ns_int;  // Ns if it is a small non-negative integer (pow by squaring), else -1
     int ns_log2; // k if Ns == 2^k (k squarings), else -1
     int pad;
+    double Pm, Pr, Ka[3];  // metalness, roughness, ambient colour: pbr() only (materials.py:47-49)
 };
 
 struct TextureDev {
@@ -95,6 +97,8 @@ struct FrameDev {
     int sky_size;
     int want_status;
     int full_stencil;  // stencil counts are wanted for every pixel (debug plane), not only under faces
+    int shading;       // B2R_SHADE_*: general_shading, or one of the alternatives of triangular.py:174-263
+    int pad2;
     int* err_flag;     // mapped pinned host word: set to 1 when a texture lookup falls outside its map (IndexError)
 };
 

@@ -890,6 +890,20 @@ __device__ __forceinline__ unsigned tonemap_pack(const float c[3]) {
     return packed;
 }
 
+// The same with x ** 0.8 evaluated in float64 and rounded once: flat_shading / gouraud write values up to 255 into the
+// frame, so the tonemapped value reaches ~21 000 before the uint8 cast wraps it -- two float32 ulp of the fast form above
+// would move ~1 % of those pixels across an integer.
+__device__ __forceinline__ unsigned tonemap_pack_wide(const float c[3]) {
+    unsigned packed = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float p = c[k] > 0.0f ? (float)pow((double)c[k], 0.8) : 0.0f;
+        const float v = __fmul_rn(p, 255.0f);
+        packed |= ((unsigned)(int)v & 0xffu) << (8 * k);
+    }
+    return packed;
+}
+
 // Small transfers done by the SMs instead of the copy engines.  A cudaMemcpyAsync / cudaMemsetAsync on the compute
 // stream queues behind whatever large transfer the same copy engine is busy with (the frames of the previous batch on
 // their way to the host): measured, that stalls the whole pipeline by ~0.8 ms per 16-frame batch.
@@ -908,6 +922,110 @@ __global__ void k_frame_consts(FrameDev Fr, int* __restrict__ counters, int n_co
 }
 
 __device__ __forceinline__ float clip01(double v) { return (float)(v < 0.05 ? 0.05 : (v > 1.0 ? 1.0 : v)); }
+
+// The flat normal of a face in the vertex dtype: Face.unit_normal_world_space (core.py:127-130)
+__device__ __forceinline__ void face_unit_normal(const ShadeStatic& fs, double fn[3]) {
+    const double (*wp)[3] = fs.wp;
+    if (fs.flags & FS_VTX_F32) {
+        float a[3], b[3], c[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { a[k] = (float)wp[0][k]; b[k] = (float)wp[1][k]; c[k] = (float)wp[2][k]; }
+        const float e0x = __fsub_rn(b[0], a[0]), e0y = __fsub_rn(b[1], a[1]), e0z = __fsub_rn(b[2], a[2]);
+        const float e1x = __fsub_rn(c[0], a[0]), e1y = __fsub_rn(c[1], a[1]), e1z = __fsub_rn(c[2], a[2]);
+        const float cx = __fsub_rn(__fmul_rn(e0y, e1z), __fmul_rn(e0z, e1y));
+        const float cy = __fsub_rn(__fmul_rn(e0z, e1x), __fmul_rn(e0x, e1z));
+        const float cz = __fsub_rn(__fmul_rn(e0x, e1y), __fmul_rn(e0y, e1x));
+        float l = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz)));
+        if (l == 0.0f) l = 1.0f;
+        fn[0] = (double)__fdiv_rn(cx, l); fn[1] = (double)__fdiv_rn(cy, l); fn[2] = (double)__fdiv_rn(cz, l);
+    } else {
+        const double e0x = wp[1][0] - wp[0][0], e0y = wp[1][1] - wp[0][1], e0z = wp[1][2] - wp[0][2];
+        const double e1x = wp[2][0] - wp[0][0], e1y = wp[2][1] - wp[0][1], e1z = wp[2][2] - wp[0][2];
+        fn[0] = e0y * e1z - e0z * e1y; fn[1] = e0z * e1x - e0x * e1z; fn[2] = e0x * e1y - e0y * e1x;
+        normalize3(fn);
+    }
+}
+
+// flat_shading / gouraud / pbr (triangular.py:174-263), the shading functions the reference keeps commented out at the
+// call site of rasterize() (triangular.py:127-130).  They receive the SCREEN barycentrics and -- pbr -- the face's
+// screen-space vertices (viewport x, y, linearised z) as positions, exactly what the reference hands them there.
+__device__ __noinline__ void shade_alt_pixel(const SceneDev& S, const ViewDev& V, const LightDev& L, const TriRec& r, int face,
+                                             int px, int py, int shading, float out[3]) {
+    const ShadeStatic& fs = S.shade[face];
+    const MaterialDev& M = S.mats[fs.material];
+    if (shading == B2R_SHADE_FLAT) {
+        double fn[3];
+        face_unit_normal(fs, fn);
+        double it = seq3(fn[0], fn[1], fn[2], L.direction[0], L.direction[1], L.direction[2]);
+        it = it < 0.3 ? 0.3 : (it > 1.0 ? 1.0 : it);
+        out[0] = out[1] = out[2] = (float)(it * 255.0);
+        return;
+    }
+    float bu, bv, bw;
+    tri_bary(r, px, py, bu, bv, bw);
+    const double (*vn)[3] = fs.vn;
+    double nb[3];   // bar @ face.normals
+    if (fs.flags & FS_NRM_F32) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            nb[k] = (double)__fmaf_rn(bw, (float)vn[2][k], __fmaf_rn(bv, (float)vn[1][k], __fmul_rn(bu, (float)vn[0][k])));
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) nb[k] = seq3((double)bu, (double)bv, (double)bw, vn[0][k], vn[1][k], vn[2][k]);
+    }
+    if (shading == B2R_SHADE_GOURAUD) {
+        double it = (nb[0] * L.direction[0] + nb[1] * L.direction[1]) + nb[2] * L.direction[2];
+        it = it < 0.0 ? 0.0 : (it > 1.0 ? 1.0 : it);
+        out[0] = out[1] = out[2] = (float)(it * 255.0);
+        return;
+    }
+    // pbr
+    const double PI = 3.141592653589793;
+    const double metallic = M.Pm, roughness = M.Pr;
+    double N[3] = {nb[0], nb[1], nb[2]};
+    if (fs.flags & FS_NRM_F32) {   // normalize() on the float32 array
+        const float nx = (float)nb[0], ny = (float)nb[1], nz = (float)nb[2];
+        float l = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(ny, ny)), __fmul_rn(nz, nz)));
+        if (l == 0.0f) l = 1.0f;
+        N[0] = (double)__fdiv_rn(nx, l); N[1] = (double)__fdiv_rn(ny, l); N[2] = (double)__fdiv_rn(nz, l);
+    } else normalize3(N);
+    const double b0 = (double)bu, b1 = (double)bv, b2 = (double)bw;
+    const double sx[3] = {r.ax, r.ax + r.v0x, r.ax + r.v1x}, sy[3] = {r.ay, r.ay + r.v0y, r.ay + r.v1y};
+    const double pos[3] = {seq3(b0, b1, b2, sx[0], sx[1], sx[2]), seq3(b0, b1, b2, sy[0], sy[1], sy[2]),
+                           seq3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2])};
+    double Vd[3] = {V.cam_pos[0] - pos[0], V.cam_pos[1] - pos[1], V.cam_pos[2] - pos[2]};
+    normalize3(Vd);
+    const double F0 = 0.04 * (1.0 - metallic) + 1.0 * metallic;
+    double lv[3] = {L.position[0] - pos[0], L.position[1] - pos[1], L.position[2] - pos[2]};
+    const double distance = norm3(lv[0], lv[1], lv[2]);
+    double Ld[3] = {lv[0], lv[1], lv[2]};
+    normalize3(Ld);
+    double Hd[3] = {Vd[0] + Ld[0], Vd[1] + Ld[1], Vd[2] + Ld[2]};
+    normalize3(Hd);
+    const double attenuation = 1.0 / (distance * distance);
+    const double a = roughness * roughness, a2 = a * a;
+    double NdotH = dot3_plain(N, Hd); NdotH = NdotH < 0 ? 0 : NdotH;
+    double den = NdotH * NdotH * (a2 - 1.0) + 1.0;
+    den = PI * den * den;
+    const double NDF = a2 / den;
+    double NdotV = dot3_plain(N, Vd); NdotV = NdotV < 0 ? 0 : NdotV;
+    double NdotL = dot3_plain(N, Ld); NdotL = NdotL < 0 ? 0 : NdotL;
+    const double r1 = roughness + 1.0, kk = (r1 * r1) / 8.0;
+    const double G = (NdotL / (NdotL * (1.0 - kk) + kk)) * (NdotV / (NdotV * (1.0 - kk) + kk));
+    double HdotV = dot3_plain(Hd, Vd); HdotV = HdotV < 0 ? 0 : HdotV;
+    const double om = 1.0 - HdotV, om2 = om * om;
+    const double Fr = F0 + (1.0 - F0) * (om2 * om2 * om);
+    const double kD = (1.0 - Fr) * (1.0 - metallic);
+    const double specular = (NDF * G * Fr) / (4.0 * NdotV * NdotL + 0.0001);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double radiance = L.color[k] * attenuation;
+        const double Lo = (kD * 1.0 / PI + specular) * radiance * NdotL;
+        double color = M.Ka[k] + Lo;
+        color = color / (color + 1.0);
+        out[k] = (float)pow(color, 1.0 / 2.2);
+    }
+}
 
 // general_shading for one pixel (triangular.py:135-171)
 // Returns false when a texture lookup fell outside its map (the reference raises IndexError there).
@@ -1001,24 +1119,7 @@ __device__ bool shade_face_pixel(const SceneDev& S, const ViewDev& V, const Ligh
         for (int k = 0; k < 3; ++k) N[k] = seq3(P[0], P[1], P[2], vn[0][k], vn[1][k], vn[2][k]);
     } else {  // flat normal in the vertex dtype (core.py:186-187)
         double fn[3];
-        if (fs.flags & FS_VTX_F32) {
-            float a[3], b[3], c[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { a[k] = (float)wp[0][k]; b[k] = (float)wp[1][k]; c[k] = (float)wp[2][k]; }
-            const float e0x = __fsub_rn(b[0], a[0]), e0y = __fsub_rn(b[1], a[1]), e0z = __fsub_rn(b[2], a[2]);
-            const float e1x = __fsub_rn(c[0], a[0]), e1y = __fsub_rn(c[1], a[1]), e1z = __fsub_rn(c[2], a[2]);
-            const float cx = __fsub_rn(__fmul_rn(e0y, e1z), __fmul_rn(e0z, e1y));
-            const float cy = __fsub_rn(__fmul_rn(e0z, e1x), __fmul_rn(e0x, e1z));
-            const float cz = __fsub_rn(__fmul_rn(e0x, e1y), __fmul_rn(e0y, e1x));
-            float l = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz)));
-            if (l == 0.0f) l = 1.0f;
-            fn[0] = (double)__fdiv_rn(cx, l); fn[1] = (double)__fdiv_rn(cy, l); fn[2] = (double)__fdiv_rn(cz, l);
-        } else {
-            const double e0x = wp[1][0] - wp[0][0], e0y = wp[1][1] - wp[0][1], e0z = wp[1][2] - wp[0][2];
-            const double e1x = wp[2][0] - wp[0][0], e1y = wp[2][1] - wp[0][1], e1z = wp[2][2] - wp[0][2];
-            fn[0] = e0y * e1z - e0z * e1y; fn[1] = e0z * e1x - e0x * e1z; fn[2] = e0x * e1y - e0y * e1x;
-            normalize3(fn);
-        }
+        face_unit_normal(fs, fn);
 #pragma unroll
         for (int k = 0; k < 3; ++k) N[k] = seq3(P[0], P[1], P[2], fn[k], fn[k], fn[k]);
     }
@@ -1612,6 +1713,9 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
 
 // Shading pass of the unfused path: one CTA of 128 threads per 32x32 tile (a warp per row), reading the packed winner
 // word k_tile<false> left behind.  Tiles whose lists are empty were never written: they are recognised here.
+// ALT = true: one of the alternative shading functions (Fr.shading != B2R_SHADE_GENERAL); a separate instantiation so that
+// the production kernel carries none of their code or stack.
+template <bool ALT>
 __global__ void __launch_bounds__(RASTER_THREADS, B2R_SHADE_MINB)
 k_shade_packed(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec* __restrict__ tris, BinDev B,
                TileOut O, int view0, int n_sub) {
@@ -1653,7 +1757,8 @@ k_shade_packed(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const
         if (px < X1) {
             if (w != PACKED_NONE) {
                 const int face = (int)(w & ~PACKED_LIT);
-                if (!shade_face_pixel(S, V, Fr.light, vtris[face], face, px, py, (w & PACKED_LIT) != 0, c)) *Fr.err_flag = 1;
+                if (ALT) shade_alt_pixel(S, V, Fr.light, vtris[face], face, px, py, Fr.shading, c);
+                else if (!shade_face_pixel(S, V, Fr.light, vtris[face], face, px, py, (w & PACKED_LIT) != 0, c)) *Fr.err_flag = 1;
             } else if (Fr.bg_mode == B2R_BG_CUBEMAP) {
                 skybox_pixel(S, V, Fr.sky_size, px, py, c);
             } else {
@@ -1662,7 +1767,7 @@ k_shade_packed(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const
             }
             if (O.f32) { float* o = O.f32 + g * 3; o[0] = c[0]; o[1] = c[1]; o[2] = c[2]; }
         }
-        const unsigned packed = const_bg ? bg : tonemap_pack(c);
+        const unsigned packed = const_bg ? bg : (ALT ? tonemap_pack_wide(c) : tonemap_pack(c));
         store_row(Fr, O.rgb, view, X0, py, packed, px < X1, lane);
     }
 }

@@ -68,6 +68,7 @@ def load(name, resolution=None):
                       resolution=tuple(resolution or meta['resolution']), system=getattr(b2r.SYSTEM, meta['system']),
                       subsystem=getattr(b2r.SUBSYSTEM, meta['subsystem']), skymap=skymap)
     scene.verbose = False
+    scene.shading = meta.get('shading', 'general')
     for m in models:
         scene.add_model(m)
     expected = {k: data[k] for k in ('rgb', 'z', 'stencil', 'winner1', 'winner3', 'ref_mvp', 'ref_mvp_dbg',

@@ -309,3 +309,18 @@ def test_overlay_fast_exit_never_hides_a_segment():
         else:
             assert len(overlay.segments(cam, dcam)) == len(overlay.segments_full(cam, dcam))
     assert fast_hits >= 40
+
+
+def test_scene_shading_modes_reach_the_abi():
+    """Scene.shading: 'general' = what the reference's render() runs; 'flat' / 'gouraud' / 'pbr' = the
+    calls commented out at triangular.py:128-130; anything else is refused."""
+    light = b2r.Light((2, 3, 3))
+    for name, code in _abi.SHADING.items():
+        fp = _abi.pack_frame_params(light, (4, 4), (_abi.B2R_BG_COLOR, (0, 0, 0)), False, shading=name)
+        assert fp.shading == code
+    with pytest.raises(ValueError):
+        _abi.pack_frame_params(light, (4, 4), (_abi.B2R_BG_COLOR, (0, 0, 0)), False, shading='toon')
+    m = b2r.Model(np.zeros((3, 4), np.float32), None, None, np.zeros((1, 3, 4), np.int32))
+    packed = _abi.PackedScene([m])
+    mat = packed.models[0].materials[0]
+    assert (mat.Pm, mat.Pr) == (0.5, 0.5) and [mat.Ka[k] for k in range(3)] == [0.3, 0.0, 0.0]   # materials.py:47-49
