@@ -66,6 +66,9 @@ struct Context {
     int aux_host = 2, aux_dev = 3;  // how many auxiliary streams the sub-chunks rotate over
     int init_tri_cap = 0, init_quad_cap = 0;  // B2R_TRI_CAP / B2R_QUAD_CAP: first per-view list capacities (tests of the grow path)
     int bin_blocks = 0, bin_share = 64;  // k_bin grid (0 = 2 per SM) and the most warps that share one quad
+    bool clip_elide = true;       // B2R_CLIP_ELIDE=0: keep the per-pixel clip test on every (clip-flagged face, tile) pair (A/B)
+    bool debug_skip_bg = false;   // B2R_DEBUG_SKIP_BG=1: debug stencil plane from the production (skip-background) stencil path
+    bool shade_f32 = true;        // B2R_SHADE_F64=1: the all-float64 shading kernel instead of float32 lighting
     int fused = 0;                // B2R_FUSED: 0 = k_tile<false> + k_shade_packed (one packed word per pixel between them; production),
                                   // 1 = k_tile<true> (shading inside the tile kernel; measured slower, kept for A/B)
     // pinned staging ring for the per-view constants: a pageable source would make cudaMemcpyAsync synchronise the
@@ -158,6 +161,7 @@ struct b2r_scene {
     DevBuf<FaceStatic> faces;
     DevBuf<int4> face_vf;
     DevBuf<ShadeStatic> shade;
+    DevBuf<ShadeLite> shade_lite;
     DevBuf<MaterialDev> mats;
     DevBuf<TextureDev> tex;
     std::vector<uchar4*> tex_data;
@@ -199,7 +203,7 @@ struct b2r_scene {
 
     SceneDev dev() const {
         SceneDev S;
-        S.pos = pos.p; S.uv = uv.p; S.nrm = nrm.p; S.faces = faces.p; S.face_vf = face_vf.p; S.shade = shade.p; S.mats = mats.p; S.tex = tex.p; S.sky = sky.p;
+        S.pos = pos.p; S.uv = uv.p; S.nrm = nrm.p; S.faces = faces.p; S.face_vf = face_vf.p; S.shade = shade.p; S.shade_lite = shade_lite.p; S.mats = mats.p; S.tex = tex.p; S.sky = sky.p;
         S.edge_v = edge_v.p; S.edge_ptr = edge_ptr.p; S.edge_inc = edge_inc.p;
         S.n_faces = n_faces; S.n_edges = n_edges;
         return S;
@@ -264,6 +268,9 @@ int b2r_init(int device) {
     if (const char* a = std::getenv("B2R_BIN_SHARE")) g.bin_share = std::max(1, std::atoi(a));
     if (const char* a = std::getenv("B2R_PIPE")) g.pipe_views = std::max(1, std::atoi(a));
     if (const char* a = std::getenv("B2R_FUSED")) g.fused = std::atoi(a) != 0;
+    if (const char* a = std::getenv("B2R_CLIP_ELIDE")) g.clip_elide = std::atoi(a) != 0;
+    if (const char* a = std::getenv("B2R_DEBUG_SKIP_BG")) g.debug_skip_bg = std::atoi(a) != 0;
+    if (const char* a = std::getenv("B2R_SHADE_F64")) g.shade_f32 = std::atoi(a) == 0;
     if (const char* a = std::getenv("B2R_AUX_DEV")) g.aux_dev = std::min(Context::N_AUX, std::max(1, std::atoi(a)));
     g.device = device;
     g.ready = true;
@@ -508,7 +515,7 @@ int b2r_scene_create(const b2r_model_desc* models, int32_t n_models, const b2r_t
             b2r_material src;
             if (m.materials && s < m.n_materials) src = m.materials[s];
             else { std::memset(&src, 0, sizeof(src)); src.Kd[0] = src.Kd[1] = src.Kd[2] = 0.8; src.Ks[0] = src.Ks[1] = src.Ks[2] = 1; src.Ns = 64; src.map_Kd = src.map_Ks = src.norm = -1; }
-            for (int k = 0; k < 3; ++k) { M.Kd[k] = src.Kd[k]; M.Ks255[k] = src.Ks[k] * 255; }
+            for (int k = 0; k < 3; ++k) { M.Kd[k] = src.Kd[k]; M.Ks255[k] = src.Ks[k] * 255; M.Kdf[k] = (float)M.Kd[k]; M.Ks255f[k] = (float)M.Ks255[k]; }
             M.Ns = src.Ns;
             M.map_Kd = src.map_Kd < n_textures ? src.map_Kd : -1;
             M.map_Ks = src.map_Ks < n_textures ? src.map_Ks : -1;
@@ -595,9 +602,44 @@ int b2r_scene_create(const b2r_model_desc* models, int32_t n_models, const b2r_t
         R.material = F.material;
         R.flags = F.flags;
     }
+    // float32 lighting records: tangent_() constants in the dtype the reference evaluates them in (core.py:205-213),
+    // the flat unit normal (core.py:127-130, 186-187) in place of missing vertex normals
+    std::vector<ShadeLite> lite(nf);
+    for (size_t f = 0; f < nf; ++f) {
+        const ShadeStatic& R = shade[f];
+        ShadeLite& L = lite[f];
+        std::memset(&L, 0, sizeof(L));
+        for (int c = 0; c < 3; ++c) {
+            L.uu[c] = R.uu[c]; L.vv[c] = R.vv[c];
+            for (int k = 0; k < 3; ++k) { L.wp[c][k] = (float)R.wp[c][k]; L.vn[c][k] = (float)R.vn[c][k]; }
+        }
+        for (int k = 0; k < 3; ++k) {
+            if (R.flags & FS_VTX_F32) {
+                L.r0[k] = (float)R.wp[1][k] - (float)R.wp[0][k]; L.r1[k] = (float)R.wp[2][k] - (float)R.wp[0][k];
+            } else {
+                L.r0[k] = (float)(R.wp[1][k] - R.wp[0][k]); L.r1[k] = (float)(R.wp[2][k] - R.wp[0][k]);
+            }
+        }
+        if (R.flags & FS_UV_F32) {
+            L.du1 = (float)R.uu[1] - (float)R.uu[0]; L.du2 = (float)R.uu[2] - (float)R.uu[0];
+            L.dv1 = (float)R.vv[1] - (float)R.vv[0]; L.dv2 = (float)R.vv[2] - (float)R.vv[0];
+        } else {
+            L.du1 = (float)(R.uu[1] - R.uu[0]); L.du2 = (float)(R.uu[2] - R.uu[0]);
+            L.dv1 = (float)(R.vv[1] - R.vv[0]); L.dv2 = (float)(R.vv[2] - R.vv[0]);
+        }
+        if (!(R.flags & FS_HAS_NORMALS)) {
+            double e0[3], e1[3], n[3];
+            for (int k = 0; k < 3; ++k) { e0[k] = R.wp[1][k] - R.wp[0][k]; e1[k] = R.wp[2][k] - R.wp[0][k]; }
+            n[0] = e0[1] * e1[2] - e0[2] * e1[1]; n[1] = e0[2] * e1[0] - e0[0] * e1[2]; n[2] = e0[0] * e1[1] - e0[1] * e1[0];
+            double l = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+            if (l == 0) l = 1;
+            for (int c = 0; c < 3; ++c) for (int k = 0; k < 3; ++k) L.vn[c][k] = (float)(n[k] / l);
+        }
+        L.material = R.material; L.flags = R.flags;
+    }
     std::vector<int4> face_vf(nf);
     for (size_t f = 0; f < nf; ++f) face_vf[f] = make_int4(faces[f].v[0], faces[f].v[1], faces[f].v[2], faces[f].flags);
-    UP(pos, pos); UP(uv, uv); UP(nrm, nrm); UP(faces, faces); UP(face_vf, face_vf); UP(shade, shade); UP(mats, mats);
+    UP(pos, pos); UP(uv, uv); UP(nrm, nrm); UP(faces, faces); UP(face_vf, face_vf); UP(shade, shade); UP(shade_lite, lite); UP(mats, mats);
     UP(edge_v, edge_v); UP(edge_ptr, edge_ptr); UP(edge_inc, edge_inc); UP(edge_model, edge_model);
     // textures: uint8 RGB -> RGBX so that one texel is one aligned 32-bit load
     std::vector<TextureDev> tex(std::max(1, n_textures));
@@ -651,7 +693,7 @@ int b2r_scene_destroy(b2r_scene* sc) {
         if (sc->sticky_slot >= 0) { for (int k = 0; k < STICKY_INTS; ++k) g.sticky[STICKY_INTS * sc->sticky_slot + k] = 0; g.sticky_free.push_back(sc->sticky_slot); }
     }
     for (int i = 0; i < 2; ++i) if (sc->rgb_copied[i]) cudaEventDestroy(sc->rgb_copied[i]);
-    sc->pos.release(); sc->uv.release(); sc->nrm.release(); sc->faces.release(); sc->face_vf.release(); sc->shade.release(); sc->mats.release(); sc->tex.release();
+    sc->pos.release(); sc->uv.release(); sc->nrm.release(); sc->faces.release(); sc->face_vf.release(); sc->shade.release(); sc->shade_lite.release(); sc->mats.release(); sc->tex.release();
     for (uchar4* d : sc->tex_data) cudaFree(d);
     sc->sky.release(); sc->edge_v.release(); sc->edge_ptr.release(); sc->edge_inc.release(); sc->edge_model.release();
     sc->sil_state.release(); sc->facing.release(); sc->sil.release(); sc->counters.release(); sc->views.release();
@@ -762,6 +804,8 @@ static void make_view(const b2r_view& v, bool with_sky, ViewDev& D) {
     std::memcpy(D.viewport, v.viewport, sizeof(D.viewport));
     std::memcpy(D.planes, v.planes, sizeof(D.planes));
     std::memcpy(D.cam_pos, v.cam_pos, sizeof(D.cam_pos));
+    for (int k = 0; k < 3; ++k) D.cam_posf[k] = (float)v.cam_pos[k];
+    D.pad_f = 0.f;
     D.zl_num = 2 * v.near_ * v.far_;  // core.py:226-228
     D.zl_sum = v.far_ + v.near_;
     D.zl_diff = v.far_ - v.near_;
@@ -823,6 +867,14 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
     Fr.light.constant = fp->light.constant; Fr.light.linear = fp->light.linear; Fr.light.quadratic = fp->light.quadratic;
     Fr.light.spot_cos_outer = fp->light.spot_cos_outer; Fr.light.spot_cos_inner = fp->light.spot_cos_inner;
     Fr.light.type = fp->light.type;
+    for (int k = 0; k < 3; ++k) {
+        Fr.lightf.position[k] = (float)fp->light.position[k]; Fr.lightf.direction[k] = (float)fp->light.direction[k];
+        Fr.lightf.color[k] = (float)fp->light.color[k]; Fr.lightf.ambient[k] = (float)fp->light.ambient[k];
+    }
+    Fr.lightf.specular_strength = (float)fp->light.specular_strength;
+    Fr.lightf.constant = (float)fp->light.constant; Fr.lightf.linear = (float)fp->light.linear; Fr.lightf.quadratic = (float)fp->light.quadratic;
+    Fr.lightf.spot_cos_outer = (float)fp->light.spot_cos_outer;
+    Fr.lightf.spot_inv_range = (float)(1.0 / (fp->light.spot_cos_inner - fp->light.spot_cos_outer));
     for (int k = 0; k < 3; ++k) Fr.background[k] = fp->background[k];
     Fr.bg_mode = fp->bg_mode;
     Fr.H = H; Fr.W = W; Fr.row_begin = row_begin; Fr.row_end = row_end;
@@ -837,7 +889,9 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
     Fr.err_flag = nullptr;  // set below, once the read-back region of this call is known
     // stencil counts are only needed under faces -- which, with a Model(depth_test=False) around, is no longer the
     // same as "pixels whose z-buffer was written": count everywhere then
-    Fr.full_stencil = ((dbg && dbg->stencil) || sc->has_no_zwrite) ? 1 : 0;
+    // B2R_DEBUG_SKIP_BG=1 (tests): hand out the stencil plane of the PRODUCTION path -- counts kept under faces only --
+    // so that its shortcuts are compared with the oracle count by count on the covered pixels
+    Fr.full_stencil = ((dbg && dbg->stencil && !g.debug_skip_bg) || sc->has_no_zwrite) ? 1 : 0;
     const int n_tiles = Fr.tiles_x * Fr.tiles_y;
     const int F = sc->n_faces, NV = std::max(1, sc->n_vertices);
     // Silhouette / quad records: far fewer edges are extruded at once than the mesh has (diablo 1 381 of 7 533, the 1M-
@@ -962,7 +1016,7 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
         CK(sc->quad_list.reserve((size_t)VB * sc->quad_cap));
         CK(sc->pair_list.reserve((size_t)VB * sc->quad_cap));
         CK(sc->overflow.reserve((size_t)VB * 2));
-        CK(sc->tile_order.reserve((size_t)VB * n_tiles));
+        CK(sc->tile_order.reserve((size_t)VB * n_tiles + VB));   // + active-tile count per view
         if (want_planes) {
             CK(sc->winner.reserve((size_t)VB * npx));
             CK(sc->stencil.reserve((size_t)VB * npx));
@@ -987,7 +1041,7 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
             B.tri_list = sc->tri_list.p; B.quad_list = sc->quad_list.p;
             B.tri_cap = sc->tri_cap; B.quad_cap = sc->quad_cap; B.overflow = sc->overflow.p;
             B.share_cap = g.bin_share;
-            B.order = sc->tile_order.p;
+            B.order = sc->tile_order.p; B.n_active = sc->tile_order.p + (size_t)VB * n_tiles;
             B.pair_list = sc->pair_list.p; B.pair_count = sc->tile_counts.p + (size_t)VB * n_tiles * 2;
             B.huge_count = B.pair_count + VB; B.huge_list = B.huge_count + VB;
             int* const coop_count = B.huge_list + (size_t)VB * BIN_HUGE_CAP;
@@ -1044,6 +1098,11 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
                 k_order<<<pv, 1024, 0, g.stream>>>(Fr, B, p0);
                 k_bin<true><<<dim3(bin_blocks, pv), 256, 0, g.stream>>>(Fr, sc->boxes.p, sc->quads.p, sc->counters.p, E, B, p0);
                 g.launches += 4;
+                if (g.clip_elide && F > 0) {
+                    k_clip_elide<<<dim3((n_tiles + 127) / 128, ELIDE_MAX_FACES, pv), 128, 0, g.stream>>>(
+                        Fr, sc->boxes.p, sc->tris.p, S.pos, S.face_vf, dviews, B, p0);
+                    ++g.launches;
+                }
                 stage_mark(g, "bin");
                 const int sub = (serial || pv <= want_sub) ? pv : std::max(1, want_sub);
                 const bool multi = !serial && (sub < pv || pipe < nv);   // tile / shading leave the main stream
@@ -1054,20 +1113,23 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
                     cudaStream_t st = multi ? g.aux[ai] : g.stream;
                     if (multi) { CK(cudaStreamWaitEvent(st, g.setup_done, 0)); aux_used[ai] = true; }
                     if (fused) {
-                        k_tile<true><<<(unsigned)sv * (unsigned)n_tiles, RASTER_THREADS, 0, st>>>(
+                        k_tile<true><<<dim3((unsigned)sv, (unsigned)n_tiles), RASTER_THREADS, 0, st>>>(
                             S, dviews, Fr, sc->tris.p, sc->quads.p, E, B, T, v0, sv);
                         ++g.launches;
                         stage_mark(g, "tile");
                     } else {
-                        k_tile<false><<<(unsigned)sv * (unsigned)n_tiles, RASTER_THREADS, 0, st>>>(
+                        k_tile<false><<<dim3((unsigned)sv, (unsigned)n_tiles), RASTER_THREADS, 0, st>>>(
                             S, dviews, Fr, sc->tris.p, sc->quads.p, E, B, T, v0, sv);
                         ++g.launches;
                         stage_mark(g, "raster");
-                        if (Fr.shading == B2R_SHADE_GENERAL)
-                            k_shade_packed<false><<<(unsigned)sv * (unsigned)n_tiles, RASTER_THREADS, 0, st>>>(
+                        if (Fr.shading == B2R_SHADE_GENERAL && g.shade_f32 && !want_f32)
+                            k_shade_packed<SHADE_F32><<<dim3((unsigned)sv, (unsigned)n_tiles), RASTER_THREADS, 0, st>>>(
+                                S, dviews, Fr, sc->tris.p, B, T, v0, sv);
+                        else if (Fr.shading == B2R_SHADE_GENERAL)
+                            k_shade_packed<SHADE_F64><<<dim3((unsigned)sv, (unsigned)n_tiles), RASTER_THREADS, 0, st>>>(
                                 S, dviews, Fr, sc->tris.p, B, T, v0, sv);
                         else
-                            k_shade_packed<true><<<(unsigned)sv * (unsigned)n_tiles, RASTER_THREADS, 0, st>>>(
+                            k_shade_packed<SHADE_ALT><<<dim3((unsigned)sv, (unsigned)n_tiles), RASTER_THREADS, 0, st>>>(
                                 S, dviews, Fr, sc->tris.p, B, T, v0, sv);
                         ++g.launches;
                         stage_mark(g, "shade");

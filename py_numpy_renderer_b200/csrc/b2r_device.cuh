@@ -45,6 +45,21 @@ struct ShadeStatic {  // 208 B
     int flags;            // FS_*
 };
 
+// The same face for the float32 lighting path (k_shade_packed<SHADE_F32>): texture addressing stays float64 (a texel
+// index is a discontinuous function of u, v), everything that only feeds the lighting sum is float32, and the
+// per-face constants of tangent_() (edge vectors, uv deltas: core.py:205-213) are evaluated once at scene creation in
+// the dtype the reference evaluates them in.
+struct __align__(16) ShadeLite {  // 176 B
+    double uu[3], vv[3];
+    float wp[3][3];            // world xyz of the corners
+    float vn[3][3];            // vertex normals; the flat unit normal three times when the model has none
+    float r0[3], r1[3];        // b - a, c - a
+    float du1, du2, dv1, dv2;  // uv deltas
+    int material;
+    int flags;
+    int pad[2];
+};
+
 struct MaterialDev {
     double Kd[3];
     double Ks255[3];  // Ks * 255 (core.py:152)
@@ -54,6 +69,7 @@ struct MaterialDev {
     int ns_log2; // k if Ns == 2^k (k squarings), else -1
     int pad;
     double Pm, Pr, Ka[3];  // metalness, roughness, ambient colour: pbr() only (materials.py:47-49)
+    float Kdf[3], Ks255f[3];  // float32 copies for the float32 lighting path
 };
 
 struct TextureDev {
@@ -74,6 +90,7 @@ struct SkyTri {  // one of the two full-screen triangles of fill_frame_from_skyb
 struct ViewDev {
     double mvp[16], mvp_dbg[16], viewport[16], planes[24];
     double cam_pos[3];
+    float cam_posf[3], pad_f;
     double zl_num, zl_sum, zl_diff;  // 2*near*far, far+near, far-near  (core.py:226-228)
     int system, backface;
     SkyTri sky[2];
@@ -86,8 +103,14 @@ struct LightDev {
     int pad;
 };
 
+struct LightLite {  // float32 copy of the light for the float32 lighting path
+    float position[3], direction[3], color[3], ambient[3];
+    float specular_strength, constant, linear, quadratic, spot_cos_outer, spot_inv_range;
+};
+
 struct FrameDev {
     LightDev light;
+    LightLite lightf;
     float background[3];
     int bg_mode;
     int H, W;

@@ -22,6 +22,14 @@
 #pragma once
 #include "b2r_device.cuh"
 
+// tuning switches of the tile kernel (A/B builds: tools/build_variant.sh <name> -DB2R_...=0)
+#ifndef B2R_ROWDIFF
+#define B2R_ROWDIFF 1      // stencil: row-level depth classification + per-row difference arrays (two atomics per row span)
+#endif
+#ifndef B2R_ROWTAB
+#define B2R_ROWTAB 1       // stencil items find their row through a shared-memory table instead of a shuffle bisection
+#endif
+
 namespace b2r {
 
 // The reference's float32 texel from the uint8 source (core.py:96-104): f32(u8/255) or f32(u8/255*2-1), float64
@@ -48,6 +56,7 @@ struct SceneDev {
     const FaceStatic* faces; // (F)
     const int4* face_vf;     // (F) v0, v1, v2, FS_* flags: what the per-view set-up needs of a face, 16 B
     const ShadeStatic* shade; // (F) gathered per-face shading inputs
+    const ShadeLite* shade_lite; // (F) the same for the float32 lighting path
     const MaterialDev* mats;
     const TextureDev* tex;
     const uchar4* sky;       // (6,S,S) RGBX
@@ -148,15 +157,19 @@ __device__ __forceinline__ void load_clip_coords(const SceneDev& S, const ViewDe
 }
 
 // covered & unclipped test of one pixel, the predicate `Bi` of triangular.py:78-87
-__device__ __forceinline__ bool tri_pixel_in(const TriRec& r, const double* cc, int px, int py, float& bu, float& bv,
-                                             float& bw) {
+__device__ __forceinline__ bool tri_pixel_in(const TriRec& r, const double* cc, bool need_clip, int px, int py,
+                                             float& bu, float& bv, float& bw) {
     bool in = tri_bary(r, px, py, bu, bv, bw);
-    if (in && (r.flags & TR_NEEDS_CLIP)) {
+    if (in && need_clip) {
         double P[3];
         persp_bary(r, bu, bv, bw, (r.flags & TR_BOX_ONE) != 0, P);
         in = pixel_unclipped(cc, P, (r.flags & TR_BOX_ONE) != 0);
     }
     return in;
+}
+__device__ __forceinline__ bool tri_pixel_in(const TriRec& r, const double* cc, int px, int py, float& bu, float& bv,
+                                             float& bw) {
+    return tri_pixel_in(r, cc, (r.flags & TR_NEEDS_CLIP) != 0, px, py, bu, bv, bw);
 }
 
 constexpr int COV_SERIAL_MAX = 128;  // boxes up to this many pixels are counted by the owning thread
@@ -465,7 +478,119 @@ struct BinDev {
     int* huge_count;  // (views) faces whose box holds more than BIN_HUGE tiles: the fill pass spreads them over the grid
     int* huge_list;   // (views, BIN_HUGE_CAP)
     int* order;       // (views, n_tiles) tiles sorted by estimated cost class, heaviest first (raster launch order)
+    int* n_active;    // (views) how many leading entries of `order` hold tiles the tile kernel has work for
 };
+
+// Can any pixel of the rectangle [x0,x1] x [y0,y1] (inclusive) pass the float32 coverage test of `tri_bary`?
+// The computed barycentrics are, up to float32 rounding, affine functions of the pixel: b_i = t_i(p) + eps_i with
+//   t_v = (d11*D20 - d01*D21)*inv,  t_w = (d00*D21 - d01*D20)*inv,  t_u = 1 - t_v - t_w   (real arithmetic on the
+// float32 constants of the record, D2k = (p-a).v_k) and |eps| bounded by the operation-by-operation error analysis
+// below (4 roundings at 2^-24 each, generously doubled).  An affine function attains its extremes over a rectangle
+// at the corners, so if some t_i stays below -E_i at all four corners, b_i < 0 for every pixel: nothing is covered.
+// Only used for big boxes (one screen-filling triangle against the tiles on the far side of its edges).
+constexpr int BIG_BOX_PX = 256;
+__device__ __forceinline__ bool tri_misses_rect(const TriRec& r, int x0, int x1, int y0, int y1) {
+    const double d00 = r.d00, d01 = r.d01, d11 = r.d11, inv = r.inv;
+    const double u32 = 5.9604644775390625e-8;  // 2^-24
+    double tmax[3] = {-1e300, -1e300, -1e300}, amax_v = 0, amax_w = 0, gv = 0, gw = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const double v2x = (double)((c & 1) ? x1 : x0) - r.ax, v2y = (double)((c & 2) ? y1 : y0) - r.ay;
+        const double D20 = v2x * r.v0x + v2y * r.v0y, D21 = v2x * r.v1x + v2y * r.v1y;
+        const double tv = (d11 * D20 - d01 * D21) * inv, tw = (d00 * D21 - d01 * D20) * inv, tu = 1.0 - tv - tw;
+        if (!(tv == tv) || !(tw == tw)) return false;
+        tmax[0] = fmax(tmax[0], tu); tmax[1] = fmax(tmax[1], tv); tmax[2] = fmax(tmax[2], tw);
+        amax_v = fmax(amax_v, fabs(tv)); amax_w = fmax(amax_w, fabs(tw));
+        gv = fmax(gv, (fabs(d11 * D20) + fabs(d01 * D21)) * fabs(inv));
+        gw = fmax(gw, (fabs(d00 * D21) + fabs(d01 * D20)) * fabs(inv));
+    }
+    const double Ev = 8.0 * u32 * (gv + amax_v) + 1e-30, Ew = 8.0 * u32 * (gw + amax_w) + 1e-30;
+    const double Eu = Ev + Ew + 8.0 * u32 * (1.0 + amax_v + amax_w);
+    return tmax[0] < -Eu || tmax[1] < -Ev || tmax[2] < -Ew;
+}
+
+// Does EVERY pixel of the rectangle [x0,x1] x [y0,y1] (inclusive) that `tri_bary` covers pass the per-pixel clip test of
+// triangular.py:80-87 (`pixel_unclipped`) in both frusta?  Then the test -- three float64 divisions and 24 FMAs per
+// pixel -- is skipped for this (triangle, tile): the floor of the headline scene reaches far outside the frustum, so
+// TR_NEEDS_CLIP is set on its two faces, yet every tile in the interior of the screen passes.
+// Why the corners decide: the reference tests -q.w < q.k < q.w (k = x, y, z) on q = P @ clip with P_i = b_i d_i / s,
+// s = sum b_j d_j.  With s > 0 this is F = sum_i b_i d_i (clip_i.w -+ clip_i.k) > 0, LINEAR in the barycentrics, and
+// the barycentrics are affine in the pixel up to the float32 rounding bounded as in tri_misses_rect (|eps_i| <= E_i).
+// An affine function attains its minimum over the rectangle at a corner, so if at all four corners s and the six F of
+// each frustum exceed the worst-case perturbation sum_i (E_i + float64 rounding) |d_i| (|clip_i.w| + |clip_i.k|), four
+// times over, every computed comparison of every pixel in the rectangle comes out true.  NaN / inf anywhere -> false.
+__device__ __noinline__ bool tri_rect_unclipped(const TriRec& r, const double* __restrict__ cc, int x0, int x1, int y0, int y1) {
+    const double d00 = r.d00, d01 = r.d01, d11 = r.d11, inv = r.inv;
+    const double u32 = 5.9604644775390625e-8, u64 = 1.1102230246251565e-16;  // 2^-24, 2^-53
+    double amax[3] = {0, 0, 0}, gv = 0, gw = 0, smin = 1e300, fmn[2] = {1e300, 1e300};
+    bool bad = false;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {   // four independent chains: unrolled so that they overlap in the float64 pipe
+        const double v2x = (double)((c & 1) ? x1 : x0) - r.ax, v2y = (double)((c & 2) ? y1 : y0) - r.ay;
+        const double D20 = v2x * r.v0x + v2y * r.v0y, D21 = v2x * r.v1x + v2y * r.v1y;
+        const double tv = (d11 * D20 - d01 * D21) * inv, tw = (d00 * D21 - d01 * D20) * inv, tu = 1.0 - tv - tw;
+        bad = bad || !(fabs(tv) < 1e30) || !(fabs(tw) < 1e30);
+        amax[0] = fmax(amax[0], fabs(tu)); amax[1] = fmax(amax[1], fabs(tv)); amax[2] = fmax(amax[2], fabs(tw));
+        gv = fmax(gv, (fabs(d11 * D20) + fabs(d01 * D21)) * fabs(inv));
+        gw = fmax(gw, (fabs(d00 * D21) + fabs(d01 * D20)) * fabs(inv));
+        const double e0 = tu * r.d[0], e1 = tv * r.d[1], e2 = tw * r.d[2];
+        const double sc = e0 + e1 + e2;
+        bad = bad || !(sc > 0);
+        smin = fmin(smin, sc);
+#pragma unroll
+        for (int cam = 0; cam < 2; ++cam) {
+            const double* q = cc + cam * 12;
+            const double W = e0 * q[3] + e1 * q[7] + e2 * q[11];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double K = e0 * q[k] + e1 * q[4 + k] + e2 * q[8 + k];
+                const double lo = W - K, hi = W + K;
+                bad = bad || !(lo > 0) || !(hi > 0);
+                fmn[cam] = fmin(fmn[cam], fmin(lo, hi));
+            }
+        }
+    }
+    const double Ev = 8.0 * u32 * (gv + amax[1]) + 1e-30, Ew = 8.0 * u32 * (gw + amax[2]) + 1e-30;
+    const double E[3] = {Ev + Ew + 8.0 * u32 * (1.0 + amax[1] + amax[2]), Ev, Ew};
+    double sb = 0, fb[2] = {0, 0};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double ci = (E[i] + 16.0 * u64 * (amax[i] + E[i])) * fabs(r.d[i]);
+        sb += ci;
+#pragma unroll
+        for (int cam = 0; cam < 2; ++cam) {
+            const double* q = cc + cam * 12 + i * 4;
+            fb[cam] += ci * (fabs(q[3]) + fmax(fmax(fabs(q[0]), fabs(q[1])), fabs(q[2])));
+        }
+    }
+    return !bad && smin > 4.0 * sb && fmn[0] > 4.0 * fb[0] && fmn[1] > 4.0 * fb[1];
+}
+
+// The clip test of a (face, tile) pair decided once, by the thread of the binning fill pass that inserts the pair:
+// true when every pixel of the tile that the face can cover passes `pixel_unclipped` (tri_rect_unclipped above), so the
+// tile kernel runs that pair without the per-pixel test.  (Deciding it inside the tile kernel was measured first: one
+// lane per CTA on a chain of ~600 dependent float64 operations while the other 127 threads wait cost more than the
+// test saves.  Here every lane of the fill pass decides its own tile.)
+__device__ __noinline__ bool face_tile_unclipped(const FrameDev& Fr, const TriRec* __restrict__ vtris, const double4* __restrict__ pos,
+                                                 const int4* __restrict__ face_vf, const ViewDev& V, int face, int tx, int ty) {
+    const TriRec r = vtris[face];
+    const int X0 = tx * TILE_W, Y0 = ty * TILE_H;
+    const int x0 = max((int)r.bx0, X0), x1 = min((int)r.bx1, min(X0 + TILE_W, Fr.W));
+    const int y0 = max((int)r.by0, max(Y0, Fr.row_begin)), y1 = min((int)r.by1, min(min(Y0 + TILE_H, Fr.H), Fr.row_end));
+    if ((x1 - x0) * (y1 - y0) < BIG_BOX_PX || x1 <= x0) return false;   // not worth a test: few pixels either way
+    const int4 fv = face_vf[face];
+    double cc[CLIP_DOUBLES];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double4 p = pos[i == 0 ? fv.x : (i == 1 ? fv.y : fv.z)];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {   // the staged form of k_tile (tile_tris): same operations, same order
+            cc[i * 4 + k] = fma(p.w, V.mvp[12 + k], fma(p.z, V.mvp[8 + k], fma(p.y, V.mvp[4 + k], p.x * V.mvp[k])));
+            cc[12 + i * 4 + k] = fma(p.w, V.mvp_dbg[12 + k], fma(p.z, V.mvp_dbg[8 + k], fma(p.y, V.mvp_dbg[4 + k], p.x * V.mvp_dbg[k])));
+        }
+    }
+    return tri_rect_unclipped(r, cc, x0, x1 - 1, y0, y1 - 1);
+}
 
 // One warp per primitive slot: lanes stride over the tiles of the primitive's box.
 // Triangles: one THREAD per face; a box touching at most BIN_SMALL tiles is binned by its own thread, bigger ones
@@ -731,8 +856,9 @@ __global__ void k_scan(FrameDev Fr, BinDev B, int* __restrict__ host_flags, int*
 // long, nearly empty tail.  Tiles are therefore bucketed by an estimate of their cost (list lengths) and the raster
 // grid walks the buckets heaviest first, the views of the sub-chunk interleaved.  One CTA per view.
 constexpr int ORDER_CLASSES = 6;
-__device__ __forceinline__ int tile_cost_class(int n_tri, int n_quad) {
-    const int cost = 4 * n_quad + n_tri;
+__device__ __forceinline__ int tile_cost_class(int n_tri, int n_quad, bool full_stencil) {
+    // a tile without triangles has no z-buffer: unless the stencil plane itself is wanted, the tile kernel skips it
+    const int cost = (n_tri == 0 && !full_stencil) ? 0 : 4 * n_quad + n_tri;
     return cost >= 1024 ? 0 : cost >= 256 ? 1 : cost >= 64 ? 2 : cost >= 16 ? 3 : cost > 0 ? 4 : 5;
 }
 __global__ void k_order(FrameDev Fr, BinDev B, int view0) {
@@ -745,50 +871,56 @@ __global__ void k_order(FrameDev Fr, BinDev B, int view0) {
     if (threadIdx.x < ORDER_CLASSES) cnt[threadIdx.x] = 0;
     __syncthreads();
     for (int t = threadIdx.x; t < n_tiles; t += blockDim.x)
-        atomicAdd(&cnt[tile_cost_class(tri_off[t + 1] - tri_off[t], quad_off[t + 1] - quad_off[t])], 1);
+        atomicAdd(&cnt[tile_cost_class(tri_off[t + 1] - tri_off[t], quad_off[t + 1] - quad_off[t], Fr.full_stencil != 0)], 1);
     __syncthreads();
     if (threadIdx.x == 0) {
         int run = 0;
         for (int c = 0; c < ORDER_CLASSES; ++c) { base[c] = run; run += cnt[c]; cnt[c] = 0; }
+        const bool lists_ok = (B.overflow[view * 2] | B.overflow[view * 2 + 1]) == 0;
+        B.n_active[view] = lists_ok ? base[ORDER_CLASSES - 1] : 0;
     }
     __syncthreads();
     for (int t = threadIdx.x; t < n_tiles; t += blockDim.x) {
-        const int c = tile_cost_class(tri_off[t + 1] - tri_off[t], quad_off[t + 1] - quad_off[t]);
+        const int c = tile_cost_class(tri_off[t + 1] - tri_off[t], quad_off[t + 1] - quad_off[t], Fr.full_stencil != 0);
         order[base[c] + atomicAdd(&cnt[c], 1)] = t;
     }
+}
+
+// Clip decision of the (screen-filling face, tile) pairs, once per pair, after the lists are filled: one thread per
+// (view, noted face, tile of its box).  Where `face_tile_unclipped` proves that no pixel of the tile can fail the clip
+// test, the thread finds the pair's entry in the tile's list and clears its TRI_CLIP_BIT: the tile kernel then runs the
+// pair without the per-pixel test (three float64 divisions and 24 FMAs per pixel; the floor of the headline scene
+// alone is half a million such pixels per view).  A kernel of its own so that the fill pass keeps its 32 registers;
+// measured alternatives: inside the tile kernel (one lane per CTA on a ~600-operation dependent chain: slower than no
+// elision), inside the fill pass (128 registers, a quarter of the occupancy: fill pass 0.06 -> 0.32 ms).
+constexpr int ELIDE_MAX_FACES = 8;   // noted faces per view that get the treatment (the rest keep the per-pixel test)
+__global__ void __launch_bounds__(128) k_clip_elide(FrameDev Fr, const TriBox* __restrict__ boxes, const TriRec* __restrict__ tris,
+                                                    const double4* __restrict__ pos, const int4* __restrict__ face_vf,
+                                                    const ViewDev* __restrict__ views, BinDev B, int view0) {
+    const int view = blockIdx.z + view0, h = blockIdx.y;
+    if (h >= min(B.huge_count[view], BIN_HUGE_CAP)) return;
+    if (B.overflow[view * 2] | B.overflow[view * 2 + 1]) return;
+    const int n_tiles = Fr.tiles_x * Fr.tiles_y;
+    const int face = B.huge_list[view * BIN_HUGE_CAP + h];
+    const TriBox r = boxes[(size_t)view * Fr.n_faces + face];
+    if (!(r.flags & TR_NEEDS_CLIP)) return;
+    const int bx0 = r.bx0, bx1 = r.bx1, by0 = max((int)r.by0, Fr.row_begin), by1 = min((int)r.by1, Fr.row_end);
+    const int tx0 = bx0 / TILE_W, ty0 = by0 / TILE_H, tw = (bx1 - 1) / TILE_W - tx0 + 1;
+    const int nt = tw * ((by1 - 1) / TILE_H - ty0 + 1);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nt) return;
+    const int tx = tx0 + i % tw, ty = ty0 + i / tw;
+    if (!face_tile_unclipped(Fr, tris + (size_t)view * Fr.n_faces, pos, face_vf, views[view], face, tx, ty)) return;
+    const int t = (ty - Fr.tile_row0) * Fr.tiles_x + tx;
+    const int* tri_off = B.tri_off + (size_t)view * (n_tiles + 1);
+    int* tri_list = B.tri_list + (size_t)view * B.tri_cap;
+    for (int k = tri_off[t]; k < tri_off[t + 1]; ++k)
+        if (tri_list[k] == (face | TRI_CLIP_BIT)) { tri_list[k] = face; break; }
 }
 
 // =====================================================================================================================
 // tile raster: z -> stencil -> winner, all in shared memory
 // =====================================================================================================================
-// Can any pixel of the rectangle [x0,x1] x [y0,y1] (inclusive) pass the float32 coverage test of `tri_bary`?
-// The computed barycentrics are, up to float32 rounding, affine functions of the pixel: b_i = t_i(p) + eps_i with
-//   t_v = (d11*D20 - d01*D21)*inv,  t_w = (d00*D21 - d01*D20)*inv,  t_u = 1 - t_v - t_w   (real arithmetic on the
-// float32 constants of the record, D2k = (p-a).v_k) and |eps| bounded by the operation-by-operation error analysis
-// below (4 roundings at 2^-24 each, generously doubled).  An affine function attains its extremes over a rectangle
-// at the corners, so if some t_i stays below -E_i at all four corners, b_i < 0 for every pixel: nothing is covered.
-// Only used for big boxes (one screen-filling triangle against the tiles on the far side of its edges).
-constexpr int BIG_BOX_PX = 256;
-__device__ __forceinline__ bool tri_misses_rect(const TriRec& r, int x0, int x1, int y0, int y1) {
-    const double d00 = r.d00, d01 = r.d01, d11 = r.d11, inv = r.inv;
-    const double u32 = 5.9604644775390625e-8;  // 2^-24
-    double tmax[3] = {-1e300, -1e300, -1e300}, amax_v = 0, amax_w = 0, gv = 0, gw = 0;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const double v2x = (double)((c & 1) ? x1 : x0) - r.ax, v2y = (double)((c & 2) ? y1 : y0) - r.ay;
-        const double D20 = v2x * r.v0x + v2y * r.v0y, D21 = v2x * r.v1x + v2y * r.v1y;
-        const double tv = (d11 * D20 - d01 * D21) * inv, tw = (d00 * D21 - d01 * D20) * inv, tu = 1.0 - tv - tw;
-        if (!(tv == tv) || !(tw == tw)) return false;
-        tmax[0] = fmax(tmax[0], tu); tmax[1] = fmax(tmax[1], tv); tmax[2] = fmax(tmax[2], tw);
-        amax_v = fmax(amax_v, fabs(tv)); amax_w = fmax(amax_w, fabs(tw));
-        gv = fmax(gv, (fabs(d11 * D20) + fabs(d01 * D21)) * fabs(inv));
-        gw = fmax(gw, (fabs(d00 * D21) + fabs(d01 * D20)) * fabs(inv));
-    }
-    const double Ev = 8.0 * u32 * (gv + amax_v) + 1e-30, Ew = 8.0 * u32 * (gw + amax_w) + 1e-30;
-    const double Eu = Ev + Ew + 8.0 * u32 * (1.0 + amax_v + amax_w);
-    return tmax[0] < -Eu || tmax[1] < -Ev || tmax[2] < -Ew;
-}
-
 // Relaxed atomic store to shared memory: several lanes / warps may name the same pixel as "last improver" in the same
 // round (the verification pass sorts it out), so the store must be an atomic access to be defined behaviour.  Costs the
 // same as a plain STS.
@@ -1160,6 +1292,154 @@ __device__ bool shade_face_pixel(const SceneDev& S, const ViewDev& V, const Ligh
     return tex_ok;
 }
 
+// ---- float32 lighting (production) ---------------------------------------------------------------------------------
+// general_shading with the float64 arithmetic of the reference kept where a result is discontinuous in its inputs --
+// coverage, perspective weights and texel addressing -- and float32 for the lighting sum itself: north_star's bar for
+// shaded RGB is 1 LSB on >= 99.9 % of the pixels; float32 lighting moves the tonemapped value by ~1e-4 LSB, i.e. it flips
+// the truncated uint8 of about one channel in 10^4 (measured per fixture in profiles/), never by more than one.  The
+// float64 form above stays available (B2R_SHADE_F64=1) and is what the fused / debug paths use.
+__device__ __forceinline__ float rsqrt_fast(float s) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(s)); return y; }
+__device__ __forceinline__ float rcp_fast(float s) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(s)); return y; }
+__device__ __forceinline__ float dot3f(const float a[3], const float b[3]) { return fmaf(a[2], b[2], fmaf(a[1], b[1], a[0] * b[0])); }
+__device__ __forceinline__ void norm3f(float v[3]) {
+    const float s = dot3f(v, v);
+    if (s > 0.f) { const float r = rsqrt_fast(s); v[0] *= r; v[1] *= r; v[2] *= r; }
+}
+__device__ __forceinline__ float clip01f(float v) { return fminf(fmaxf(v, 0.05f), 1.0f); }
+// texel address of Face.get_UV (core.py:138-143) in float64, the texel itself undecoded
+__device__ __forceinline__ bool texel_raw(const TextureDev& T, const double P[3], const double uu[3], const double vv[3], uchar4& t) {
+    double cu = gemv3(P[0], P[1], P[2], uu[0], uu[1], uu[2]);
+    double cv = gemv3(P[0], P[1], P[2], vv[0], vv[1], vv[2]);
+    cu = cu > 1.0 ? 1.0 : cu;
+    double rv = 1.0 - cv;
+    rv = rv > 1.0 ? 1.0 : rv;
+    int col = (int)(cu * (double)(T.width - 1));
+    int row = (int)(rv * (double)(T.height - 1));
+    if (col < 0) col += T.width;
+    if (row < 0) row += T.height;
+    bool ok = (cu == cu) && (rv == rv);
+    if (col < 0 || col >= T.width) { col = 0; ok = false; }
+    if (row < 0 || row >= T.height) { row = 0; ok = false; }
+    t = __ldg(T.texels + (size_t)row * T.width + col);
+    return ok;
+}
+__device__ __forceinline__ void texel_decode_f(const uchar4 t, int snorm, float out[3]) {
+    const float a = snorm ? (2.0f / 255.0f) : (1.0f / 255.0f), b = snorm ? -1.0f : 0.0f;
+    out[0] = fmaf((float)t.x, a, b); out[1] = fmaf((float)t.y, a, b); out[2] = fmaf((float)t.z, a, b);
+}
+
+__device__ bool shade_face_pixel_f32(const SceneDev& S, const ViewDev& V, const LightLite& L, int light_type, const TriRec& r,
+                                     int face, int px, int py, bool lit, float out[3]) {
+    bool tex_ok = true;
+    const ShadeLite& fs = S.shade_lite[face];
+    const MaterialDev& M = S.mats[fs.material];
+    float bu, bv, bw;
+    tri_bary(r, px, py, bu, bv, bw);
+    double P[3];
+    {   // Face.screen_perspective (core.py:155-160) in float64: it feeds the texel addresses
+        const double b0 = (double)bu, b1 = (double)bv, b2 = (double)bw;
+        const double inv_w = 1.0 / gemv3(b0, b1, b2, r.d[0], r.d[1], r.d[2]);
+        P[0] = b0 * r.d[0] * inv_w; P[1] = b1 * r.d[1] * inv_w; P[2] = b2 * r.d[2] * inv_w;
+    }
+    const float p0 = (float)P[0], p1 = (float)P[1], p2 = (float)P[2];
+    float albedo[3];
+    if (M.map_Kd >= 0) {
+        const TextureDev& T = S.tex[M.map_Kd];
+        uchar4 t;
+        tex_ok = texel_raw(T, P, fs.uu, fs.vv, t) && tex_ok;
+        texel_decode_f(t, T.decode, albedo);
+    } else {
+        albedo[0] = M.Kdf[0]; albedo[1] = M.Kdf[1]; albedo[2] = M.Kdf[2];
+    }
+    float frag[3], dl[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        frag[k] = fmaf(p2, fs.wp[2][k], fmaf(p1, fs.wp[1][k], p0 * fs.wp[0][k]));
+        dl[k] = L.position[k] - frag[k];
+    }
+    const float d2 = dot3f(dl, dl);
+    const float rd = d2 > 0.f ? rsqrt_fast(d2) : 0.f;
+    const float dist = d2 * rd;
+    const float att = rcp_fast(fmaf(dist, fmaf(L.quadratic, dist, L.linear), L.constant));  // core.py:517-524
+    if (!lit) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) out[k] = clip01f(att * L.ambient[k] * albedo[k]);
+        return tex_ok;
+    }
+    // Face.get_normals (core.py:175-189)
+    float N[3];
+    if (M.norm >= 0) {
+        const TextureDev& T = S.tex[M.norm];
+        uchar4 tq;
+        tex_ok = texel_raw(T, P, fs.uu, fs.vv, tq) && tex_ok;
+        float t[3];
+        texel_decode_f(tq, T.decode, t);
+        if (T.tangent) {  // Face.tangent_ (core.py:191-224)
+            float n[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) n[k] = fmaf(p2, fs.vn[2][k], fmaf(p1, fs.vn[1][k], p0 * fs.vn[0][k]));
+            norm3f(n);
+            const float* r0 = fs.r0;
+            const float* r1 = fs.r1;
+            // inv(A) @ (d1, d2, 0) = (d1 * (r1 x n) + d2 * (n x r0)) / det(A), normalised right away: only the sign of det survives
+            const float c1[3] = {fmaf(r1[1], n[2], -(r1[2] * n[1])), fmaf(r1[2], n[0], -(r1[0] * n[2])), fmaf(r1[0], n[1], -(r1[1] * n[0]))};
+            const float c2[3] = {fmaf(n[1], r0[2], -(n[2] * r0[1])), fmaf(n[2], r0[0], -(n[0] * r0[2])), fmaf(n[0], r0[1], -(n[1] * r0[0]))};
+            const float det = dot3f(r0, c1);
+            const float sg = det < 0.f ? -1.0f : 1.0f;
+            float ti[3], tj[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                ti[q] = sg * fmaf(fs.du1, c1[q], fs.du2 * c2[q]);
+                tj[q] = sg * fmaf(fs.dv1, c1[q], fs.dv2 * c2[q]);
+            }
+            norm3f(ti); norm3f(tj);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) N[q] = fmaf(n[q], t[2], fmaf(tj[q], t[1], ti[q] * t[0]));
+        } else {
+            N[0] = t[0]; N[1] = t[1]; N[2] = t[2];
+        }
+    } else {  // interpolated vertex normals, or the flat normal (stored three times: core.py:186-187)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) N[k] = fmaf(p2, fs.vn[2][k], fmaf(p1, fs.vn[1][k], p0 * fs.vn[0][k]));
+    }
+    norm3f(N);
+    float Ld[3];
+    if (light_type == B2R_LIGHT_DIRECTIONAL) { Ld[0] = L.direction[0]; Ld[1] = L.direction[1]; Ld[2] = L.direction[2]; }
+    else { Ld[0] = dl[0] * rd; Ld[1] = dl[1] * rd; Ld[2] = dl[2] * rd; }
+    float Vd[3] = {V.cam_posf[0] - frag[0], V.cam_posf[1] - frag[1], V.cam_posf[2] - frag[2]};
+    norm3f(Vd);
+    if (light_type == B2R_LIGHT_SPOT) {  // triangular.py:157-161, core.py:497-515
+        float x = (dot3f(L.direction, Ld) - L.spot_cos_outer) * L.spot_inv_range;
+        x = fminf(fmaxf(x, 0.f), 1.f);
+        const float sm = x * x * fmaf(-2.0f, x, 3.0f);
+        albedo[0] *= sm; albedo[1] *= sm; albedo[2] *= sm;
+    }
+    float spec_light[3];
+    if (M.map_Ks >= 0) {  // core.py:145-153: float32 texel * 255
+        const TextureDev& T = S.tex[M.map_Ks];
+        uchar4 tq;
+        tex_ok = texel_raw(T, P, fs.uu, fs.vv, tq) && tex_ok;
+        float t[3];
+        texel_decode_f(tq, T.decode, t);
+        spec_light[0] = spec_light[1] = spec_light[2] = t[0] * 255.0f;
+    } else {
+        spec_light[0] = M.Ks255f[0]; spec_light[1] = M.Ks255f[1]; spec_light[2] = M.Ks255f[2];
+    }
+    float Hd[3] = {Ld[0] + Vd[0], Ld[1] + Vd[1], Ld[2] + Vd[2]};
+    norm3f(Hd);
+    const float nh = fmaxf(dot3f(N, Hd), 0.f);
+    float sr;
+    if (M.ns_log2 == 6) { sr = nh * nh; sr *= sr; sr *= sr; sr *= sr; sr *= sr; sr *= sr; }
+    else if (M.ns_log2 >= 0) { sr = nh; for (int i = 0; i < M.ns_log2; ++i) sr *= sr; }
+    else sr = (float)pow_ns((double)nh, M);
+    const float nl = dot3f(N, Ld);
+    const float ss = sr * L.specular_strength;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        out[k] = clip01f(att * albedo[k] * fmaf(L.color[k], fmaf(ss, spec_light[k], nl), L.ambient[k]));
+    return tex_ok;
+}
+
 // cube_map.py:63-101 for one background pixel; returns false when neither screen triangle covers it
 __device__ __forceinline__ bool skybox_pixel(const SceneDev& S, const ViewDev& V, int sky_size, int px, int py, float out[3]) {
 #pragma unroll
@@ -1254,11 +1534,12 @@ struct TileSmem {
     int next_quad;
     int uniform;
     int need_full;
+    int use_diff;
 };
 // One pass over the tile's triangle list.  PASS 1: zbuf + last improver, PASS 3: full winner pass (+ status bits).
 template <int PASS>
-__device__ __noinline__ void tile_tris(TileSmem& sm, const SceneDev& S, const ViewDev& V,
-                                       const TriRec* __restrict__ vtris, const int* __restrict__ tri_list,
+__device__ __noinline__ void tile_tris(TileSmem& sm, const double4* __restrict__ pos, const int4* __restrict__ face_vf,
+                                       const ViewDev& V, const TriRec* __restrict__ vtris, const int* __restrict__ tri_list,
                                        int t_beg, int t_end, int X0, int Y0, int X1, int Yb0, int Y1, bool rh,
                                        uint8_t* status_view) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1290,7 +1571,8 @@ __device__ __noinline__ void tile_tris(TileSmem& sm, const SceneDev& S, const Vi
             const int slot = sm.clip_slot[t];
             if (slot < 0) continue;
             const int cam = j / 12, vtx = (j % 12) >> 2, k = j & 3;
-            const double4 p = S.pos[S.faces[sm.face[t]].v[vtx]];
+            const int4 fv = face_vf[sm.face[t]];
+            const double4 p = pos[vtx == 0 ? fv.x : (vtx == 1 ? fv.y : fv.z)];
             const double* M = cam ? V.mvp_dbg : V.mvp;
             sm.clip[slot][j] = fma(p.w, M[12 + k], fma(p.z, M[8 + k], fma(p.y, M[4 + k], p.x * M[k])));
         }
@@ -1332,7 +1614,8 @@ __device__ __noinline__ void tile_tris(TileSmem& sm, const SceneDev& S, const Vi
             const double* cc = sm.clip[slot < 0 ? 0 : slot];
             float bu, bv, bw;
             if (PASS == 1) B2R_STAT(12, 1);
-            if (!tri_pixel_in(r, cc, px, py, bu, bv, bw)) continue;
+            if (PASS == 1 && slot >= 0) B2R_STAT(10, 1);
+            if (!tri_pixel_in(r, cc, slot >= 0, px, py, bu, bv, bw)) continue;
             if (PASS == 1) B2R_STAT(13, 1);
             const double b0 = (double)bu, b1 = (double)bv, b2 = (double)bw;
             const double z = (r.flags & TR_COV_ONE) ? seq3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2])
@@ -1397,10 +1680,14 @@ __global__ void __launch_bounds__(RASTER_THREADS, FUSED ? B2R_TILE_MINB : B2R_TI
 k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec* __restrict__ tris,
        const QuadRec* __restrict__ quads, int quad_stride, BinDev B, TileOut O, int view0, int n_sub) {
     __shared__ TileSmem sm;
-    const int view = (int)(blockIdx.x % (unsigned)n_sub) + view0;
+    // grid (views of the sub-chunk, tile rank): x runs fastest, so the views stay interleaved within a cost class
+    const int view = (int)blockIdx.x + view0;
+    // ranks past the active tiles of this view (about half the screen in the headline scene): nothing to do, and
+    // k_shade_packed recognises those tiles itself -- leave before any other work
+    if (!FUSED && !(O.winner || O.stencil || O.z) && (int)blockIdx.y >= B.n_active[view]) return;
     const ViewDev& V = views[view];
     const int n_tiles = Fr.tiles_x * Fr.tiles_y;
-    const int tile = B.order[(size_t)view * n_tiles + blockIdx.x / (unsigned)n_sub];
+    const int tile = B.order[(size_t)view * n_tiles + blockIdx.y];
     const int tx = tile % Fr.tiles_x, ty = tile / Fr.tiles_x + Fr.tile_row0;
     const int X0 = tx * TILE_W, Y0 = ty * TILE_H;
     const int X1 = min(X0 + TILE_W, Fr.W), Y1 = min(min(Y0 + TILE_H, Fr.H), Fr.row_end);
@@ -1444,26 +1731,53 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
     if (threadIdx.x == 0) { B2R_STAT(11, 1); B2R_STAT(14, q_end - q_beg); B2R_STAT(15, t_end - t_beg); }
     const unsigned long long z_init = zkey(z_bg);
     for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) { sm.z[i] = z_init; sm.id[i] = -1; sm.st[i] = 0; }
-    if (threadIdx.x == 0) { sm.uniform = 0; sm.need_full = 0; sm.next_quad = 0; }
+    if (threadIdx.x == 0) { sm.uniform = 0; sm.need_full = 0; sm.next_quad = 0; sm.use_diff = 0; }
     const TriRec* vtris = tris + (size_t)view * Fr.n_faces;
     const int* tri_list = B.tri_list + (size_t)view * B.tri_cap;
     uint8_t* status_view = O.status ? O.status + (size_t)view * Fr.n_faces : nullptr;
 
-    tile_tris<1>(sm, S, V, vtris, tri_list, t_beg, t_end, X0, Y0, X1, Yb0, Y1, rh, status_view);
+    tile_tris<1>(sm, S.pos, S.face_vf, V, vtris, tri_list, t_beg, t_end, X0, Y0, X1, Yb0, Y1, rh, status_view);
     __syncthreads();
 
     // ---- stencil (triangular.py:341-368) ----
     const bool skip_bg = !Fr.full_stencil;
+#if B2R_ROWTAB
+    // the staging area of the triangle rounds is idle during the stencil phase: 1 KB of it per warp holds the row table
+    static_assert(sizeof(sm.tri) >= RASTER_WARPS * TILE_PX, "row tables alias the triangle staging area");
+    unsigned char* const rowtab = reinterpret_cast<unsigned char*>(sm.tri) + wid * TILE_PX;
+#endif
     unsigned long long kb_min = ~0ull, kb_max = 0ull;
+#if B2R_ROWDIFF
+    // Also idle during the stencil phase: the clip-coordinate staging area.  It holds (a) the z-buffer range of the
+    // covered pixels of every tile ROW and (b) a per-row DIFFERENCE ARRAY of stencil increments: a row of a (quad, tile)
+    // pair whose span passes the depth test as a whole adds +-1 at the span's first pixel and -+1 behind its last one --
+    // two shared-memory atomics instead of one per pixel -- and one prefix sum per row at the end of the phase turns
+    // the array into counts.  Entries are 16-bit halves of a word, biased by 0x8000 so that a decrement of the low half
+    // never borrows from the high half (a tile sees far fewer than 32 767 pairs); the row pitch of 17 words keeps the
+    // rows on different banks.
+    constexpr int DIFF_PITCH = 17;
+    static_assert(sizeof(sm.clip) >= TILE_H * DIFF_PITCH * 4 + TILE_H * 16, "row arrays alias the clip staging area");
+    unsigned* const diff = reinterpret_cast<unsigned*>(sm.clip);
+    unsigned long long* const rowk = reinterpret_cast<unsigned long long*>(diff + TILE_H * DIFF_PITCH);   // [row][min, max]
+    bool used_diff = false;
+#endif
     if (skip_bg && q_beg < q_end) {
-        for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) {
+#if B2R_ROWDIFF
+        for (int i = threadIdx.x; i < TILE_H * DIFF_PITCH; i += RASTER_THREADS) diff[i] = 0x80008000u;
+#endif
+        for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) {   // one tile row per warp and iteration
             const unsigned long long k = sm.z[i];
-            if (k != z_init) { kb_min = min(kb_min, k); kb_max = max(kb_max, k); }
-        }
+            unsigned long long rmin = ~0ull, rmax = 0ull;
+            if (k != z_init) { rmin = k; rmax = k; }
 #pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            kb_min = min(kb_min, __shfl_xor_sync(0xffffffffu, kb_min, o));
-            kb_max = max(kb_max, __shfl_xor_sync(0xffffffffu, kb_max, o));
+            for (int o = 16; o; o >>= 1) {
+                rmin = min(rmin, __shfl_xor_sync(0xffffffffu, rmin, o));
+                rmax = max(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+            }
+#if B2R_ROWDIFF
+            if (lane == 0) { rowk[2 * (i >> 5)] = rmin; rowk[2 * (i >> 5) + 1] = rmax; }
+#endif
+            kb_min = min(kb_min, rmin); kb_max = max(kb_max, rmax);
         }
         if (lane == 0) { sm.red_min[wid] = kb_min; sm.red_max[wid] = kb_max; }
         __syncthreads();
@@ -1584,6 +1898,39 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
                     }
                 }
                 const int delta = front ? 1 : -1;
+#if B2R_ROWDIFF
+                if (skip_bg) {
+                    // row-level depth classification (lane = row): the quad depth, as the reference rounds it, is monotone
+                    // along a row, so its values at the two ends of the span bound it over the span; against the range of
+                    // the row's covered z-buffer entries the whole span fails (dropped), passes (difference array) or
+                    // stays undecided (per-pixel items below).  `all_pass` pairs pass in every row.
+                    bool row_pass = all_pass;
+                    if (hi >= lo && !all_pass) {
+                        const unsigned long long rmin = rowk[2 * lane], rmax = rowk[2 * lane + 1];
+                        if (rmin > rmax) hi = lo - 1;   // no covered pixel in this row
+                        else {
+                            const double t = R.ny * (double)py;
+                            const double z0 = -((R.nx * (double)lo + t) + R.D) / R.nz, z1 = -((R.nx * (double)hi + t) + R.D) / R.nz;
+                            const double den0 = V.zl_sum - z0 * V.zl_diff, den1 = V.zl_sum - z1 * V.zl_diff;
+                            const double q0 = V.zl_num / den0, q1 = V.zl_num / den1;
+                            if (q0 == q0 && q1 == q1 && ((den0 > 0 && den1 > 0) || (den0 < 0 && den1 < 0))) {
+                                const unsigned long long k0 = zkey(q0), k1 = zkey(q1);
+                                const unsigned long long kmin = min(k0, k1), kmax = max(k0, k1);
+                                if (rh ? (kmin > rmax) : (kmax < rmin)) hi = lo - 1;          // every covered pixel fails
+                                else if (rh ? (kmax <= rmin) : (kmin >= rmax)) row_pass = true;  // every covered pixel passes
+                            }
+                        }
+                    }
+                    if (row_pass && hi >= lo) {
+                        const int a = lo - X0, b = hi - X0 + 1;
+                        unsigned* const drow = diff + lane * DIFF_PITCH;
+                        atomicAdd(drow + (a >> 1), (unsigned)delta << (16 * (a & 1)));
+                        if (b < TILE_W) atomicAdd(drow + (b >> 1), (unsigned)(-delta) << (16 * (b & 1)));
+                        used_diff = true;
+                        hi = lo - 1;
+                    }
+                }
+#endif
                 // The spans of the 32 rows are flattened into one dense pixel list and dealt to the lanes, so every lane
                 // works whatever the shape of the quad: pixel k lies in the row r with start[r] <= k < start[r+1]
                 // (inclusive scan over the lanes, then a 5-step bisection through shuffles).  Two pixels per lane and
@@ -1595,7 +1942,20 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
                 for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
                 const int total = __shfl_sync(0xffffffffu, incl, 31);
                 if (lane == 0) { B2R_STAT(2, 1); B2R_STAT(3, total); }
-                auto locate = [&](int k, int& lx, int& r) {  // every lane takes part in the shuffles
+#if B2R_ROWTAB
+                // row table: entry k of the warp's table names the row of item k (written by the lane that owns the row);
+                // an item is then one shared-memory byte and one shuffle away from its pixel (round 1/2a: a 5-step
+                // bisection through shuffles per item, ~18 % of the kernel's instructions)
+                const int off = lo - X0 - (incl - len);   // lx = k + off for the items k of this lane's row
+                __syncwarp();                             // the previous pair's table is fully consumed
+                for (int j = incl - len; j < incl; ++j) rowtab[j] = (unsigned char)lane;
+                __syncwarp();
+                auto locate = [&](int k, bool valid, int& lx, int& r) {
+                    r = valid ? (int)rowtab[k] : 0;
+                    lx = k + __shfl_sync(0xffffffffu, off, r);
+                };
+#else
+                auto locate = [&](int k, bool, int& lx, int& r) {  // every lane takes part in the shuffles
                     r = 0;  // smallest lane with incl[r] > k
 #pragma unroll
                     for (int step = 16; step; step >>= 1) {
@@ -1605,15 +1965,16 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
                     const int row_incl = __shfl_sync(0xffffffffu, incl, r), row_len = __shfl_sync(0xffffffffu, len, r);
                     lx = __shfl_sync(0xffffffffu, lo, r) + (k - (row_incl - row_len)) - X0;
                 };
+#endif
                 auto quad_depth = [&](int px, int qy) {  // z = -(nx*px + ny*py + D)/nz, linearised (triangular.py:352-354)
                     const double z = -(R.nx * (double)px + R.ny * (double)qy + R.D) / R.nz;
                     return V.zl_num / (V.zl_sum - z * V.zl_diff);
                 };
                 for (int k = lane; k < ((total + 63) & ~63); k += 64) {
                     int lxa, ra, lxb, rb;
-                    locate(k, lxa, ra);
-                    locate(k + 32, lxb, rb);
                     const bool va = k < total, vb = k + 32 < total;
+                    locate(k, va, lxa, ra);
+                    locate(k + 32, vb, lxb, rb);
                     const int pa = va ? tpix(lxa, ra) : 0, pb = vb ? tpix(lxb, rb) : 0;
                     const unsigned long long kba = sm.z[pa], kbb = sm.z[pb];
                     bool hit_a = va && !(skip_bg && kba == z_init), hit_b = vb && !(skip_bg && kbb == z_init);
@@ -1630,7 +1991,22 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
         }
     }
     if (skip_bg && lane == 0 && uniform) atomicAdd(&sm.uniform, uniform);
+#if B2R_ROWDIFF
+    if (__any_sync(0xffffffffu, used_diff) && lane == 0) sm.use_diff = 1;
+#endif
     __syncthreads();
+#if B2R_ROWDIFF
+    if (sm.use_diff) {   // difference arrays -> counts: a warp per row, inclusive scan over the 32 pixels
+        for (int row = wid; row < TILE_H; row += RASTER_WARPS) {
+            const unsigned w = diff[row * DIFF_PITCH + (lane >> 1)];
+            int v = (int)((w >> (16 * (lane & 1))) & 0xffffu) - 0x8000;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+            if (v) sm.st[tpix(lane, row)] += v;
+        }
+        __syncthreads();
+    }
+#endif
     if (skip_bg && sm.uniform) {
         const int uadd = sm.uniform;
         for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) if (sm.z[i] != z_init) sm.st[i] += uadd;
@@ -1658,7 +2034,7 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
     if (sm.need_full) {
         if (threadIdx.x == 0) B2R_STAT(7, 1);
         for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) sm.id[i] = -1;
-        tile_tris<3>(sm, S, V, vtris, tri_list, t_beg, t_end, X0, Y0, X1, Yb0, Y1, rh, status_view);
+        tile_tris<3>(sm, S.pos, S.face_vf, V, vtris, tri_list, t_beg, t_end, X0, Y0, X1, Yb0, Y1, rh, status_view);
         __syncthreads();
     } else if (status_view) {
         // Pass-3 status (core.py:624-636) without the full pass: no exact tie was seen in this tile, so the faces that pass
@@ -1713,16 +2089,19 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
 
 // Shading pass of the unfused path: one CTA of 128 threads per 32x32 tile (a warp per row), reading the packed winner
 // word k_tile<false> left behind.  Tiles whose lists are empty were never written: they are recognised here.
-// ALT = true: one of the alternative shading functions (Fr.shading != B2R_SHADE_GENERAL); a separate instantiation so that
-// the production kernel carries none of their code or stack.
-template <bool ALT>
+// MODE: SHADE_F32 (production) general_shading with float32 lighting, SHADE_F64 the all-float64 form (B2R_SHADE_F64=1,
+// and whenever the float frame is handed out), SHADE_ALT one of the alternative shading functions
+// (Fr.shading != B2R_SHADE_GENERAL); separate instantiations so that the production kernel carries none of the others'
+// code or stack.
+enum : int { SHADE_F64 = 0, SHADE_ALT = 1, SHADE_F32 = 2 };
+template <int MODE>
 __global__ void __launch_bounds__(RASTER_THREADS, B2R_SHADE_MINB)
 k_shade_packed(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec* __restrict__ tris, BinDev B,
                TileOut O, int view0, int n_sub) {
-    const int view = (int)(blockIdx.x % (unsigned)n_sub) + view0;
+    const int view = (int)blockIdx.x + view0;
     const ViewDev& V = views[view];
     const int n_tiles = Fr.tiles_x * Fr.tiles_y;
-    const int tile = B.order[(size_t)view * n_tiles + blockIdx.x / (unsigned)n_sub];
+    const int tile = B.order[(size_t)view * n_tiles + blockIdx.y];
     const int tx = tile % Fr.tiles_x, ty = tile / Fr.tiles_x + Fr.tile_row0;
     const int X0 = tx * TILE_W, Y0 = ty * TILE_H;
     const int X1 = min(X0 + TILE_W, Fr.W), Y1 = min(min(Y0 + TILE_H, Fr.H), Fr.row_end);
@@ -1757,8 +2136,10 @@ k_shade_packed(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const
         if (px < X1) {
             if (w != PACKED_NONE) {
                 const int face = (int)(w & ~PACKED_LIT);
-                if (ALT) shade_alt_pixel(S, V, Fr.light, vtris[face], face, px, py, Fr.shading, c);
-                else if (!shade_face_pixel(S, V, Fr.light, vtris[face], face, px, py, (w & PACKED_LIT) != 0, c)) *Fr.err_flag = 1;
+                if (MODE == SHADE_ALT) shade_alt_pixel(S, V, Fr.light, vtris[face], face, px, py, Fr.shading, c);
+                else if (MODE == SHADE_F32) {
+                    if (!shade_face_pixel_f32(S, V, Fr.lightf, Fr.light.type, vtris[face], face, px, py, (w & PACKED_LIT) != 0, c)) *Fr.err_flag = 1;
+                } else if (!shade_face_pixel(S, V, Fr.light, vtris[face], face, px, py, (w & PACKED_LIT) != 0, c)) *Fr.err_flag = 1;
             } else if (Fr.bg_mode == B2R_BG_CUBEMAP) {
                 skybox_pixel(S, V, Fr.sky_size, px, py, c);
             } else {
@@ -1767,7 +2148,7 @@ k_shade_packed(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const
             }
             if (O.f32) { float* o = O.f32 + g * 3; o[0] = c[0]; o[1] = c[1]; o[2] = c[2]; }
         }
-        const unsigned packed = const_bg ? bg : (ALT ? tonemap_pack_wide(c) : tonemap_pack(c));
+        const unsigned packed = const_bg ? bg : (MODE == SHADE_ALT ? tonemap_pack_wide(c) : tonemap_pack(c));
         store_row(Fr, O.rgb, view, X0, py, packed, px < X1, lane);
     }
 }

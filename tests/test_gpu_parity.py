@@ -347,3 +347,37 @@ for name in ("g2_diablo_floor_point", "g6_skybox_orthographic", "g12_depth_test_
     res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, B2R_FUSED="1"), capture_output=True, text=True,
                          timeout=600)
     assert res.returncode == 0 and res.stdout.count("FUSED-OK") == 3, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_production_stencil_path_counts_equal_the_oracle_under_faces():
+    """The production stencil path (no debug planes: background pixels skipped, whole (quad, tile) pairs and whole rows
+    classified by depth range, per-row difference arrays) normally only shows through the lit bit.  B2R_DEBUG_SKIP_BG=1
+    hands out ITS stencil plane: on every covered pixel the count must equal the oracle's, and so must z and the winner.
+    B2R_SHADE_F64=1 in the same child: the all-float64 shading kernel stays selectable and within the RGB bar."""
+    import subprocess
+    import sys
+    code = r'''
+import sys
+sys.path[:0] = [%r, %r + "/tests", %r + "/oracle"]
+import numpy as np
+import golden_util as gu, oracle as orc
+for name in ("g2_diablo_floor_point", "g3_diablo_floor_spot", "g4_diablo_floor_directional", "g8_torus_flat", "g9_diablo_transformed",
+             "g7_cube_mtl_rh_directx", "g7_cube_mtl_lh_directx"):
+    scene, exp, meta = gu.load(name)
+    scene.persist_silhouette = False
+    ref = gu.oracle_frame(orc, scene)
+    dbg = {}
+    rgb = scene.render(debug=dbg)
+    cov = ref["winner"] >= 0
+    assert np.array_equal(dbg["winner"], ref["winner"]), name
+    assert np.array_equal(dbg["z"][cov], ref["z"][cov]), name
+    assert np.array_equal(dbg["stencil"][cov], ref["stencil"][cov]), (name, int((dbg["stencil"][cov] != ref["stencil"][cov]).sum()))
+    assert (ref["stencil"][cov] != 0).any() or name.startswith("g7"), name
+    d = np.abs(rgb.astype(int) - ref["rgb"].astype(int)).max(-1)
+    assert (d > 1).sum() == 0 and (d > 0).sum() * 1000 <= d.size, (name, int((d > 0).sum()))
+    print("SKIPBG-OK", name, int(cov.sum()), int((ref["stencil"][cov] != 0).sum()))
+''' % (ROOT, ROOT, ROOT)
+    res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, B2R_DEBUG_SKIP_BG="1", B2R_SHADE_F64="1"),
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and res.stdout.count("SKIPBG-OK") == 7, res.stdout[-2000:] + res.stderr[-2000:]

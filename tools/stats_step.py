@@ -11,7 +11,7 @@ scene = scenes.kat2(scenes.asset_root(), (1080, 1920)) if workload == "diablo" e
 out = torch.empty((views, 1080, 1920, 3), dtype=torch.uint8, device="cuda:0")
 buf = (ctypes.c_ulonglong * 16)()
 names = ["quad_tile_pairs", "pairs_rejected_by_depth_range", "pairs_with_pixel_work", "stencil_pixel_items",
-         "pairs_uniform_counter", "pairs_full_no_span_search", "pairs_all_pass", "tiles_full_winner_pass", "-", "-", "-",
+         "pairs_uniform_counter", "pairs_full_no_span_search", "pairs_all_pass", "tiles_full_winner_pass", "clip_elision_tests", "clip_elision_hits", "tri_pixel_tests_with_clip",
          "tiles", "tri_pixel_tests", "tri_pixel_covered", "quad_list_entries", "tri_list_entries"]
 for it in range(2):
     cams = scenes.orbit_cameras(views, start=0.37 * it)
