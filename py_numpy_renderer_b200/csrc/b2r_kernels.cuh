@@ -26,9 +26,6 @@
 #ifndef B2R_ROWDIFF
 #define B2R_ROWDIFF 1      // stencil: row-level depth classification + per-row difference arrays (two atomics per row span)
 #endif
-#ifndef B2R_ROWTAB
-#define B2R_ROWTAB 1       // stencil items find their row through a shared-memory table instead of a shuffle bisection
-#endif
 
 namespace b2r {
 
@@ -519,7 +516,7 @@ __device__ __forceinline__ bool tri_misses_rect(const TriRec& r, int x0, int x1,
 // An affine function attains its minimum over the rectangle at a corner, so if at all four corners s and the six F of
 // each frustum exceed the worst-case perturbation sum_i (E_i + float64 rounding) |d_i| (|clip_i.w| + |clip_i.k|), four
 // times over, every computed comparison of every pixel in the rectangle comes out true.  NaN / inf anywhere -> false.
-__device__ __noinline__ bool tri_rect_unclipped(const TriRec& r, const double* __restrict__ cc, int x0, int x1, int y0, int y1) {
+__device__ __forceinline__ bool tri_rect_unclipped(const TriRec& r, const double* __restrict__ cc, int x0, int x1, int y0, int y1) {
     const double d00 = r.d00, d01 = r.d01, d11 = r.d11, inv = r.inv;
     const double u32 = 5.9604644775390625e-8, u64 = 1.1102230246251565e-16;  // 2^-24, 2^-53
     double amax[3] = {0, 0, 0}, gv = 0, gw = 0, smin = 1e300, fmn[2] = {1e300, 1e300};
@@ -571,7 +568,7 @@ __device__ __noinline__ bool tri_rect_unclipped(const TriRec& r, const double* _
 // tile kernel runs that pair without the per-pixel test.  (Deciding it inside the tile kernel was measured first: one
 // lane per CTA on a chain of ~600 dependent float64 operations while the other 127 threads wait cost more than the
 // test saves.  Here every lane of the fill pass decides its own tile.)
-__device__ __noinline__ bool face_tile_unclipped(const FrameDev& Fr, const TriRec* __restrict__ vtris, const double4* __restrict__ pos,
+__device__ __forceinline__ bool face_tile_unclipped(const FrameDev& Fr, const TriRec* __restrict__ vtris, const double4* __restrict__ pos,
                                                  const int4* __restrict__ face_vf, const ViewDev& V, int face, int tx, int ty) {
     const TriRec r = vtris[face];
     const int X0 = tx * TILE_W, Y0 = ty * TILE_H;
@@ -1502,6 +1499,20 @@ __device__ __forceinline__ bool skybox_pixel(const SceneDev& S, const ViewDev& V
 // second 30 records in the memory of the still unused stencil plane): +3 % on diablo, no gain on the 1M-triangle torus,
 // whose tile time is its 17.8 k shadow quads, not the rounds.
 // =====================================================================================================================
+// 64-bit warp-wide minimum / maximum through two 32-bit REDUX steps (high words, then the low words of the lanes that
+// hold the winning high word) instead of five shuffle rounds of 64-bit values
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+    const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
+    const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+    return ((unsigned long long)mh << 32) | ml;
+}
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+    const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    return ((unsigned long long)mh << 32) | ml;
+}
 __device__ __forceinline__ int tpix(int x, int y) { return (y << 5) | ((x ^ y) & 31); }  // x, y in [0, 32)
 
 constexpr unsigned PACKED_LIT = 0x80000000u;   // bit 31 of the packed winner word: stencil == 0
@@ -1741,11 +1752,9 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
 
     // ---- stencil (triangular.py:341-368) ----
     const bool skip_bg = !Fr.full_stencil;
-#if B2R_ROWTAB
     // the staging area of the triangle rounds is idle during the stencil phase: 1 KB of it per warp holds the row table
     static_assert(sizeof(sm.tri) >= RASTER_WARPS * TILE_PX, "row tables alias the triangle staging area");
     unsigned char* const rowtab = reinterpret_cast<unsigned char*>(sm.tri) + wid * TILE_PX;
-#endif
     unsigned long long kb_min = ~0ull, kb_max = 0ull;
 #if B2R_ROWDIFF
     // Also idle during the stencil phase: the clip-coordinate staging area.  It holds (a) the z-buffer range of the
@@ -1767,13 +1776,7 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
 #endif
         for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) {   // one tile row per warp and iteration
             const unsigned long long k = sm.z[i];
-            unsigned long long rmin = ~0ull, rmax = 0ull;
-            if (k != z_init) { rmin = k; rmax = k; }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                rmin = min(rmin, __shfl_xor_sync(0xffffffffu, rmin, o));
-                rmax = max(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
-            }
+            const unsigned long long rmin = warp_min_u64(k != z_init ? k : ~0ull), rmax = warp_max_u64(k != z_init ? k : 0ull);
 #if B2R_ROWDIFF
             if (lane == 0) { rowk[2 * (i >> 5)] = rmin; rowk[2 * (i >> 5) + 1] = rmax; }
 #endif
@@ -1880,17 +1883,18 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
                         if (!pred(lo)) hi = lo - 1;
                         continue;
                     }
-                    const double est = xi + c / ey;   // where f changes sign; then walk to the exact cut
+                    // where f changes sign, estimated in float32 (the walk below finds the exact cut whatever the estimate)
+                    const float est = (float)xi + __fdividef((float)c, (float)ey);
                     if (up) {
                         if (!pred(hi)) { hi = lo - 1; continue; }
-                        int k = est >= (double)hi ? hi : (est <= (double)lo ? lo : (int)ceil(est));
+                        int k = est >= (float)hi ? hi : (est <= (float)lo ? lo : (int)ceilf(est));
                         if (!(est == est)) k = lo;
                         while (k > lo && pred(k - 1)) --k;
                         while (!pred(k)) ++k;
                         lo = k;
                     } else {
                         if (!pred(lo)) { hi = lo - 1; continue; }
-                        int k = est >= (double)hi ? hi : (est <= (double)lo ? lo : (int)floor(est));
+                        int k = est >= (float)hi ? hi : (est <= (float)lo ? lo : (int)floorf(est));
                         if (!(est == est)) k = hi;
                         while (k < hi && pred(k + 1)) ++k;
                         while (!pred(k)) --k;
@@ -1942,10 +1946,9 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
                 for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
                 const int total = __shfl_sync(0xffffffffu, incl, 31);
                 if (lane == 0) { B2R_STAT(2, 1); B2R_STAT(3, total); }
-#if B2R_ROWTAB
                 // row table: entry k of the warp's table names the row of item k (written by the lane that owns the row);
-                // an item is then one shared-memory byte and one shuffle away from its pixel (round 1/2a: a 5-step
-                // bisection through shuffles per item, ~18 % of the kernel's instructions)
+                // an item is then one shared-memory byte and one shuffle away from its pixel (before: a 5-step bisection
+                // through shuffles per item)
                 const int off = lo - X0 - (incl - len);   // lx = k + off for the items k of this lane's row
                 __syncwarp();                             // the previous pair's table is fully consumed
                 for (int j = incl - len; j < incl; ++j) rowtab[j] = (unsigned char)lane;
@@ -1954,38 +1957,25 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
                     r = valid ? (int)rowtab[k] : 0;
                     lx = k + __shfl_sync(0xffffffffu, off, r);
                 };
-#else
-                auto locate = [&](int k, bool, int& lx, int& r) {  // every lane takes part in the shuffles
-                    r = 0;  // smallest lane with incl[r] > k
-#pragma unroll
-                    for (int step = 16; step; step >>= 1) {
-                        const int probe = __shfl_sync(0xffffffffu, incl, r + step - 1);
-                        if (probe <= k) r += step;
-                    }
-                    const int row_incl = __shfl_sync(0xffffffffu, incl, r), row_len = __shfl_sync(0xffffffffu, len, r);
-                    lx = __shfl_sync(0xffffffffu, lo, r) + (k - (row_incl - row_len)) - X0;
-                };
-#endif
                 auto quad_depth = [&](int px, int qy) {  // z = -(nx*px + ny*py + D)/nz, linearised (triangular.py:352-354)
                     const double z = -(R.nx * (double)px + R.ny * (double)qy + R.D) / R.nz;
                     return V.zl_num / (V.zl_sum - z * V.zl_diff);
                 };
-                for (int k = lane; k < ((total + 63) & ~63); k += 64) {
-                    int lxa, ra, lxb, rb;
-                    const bool va = k < total, vb = k + 32 < total;
-                    locate(k, va, lxa, ra);
-                    locate(k + 32, vb, lxb, rb);
-                    const int pa = va ? tpix(lxa, ra) : 0, pb = vb ? tpix(lxb, rb) : 0;
-                    const unsigned long long kba = sm.z[pa], kbb = sm.z[pb];
-                    bool hit_a = va && !(skip_bg && kba == z_init), hit_b = vb && !(skip_bg && kbb == z_init);
+                // what is left for the per-pixel path after the row classification is a tenth of the items: one pixel per
+                // lane and iteration keeps the loop (and the kernel's instruction footprint) small
+                for (int k = lane; k < ((total + 31) & ~31); k += 32) {
+                    int lx, r;
+                    const bool valid = k < total;
+                    locate(k, valid, lx, r);
+                    const int p = valid ? tpix(lx, r) : 0;
+                    const unsigned long long kb = sm.z[p];
+                    bool hit = valid && !(skip_bg && kb == z_init);
                     if (!all_pass) {
-                        const double za = quad_depth(X0 + lxa, Y0 + ra), zb = quad_depth(X0 + lxb, Y0 + rb);
-                        const unsigned long long kza = zkey(za), kzb = zkey(zb);
-                        hit_a = hit_a && za == za && (rh ? (kba >= kza) : (kba <= kza));
-                        hit_b = hit_b && zb == zb && (rh ? (kbb >= kzb) : (kbb <= kzb));
+                        const double zq = quad_depth(X0 + lx, Y0 + r);
+                        const unsigned long long kz = zkey(zq);
+                        hit = hit && zq == zq && (rh ? (kb >= kz) : (kb <= kz));
                     }
-                    if (hit_a) atomicAdd(&sm.st[pa], delta);
-                    if (hit_b) atomicAdd(&sm.st[pb], delta);
+                    if (hit) atomicAdd(&sm.st[p], delta);
                 }
             }  // survivors of this grab
         }
