@@ -1091,12 +1091,21 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
                 k_quad_setup<<<dim3(quad_blocks, pv), 64, 0, g.stream>>>(sc->sil.p, sc->counters.p, dviews, Fr, sc->quads.p, E, p0);
                 ++g.launches;
                 stage_mark(g, "quad_setup");
-                if (fork) CK(cudaStreamWaitEvent(g.stream, g.tri_done, 0));
                 const int bin_blocks = g.bin_blocks ? g.bin_blocks : g.sm_count * 2;
-                k_bin<false><<<dim3(bin_blocks, pv), 256, 0, g.stream>>>(Fr, sc->boxes.p, sc->quads.p, sc->counters.p, E, B, p0);
+                if (fork) {
+                    // count pass in two halves: the quads (the long half) do not wait for triangle set-up, the triangles
+                    // are counted on the set-up stream behind k_tri_count; both join before the scan
+                    k_bin<false><<<dim3(bin_blocks, pv), 256, 0, g.stream>>>(Fr, sc->boxes.p, sc->quads.p, sc->counters.p, E, B, p0, 2);
+                    k_bin<false><<<dim3(bin_blocks, pv), 256, 0, g.fork_stream>>>(Fr, sc->boxes.p, sc->quads.p, sc->counters.p, E, B, p0, 1);
+                    ++g.launches;
+                    CK(cudaEventRecord(g.tri_done, g.fork_stream));
+                    CK(cudaStreamWaitEvent(g.stream, g.tri_done, 0));
+                } else {
+                    k_bin<false><<<dim3(bin_blocks, pv), 256, 0, g.stream>>>(Fr, sc->boxes.p, sc->quads.p, sc->counters.p, E, B, p0, 3);
+                }
                 k_scan<<<dim3(pv, 2), 1024, 0, g.stream>>>(Fr, B, flags + 2 * first, sticky, p0, sc->counters.p, E, need_sil_flag);
                 k_order<<<pv, 1024, 0, g.stream>>>(Fr, B, p0);
-                k_bin<true><<<dim3(bin_blocks, pv), 256, 0, g.stream>>>(Fr, sc->boxes.p, sc->quads.p, sc->counters.p, E, B, p0);
+                k_bin<true><<<dim3(bin_blocks, pv), 256, 0, g.stream>>>(Fr, sc->boxes.p, sc->quads.p, sc->counters.p, E, B, p0, 3);
                 g.launches += 4;
                 if (g.clip_elide && F > 0) {
                     k_clip_elide<<<dim3((n_tiles + 127) / 128, ELIDE_MAX_FACES, pv), 128, 0, g.stream>>>(

@@ -599,7 +599,9 @@ constexpr int BIN_PAIR_BUF = 128;  // per-warp shared-memory run of (quad, tile)
 constexpr int BIN_SUPER = 4;  // quads: tiles are classified in blocks of BIN_SUPER x BIN_SUPER first
 template <bool FILL>
 __global__ void k_bin(FrameDev Fr, const TriBox* __restrict__ boxes, const QuadRec* __restrict__ quads,
-                      const int* __restrict__ sil_count, int quad_stride, BinDev B, int view0) {
+                      const int* __restrict__ sil_count, int quad_stride, BinDev B, int view0, int parts) {
+    // parts: 1 = triangles, 2 = shadow quads, 3 = both.  The count pass runs as two launches when triangle set-up has
+    // its own stream: the quad half (the long one) starts right after k_quad_setup, the triangle half after k_tri_count.
     const int view = blockIdx.y + view0;
     const int lane = threadIdx.x & 31;
     const int n_tiles = Fr.tiles_x * Fr.tiles_y;
@@ -613,7 +615,7 @@ __global__ void k_bin(FrameDev Fr, const TriBox* __restrict__ boxes, const QuadR
     const int* const quad_off = B.quad_off + (size_t)view * (n_tiles + 1);
     int* const tri_list = B.tri_list + (size_t)view * B.tri_cap;
     int* const quad_list = B.quad_list + (size_t)view * B.quad_cap;
-    for (int base = blockIdx.x * blockDim.x + threadIdx.x - lane; base < Fr.n_faces; base += stride) {
+    for (int base = blockIdx.x * blockDim.x + threadIdx.x - lane; (parts & 1) && base < Fr.n_faces; base += stride) {
         const int slot = base + lane;
         int bx0 = 0, bx1 = 0, by0 = 0, by1 = 0;
         bool valid = false;
@@ -708,6 +710,7 @@ __global__ void k_bin(FrameDev Fr, const TriBox* __restrict__ boxes, const QuadR
         }
         return;
     }
+    if (!(parts & 2)) return;
     // Count pass.  A quad whose box spans the screen has hundreds of tiles to classify, each a chain of dependent
     // float64 operations: the grid's warps are split evenly over the quads (`share` warps each, striding over the
     // blocks of the box).  Surviving pairs collect in a per-warp shared-memory run and reach the per-view pair list
@@ -1863,15 +1866,25 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
                 if (py < ry0 || py > ry1) hi = lo - 1;
                 const int nv = full ? 0 : R.n;
                 if (full && lane == 0) B2R_STAT(5, 1);
-                for (int e = 0; e < nv; ++e) {
-                    const int j = (e + 1 == nv) ? 0 : e + 1;
-                    const double xi = R.x[e], yi = R.y[e];
-                    const double ex = R.x[j] - xi, ey = R.y[j] - yi;
-                    {   // (warp-uniform) an edge whose worst corner of the rectangle is already inside constrains no row
-                        const double fworst = front ? edge_fn(ey >= 0 ? rx0 : rx1, ex <= 0 ? ry0 : ry1, xi, yi, ex, ey)
-                                                    : edge_fn(ey >= 0 ? rx1 : rx0, ex <= 0 ? ry1 : ry0, xi, yi, ex, ey);
-                        if (front ? (fworst > 0) : (fworst < 0)) continue;
-                    }
+                // Lane e < nv owns edge e: its vectors, and whether it constrains any row of the rectangle at all -- an edge
+                // whose worst corner of the rectangle is already inside does not (most edges of a sliver crossing the
+                // tile).  One lane per edge decides that; before, every lane decided it for every edge.
+                double own_x = 0, own_y = 0, own_ex = 0, own_ey = 0;
+                bool constrains = false;
+                if (lane < nv) {
+                    const int j = (lane + 1 == nv) ? 0 : lane + 1;
+                    own_x = R.x[lane]; own_y = R.y[lane];
+                    own_ex = R.x[j] - own_x; own_ey = R.y[j] - own_y;
+                    const double fworst = front ? edge_fn(own_ey >= 0 ? rx0 : rx1, own_ex <= 0 ? ry0 : ry1, own_x, own_y, own_ex, own_ey)
+                                                : edge_fn(own_ey >= 0 ? rx1 : rx0, own_ex <= 0 ? ry1 : ry0, own_x, own_y, own_ex, own_ey);
+                    constrains = !(front ? (fworst > 0) : (fworst < 0));
+                }
+                unsigned edges_left = __ballot_sync(0xffffffffu, constrains);
+                while (edges_left) {
+                    const int e = __ffs(edges_left) - 1;
+                    edges_left &= edges_left - 1;
+                    const double xi = __shfl_sync(0xffffffffu, own_x, e), yi = __shfl_sync(0xffffffffu, own_y, e);
+                    const double ex = __shfl_sync(0xffffffffu, own_ex, e), ey = __shfl_sync(0xffffffffu, own_ey, e);
                     if (lo > hi) continue;
                     const double c = ((double)py - yi) * ex;
                     auto pred = [&](int px) {  // front ? f > 0 : f < 0 with f = (px - xi)*ey - c  (triangular.py:305-311)
