@@ -23,6 +23,9 @@
 #include "b2r_device.cuh"
 
 // tuning switches of the tile kernel (A/B builds: tools/build_variant.sh <name> -DB2R_...=0)
+#ifndef B2R_SKIP
+#define B2R_SKIP 0         // timing experiments only (wrong frames): 1 depth pass, 2 stencil phase, 4 winner verification,
+#endif                     // 8 span search, 16 everything after the span search of a pair, 32 output store
 #ifndef B2R_ROWDIFF
 #define B2R_ROWDIFF 1      // stencil: row-level depth classification + per-row difference arrays (two atomics per row span)
 #endif
@@ -1518,6 +1521,7 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
 }
 __device__ __forceinline__ int tpix(int x, int y) { return (y << 5) | ((x ^ y) & 31); }  // x, y in [0, 32)
 
+constexpr int STAMP_RACED = 0x7fffffff;     // depth pass: two improvements of this pixel in one round (see tile_tris)
 constexpr unsigned PACKED_LIT = 0x80000000u;   // bit 31 of the packed winner word: stencil == 0
 constexpr unsigned PACKED_NONE = 0x7fffffffu;  // no face (background)
 
@@ -1557,8 +1561,9 @@ __device__ __noinline__ void tile_tris(TileSmem& sm, const double4* __restrict__
                                        int t_beg, int t_end, int X0, int Y0, int X1, int Yb0, int Y1, bool rh,
                                        uint8_t* status_view) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int n = 0;
+    int n = 0, round_stamp = 0;
     for (int base = t_beg; base < t_end; base += n) {
+        ++round_stamp;
         __syncthreads();  // previous round fully consumed
         if (wid == 0) {   // choose the round: up to 32 triangles, at most STAGE_CLIP of them with a clip test (the tile-list
                           // entry carries that flag: no dependent load of the record here)
@@ -1645,7 +1650,15 @@ __device__ __noinline__ void tile_tris(TileSmem& sm, const double4* __restrict__
                     if (r.flags & TR_NO_ZWRITE) { sm.need_full = 1; continue; }
                     const unsigned long long old = rh ? atomicMin(&sm.z[p], key) : atomicMax(&sm.z[p], key);
                     if (old == key) sm.need_full = 1;                                               // exact tie
-                    else if (rh ? (key < old) : (key > old)) store_relaxed_smem(&sm.id[p], face);   // last improver
+                    else if (rh ? (key < old) : (key > old)) {
+                        store_relaxed_smem(&sm.id[p], face);   // last improver
+                        // Only two improvements of one pixel within the SAME round can leave a stale id behind (their
+                        // stores are unordered; rounds are separated by barriers).  The idle stencil plane keeps the
+                        // round of a pixel's last improvement; a second one in that round marks the pixel for the
+                        // verification below -- every other pixel is trusted as it is.
+                        const int prev = atomicMax(&sm.st[p], round_stamp);
+                        if (prev == round_stamp) atomicMax(&sm.st[p], STAMP_RACED);
+                    }
                 } else {
                     // writing faces colour where they ARE the z-buffer; non-writing ones wherever they pass the test
                     // against the final z-buffer (zbuf >= z for RH, <= for LH)
@@ -1750,7 +1763,25 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
     const int* tri_list = B.tri_list + (size_t)view * B.tri_cap;
     uint8_t* status_view = O.status ? O.status + (size_t)view * Fr.n_faces : nullptr;
 
-    tile_tris<1>(sm, S.pos, S.face_vf, V, vtris, tri_list, t_beg, t_end, X0, Y0, X1, Yb0, Y1, rh, status_view);
+    if (!(B2R_SKIP & 1)) tile_tris<1>(sm, S.pos, S.face_vf, V, vtris, tri_list, t_beg, t_end, X0, Y0, X1, Yb0, Y1, rh, status_view);
+    __syncthreads();
+    // ---- winner: the last improver, verified where two improvements raced; full pass on ties / lost races ----
+    for (int p = threadIdx.x; p < TILE_PX; p += RASTER_THREADS) {
+        const int stamp = sm.st[p];
+        sm.st[p] = 0;   // the plane becomes the stencil count
+        const int f = sm.id[p];
+        const unsigned long long kb = sm.z[p];
+        if (f < 0) { if (kb != z_init) sm.need_full = 1; continue; }
+        if (stamp != STAMP_RACED || (B2R_SKIP & 4)) continue;
+        const int ly = p >> 5, lx = (p ^ ly) & 31;
+        const TriRec& r = vtris[f];
+        float bu, bv, bw;
+        tri_bary(r, X0 + lx, Y0 + ly, bu, bv, bw);
+        const double b0 = (double)bu, b1 = (double)bv, b2 = (double)bw;
+        const double z = (r.flags & TR_COV_ONE) ? seq3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2])
+                                                : gemv3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2]);
+        if (!(z == z) || zkey(z) != kb) sm.need_full = 1;
+    }
     __syncthreads();
 
     // ---- stencil (triangular.py:341-368) ----
@@ -1792,7 +1823,7 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
     }
     const bool any_cov = kb_min <= kb_max;
     int uniform = 0;
-    if (!skip_bg || any_cov) {
+    if ((!skip_bg || any_cov) && !(B2R_SKIP & 2)) {
         const int* quad_list = B.quad_list + (size_t)view * B.quad_cap;
         const QuadRec* vquads = quads + (size_t)view * quad_stride;
         const int n_pairs = q_end - q_beg;
@@ -1880,6 +1911,7 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
                     constrains = !(front ? (fworst > 0) : (fworst < 0));
                 }
                 unsigned edges_left = __ballot_sync(0xffffffffu, constrains);
+                if (B2R_SKIP & 8) edges_left = 0;
                 while (edges_left) {
                     const int e = __ffs(edges_left) - 1;
                     edges_left &= edges_left - 1;
@@ -1915,6 +1947,7 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
                     }
                 }
                 const int delta = front ? 1 : -1;
+                if (B2R_SKIP & 16) continue;
 #if B2R_ROWDIFF
                 if (skip_bg) {
                     // row-level depth classification (lane = row): the quad depth, as the reference rounds it, is monotone
@@ -1953,6 +1986,7 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
                 // (inclusive scan over the lanes, then a 5-step bisection through shuffles).  Two pixels per lane and
                 // iteration, written as straight-line code: their depth evaluations (two dependent float64 divisions
                 // each) are independent and overlap in the pipeline.
+                if (!__any_sync(0xffffffffu, hi >= lo)) continue;   // every row was dropped or went to the difference array
                 const int len = max(hi - lo + 1, 0);
                 int incl = len;
 #pragma unroll
@@ -2016,24 +2050,6 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
         __syncthreads();
     }
 
-    // ---- winner: verified last improver, full pass on ties / lost races ----
-    if (!sm.need_full) {
-        for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) {
-            const int ly = i >> 5, lx = i & 31;
-            const int p = tpix(lx, ly);
-            const int f = sm.id[p];
-            const unsigned long long kb = sm.z[p];
-            if (f < 0) { if (kb != z_init) sm.need_full = 1; continue; }
-            const TriRec& r = vtris[f];
-            float bu, bv, bw;
-            tri_bary(r, X0 + lx, Y0 + ly, bu, bv, bw);
-            const double b0 = (double)bu, b1 = (double)bv, b2 = (double)bw;
-            const double z = (r.flags & TR_COV_ONE) ? seq3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2])
-                                                    : gemv3(b0, b1, b2, r.zl[0], r.zl[1], r.zl[2]);
-            if (!(z == z) || zkey(z) != kb) sm.need_full = 1;
-        }
-    }
-    __syncthreads();
     if (sm.need_full) {
         if (threadIdx.x == 0) B2R_STAT(7, 1);
         for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) sm.id[i] = -1;
