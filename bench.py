@@ -427,8 +427,9 @@ def measure_scene(scene, cam_fn, B, K, Wm, torch, _native, lib_stream, flush, pe
     stage = {k: v / n_st for k, v in stage.items()}
     # end to end
     pinned = [torch.empty((B, H, W, 3), dtype=torch.uint8, pin_memory=True).numpy() for _ in range(2)]
-    cams, dcams = cam_fn(1000, B)
-    scene.render_batch(cams, debug_cameras=dcams, out=pinned[0])
+    for w in range(2):   # warm-up of BOTH staging slots of the asynchronous path (their first use allocates device memory)
+        cams, dcams = cam_fn(1000 + w, B)
+        scene.render_batch_async(cams, debug_cameras=dcams, out=pinned[w]).result()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     fl = None
@@ -857,7 +858,7 @@ def main():
                     "whole_frame_frac": balg["total"] * value / world / 1e9 / peak,
                     "stages": stages,
                     "note": "HBM is the roofline the contract names; ncu shows the tile kernel bound by issue slots "
-                            "(float64 edge / depth / Phong arithmetic the reference's semantics prescribe), see "
+                            "(float64 edge / depth arithmetic the reference's semantics prescribe), see "
                             "profiles/README.md and the per-stage `ceiling` entries"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
@@ -876,6 +877,9 @@ def main():
                                         f"{gather_mode} gather per step" + ("" if bands is not None else
                                                                             ", overlapped with the next render")))
                        if world > 1 else "single GPU",
+                       "arithmetic": "float64 coverage / depth / stencil / perspective weights / texel addressing (bit-exact "
+                                     "against the reference), float32 lighting sum (B2R_SHADE_F64=1 selects the all-float64 "
+                                     "shading kernel)" if not os.environ.get("B2R_SHADE_F64") else "float64 throughout",
                        "l2": "flushed before every step (256 MiB memset, inside the timed region)",
                        "timing": "one CUDA-event pair around the K steps (first flush .. last transfer), MAX over ranks; "
                                  "stage times from a separate per-step-synchronised pass",

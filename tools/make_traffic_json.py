@@ -13,7 +13,7 @@ raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_outpu
 rows = list(csv.reader(io.StringIO(raw)))
 idx = {h: i for i, h in enumerate(rows[0])}
 units = rows[1]
-STAGE = {"k_tile": "raster", "k_shade_packed": "shade", "k_bin": "bin", "k_scan": "bin", "k_order": "bin",
+STAGE = {"k_tile": "raster", "k_shade_packed": "shade", "k_bin": "bin", "k_scan": "bin", "k_order": "bin", "k_clip_elide": "bin",
          "k_tri_setup": "tri_setup", "k_vertex": "tri_setup", "k_tri_count": "tri_setup", "k_quad_setup": "quad_setup",
          "k_facing": "silhouette", "k_silhouette": "silhouette", "k_frame_consts": "silhouette"}
 
