@@ -15,7 +15,7 @@ import json,sys
 f=sys.argv[1]
 try:
     d=json.loads([l for l in open(f"gpurun_out/r2c31_{f}.json").read().splitlines() if l.startswith("{")][-1])
-    print(f, "value", round(d["value"]), "e2e", round(d["e2e"]["value"]), "ms/step", round(d["ms_per_step"],3), d["scaling"], d.get("byte_check"), "pcie", round(d["e2e"]["pcie_gbs"],1), round(d["e2e"].get("pcie_frac",0),3), d["config"]["parallelism"][:80])
+    print(f, "value", round(d["value"]), "e2e", round(d["e2e"]["value"]), "ms/step", round(d["ms_per_step"],3), d["scaling"], d.get("byte_check"), "pcie", round(d["e2e"]["pcie_gbs"],1), d["e2e"].get("pcie_frac"), d["config"]["parallelism"][:80])
 except Exception as e:
     print(f, "failed", e); print(open(f"gpurun_out/r2c31_{f}.err").read()[-1500:])
 PY
