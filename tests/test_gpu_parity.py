@@ -69,6 +69,29 @@ def test_c3_synthetic_1080p_vs_oracle(light, oracle):
     assert (got['stencil'] != 0).sum() > 10000 and (got['winner'] >= 0).sum() > 500000
 
 
+@pytest.mark.parametrize("dbg_cam", ["narrow", "offset", "near_far"])
+def test_clip_elision_keeps_the_cut_of_the_debug_frustum_1080p(dbg_cam, oracle):
+    """k_clip_elide drops the per-pixel clip test of a (screen-filling face, tile) pair only where all four corners prove
+    that every pixel passes in BOTH frusta.  Here the debug camera's frustum cuts through the visible floor and figure
+    (narrower / looking from the side / short far plane), so tiles along the cut must keep the test: z, stencil and
+    winner bit-exact against the oracle at the size where the floor's faces are 'huge' (more than 256 tiles)."""
+    scene = scenes.c3_synthetic((1080, 1920))
+    if dbg_cam == "narrow":
+        scene.debug_camera = b2r.Camera((0.5, 1.5, 3), center=np.array((0, 0, 0)), fovy=28, near=0.1, far=10, backface_culling=True)
+    elif dbg_cam == "offset":
+        scene.debug_camera = b2r.Camera((2.5, 1.0, 2.0), center=np.array((0.3, -0.6, 0)), fovy=50, near=0.1, far=10, backface_culling=True)
+    else:
+        scene.debug_camera = b2r.Camera((0.5, 1.5, 3), center=np.array((0, 0, 0)), fovy=90, near=2.9, far=3.9, backface_culling=True)
+    got = gpu_render(scene)
+    want = gu.oracle_frame(oracle, scene)
+    rep = gu.compare_planes(got, want)
+    assert rep['z_mismatch'] == 0 and rep['stencil_mismatch'] == 0 and rep['winner_mismatch'] == 0, rep
+    assert rep['rgb_px_gt1'] == 0 and rep['rgb_px_diff'] * 1000 <= rep['pixels'], rep
+    covered = int((got['winner'] >= 0).sum())
+    full = int((gpu_render(scenes.c3_synthetic((1080, 1920)))['winner'] >= 0).sum())
+    assert 10000 < covered < full - 10000, (covered, full)    # the cut really removes a good part of the frame
+
+
 @pytest.mark.skipif(scenes.asset_root() is None, reason="reference assets not staged")
 def test_kat2_real_assets_1080p(oracle):
     """The headline scene itself: diablo3_pose (diffuse + tangent normal map) + floor, 1080p (SURVEY KAT-2)."""
