@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define B2R_ABI_VERSION 5
+#define B2R_ABI_VERSION 6
 #define B2R_MAX_POLY 12 /* a quad clipped by 6 planes has at most 10 vertices */
 
 /* Light kinds: obj/lightning.py:4-7 */
@@ -219,6 +219,13 @@ int b2r_set_stage_timing(int enabled);
 int b2r_window_create(int64_t bytes, void** dev_ptr, void* handle_out);
 int b2r_window_open(const void* handle, void** dev_ptr);
 int b2r_window_close(void* dev_ptr);      /* opened with b2r_window_open */
+/* Sparse push of n_views finished frames (n_views, height, width, 3) uint8 from this device into a window block (this
+ * device's own memory or a peer's, mapped with b2r_window_open), asynchronously on `stream` (a cudaStream_t).  One 32x32
+ * tile at a time: a tile that holds a single colour now and held exactly that after the previous push into the same
+ * block is not stored again, so a frame's constant background crosses NVLink once.  `state_dev`: n_views * ceil(height/32)
+ * * (width/32) words on THIS device, zeroed before the first push into a block and kept with it.  width % 32 == 0. */
+int b2r_window_push(const uint8_t* src_dev, uint8_t* dst_dev, int32_t n_views, int32_t height, int32_t width,
+                    uint32_t* state_dev, void* stream);
 int b2r_window_destroy(void* dev_ptr);    /* created with b2r_window_create */
 
 /* ---- native OBJ tokenizer (host only) ---------------------------------------------------------

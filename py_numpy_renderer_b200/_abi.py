@@ -13,7 +13,7 @@ from .constants import SYSTEM
 from .lightning import Lightning
 from .materials import Texture
 
-B2R_ABI_VERSION = 5
+B2R_ABI_VERSION = 6
 B2R_ERR_INDEX = 2
 B2R_F32, B2R_F64 = 0, 1
 B2R_TEX_UNORM, B2R_TEX_SNORM = 0, 1

@@ -55,6 +55,7 @@ _SYMBOLS = {
     "b2r_window_create": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
     "b2r_window_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "b2r_window_close": (C.c_int, [C.c_void_p]),
+    "b2r_window_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "b2r_window_destroy": (C.c_int, [C.c_void_p]),
     "b2r_host_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
     "b2r_host_free": (C.c_int, [C.c_void_p]),
@@ -398,6 +399,12 @@ def window_open(handle: bytes):
     ptr = C.c_void_p()
     _check(lib.b2r_window_open(C.create_string_buffer(handle, 64), C.byref(ptr)))
     return int(ptr.value)
+
+
+def window_push(src_ptr, dst_ptr, n_views, height, width, state_ptr, stream=0):
+    """Sparse tile push of finished frames into a window block on `stream` (a cudaStream_t as int); see include/b2r.h."""
+    _check(init().b2r_window_push(C.c_void_p(int(src_ptr)), C.c_void_p(int(dst_ptr)), int(n_views), int(height), int(width),
+                                  C.c_void_p(int(state_ptr)), C.c_void_p(int(stream))))
 
 
 def window_close(ptr):

@@ -430,6 +430,21 @@ int b2r_window_create(int64_t bytes, void** dev_ptr, void* handle_out) {
     *dev_ptr = p;
     return 0;
 }
+int b2r_window_push(const uint8_t* src_dev, uint8_t* dst_dev, int32_t n_views, int32_t height, int32_t width,
+                    uint32_t* state_dev, void* stream) {
+    CTX_OR_FAIL();
+    if (!src_dev || !dst_dev || !state_dev || n_views <= 0 || height <= 0 || width <= 0)
+        return fail("b2r_window_push: bad arguments");
+    if (width % TILE_W != 0 || ((uintptr_t)src_dev | (uintptr_t)dst_dev) % 16 != 0)
+        return fail("b2r_window_push: the width must be a multiple of 32 and both buffers 16-byte aligned");
+    CK(cudaSetDevice(g.device));
+    const int total = n_views * (width / TILE_W) * ((height + TILE_H - 1) / TILE_H);
+    const int blocks = std::max(1, std::min((total + 3) / 4, 2 * g.sm_count));   // light looping CTAs (4 warps, a tile each): they share the SMs with the next render
+    k_window_push<<<blocks, PUSH_THREADS, 0, (cudaStream_t)stream>>>(src_dev, dst_dev, n_views, height, width, state_dev);
+    ++g.launches;
+    CK(cudaGetLastError());
+    return 0;
+}
 int b2r_window_open(const void* handle, void** dev_ptr) {
     CTX_OR_FAIL();
     if (!handle || !dev_ptr) return fail("b2r_window_open: bad arguments");

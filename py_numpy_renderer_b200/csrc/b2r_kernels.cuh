@@ -10,22 +10,29 @@
 //                                                                          (plane_intersection.py:59-86, triangular.py:319-340)
 //   k_bin<FILL>     per primitive    tile lists (count / fill): thread per face, warp per quad with the exact
 //                                    corner classification of every (quad, tile) pair
-//   k_scan          per view         exclusive scan of the tile counts
+//   k_scan, k_order per view         exclusive scan of the tile counts; tiles bucketed by cost, active tiles counted
+//   k_clip_elide    per (screen-filling face, tile)  proof that no pixel of the tile fails the per-pixel clip test: the
+//                                    list entry loses its clip bit                           (triangular.py:80-87)
 //   k_tile<FUSED>   per 32x32 tile   (1) depth: staged triangle lists, dense (triangle,pixel) dealing, 64-bit keyed
-//                                    smem atomics  (2) stencil: depth-range classification, exact row spans, dense
-//                                    pixel dealing  (3) winner: verified last-improver, full pass only on ties
+//                                    smem atomics, race stamps  (2) winner: last improver, verified where two
+//                                    improvements raced, full pass only on ties  (3) stencil: depth-range classification
+//                                    of (quad,tile) pairs, exact row spans, row-level depth classification -> per-row
+//                                    difference arrays, the rest as dense per-pixel items
 //                                    (4) one packed word per pixel (winner | lit << 31) -- or, FUSED, the shading itself
 //                                                                          (triangular.py:78-118, 341-368)
-//   k_shade_packed  per 32x32 tile   Phong + textures + tangent normal maps + skybox + tonemap, warp-packed stores;
+//   k_shade_packed<MODE> per 32x32 tile   Phong + textures + tangent normal maps + skybox + tonemap, warp-packed stores;
+//                                    SHADE_F32 (production): float64 coverage / perspective weights / texel addresses,
+//                                    float32 lighting; SHADE_F64: all float64; SHADE_ALT: flat / gouraud / pbr;
 //                                    tiles without primitives are recognised from their empty lists
 //                                                                          (triangular.py:135-171, core.py:138-228,640; cube_map.py:63-101)
+//   k_window_push   per 32x32 tile   multi-GPU: sparse push of finished frames into the assembling rank's window (peer stores)
 #pragma once
 #include "b2r_device.cuh"
 
 // tuning switches of the tile kernel (A/B builds: tools/build_variant.sh <name> -DB2R_...=0)
 #ifndef B2R_SKIP
 #define B2R_SKIP 0         // timing experiments only (wrong frames): 1 depth pass, 2 stencil phase, 4 winner verification,
-#endif                     // 8 span search, 16 everything after the span search of a pair, 32 output store
+#endif                     // 8 span search, 16 everything after the span search of a pair (profiles/r02_phase_timing.md)
 #ifndef B2R_ROWDIFF
 #define B2R_ROWDIFF 1      // stencil: row-level depth classification + per-row difference arrays (two atomics per row span)
 #endif
@@ -2179,6 +2186,67 @@ __global__ void k_status_resolve(uint8_t* __restrict__ status, size_t n) {
     const uint8_t s = status[i];
     if ((s & 0xE0) != 0xE0) return;
     status[i] = (s & 4) ? B2R_FACE_RENDERED : ((s & 1) ? B2R_FACE_EMPTY_Z : B2R_FACE_CLIPPED);
+}
+
+// =====================================================================================================================
+// Multi-GPU output window: sparse push of finished frames into the assembling rank's buffer over NVLink.
+// One 32x32 tile at a time: the tile's 32 row segments (96 bytes each) are read from the local frames with 16-byte
+// loads; if every pixel of the tile has the colour of its first pixel AND the destination tile is known to hold exactly
+// that (state: what this rank pushed into the same window block the last time), nothing is stored -- the constant
+// background of a frame (about half of the headline scene's tiles) never crosses the link again.  Otherwise the tile is
+// stored with 16-byte peer stores and the state updated.  Purely content based, hence exact whatever was rendered.
+// Why: seven peers pushing whole frames deliver 7 x 398 MB per 64-frame step into ONE 900 GB/s NVLink port; with the
+// renderers at 3.4 ms per step that port (748 GB/s measured) bounded the 8-GPU weak-scaling efficiency at 0.92.
+// Persistent CTAs (a low-priority stream, under the next step's render), 192 threads = one 16-byte piece of the tile each.
+// Requires W % 32 == 0 (rows and tile segments are then 16-byte aligned); the host wrapper falls back to a plain copy.
+// =====================================================================================================================
+constexpr int PUSH_THREADS = 128;   // four warps, a tile each: 32 lanes x 6 pieces of 16 bytes = the tile's 32 rows of 96 bytes
+__global__ void __launch_bounds__(PUSH_THREADS, 8) k_window_push(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int n_views,
+                                                              int H, int W, unsigned* __restrict__ state) {
+    const int tiles_x = W / TILE_W, tiles_y = (H + TILE_H - 1) / TILE_H;
+    const int n_tiles = tiles_x * tiles_y, total = n_views * n_tiles;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * PUSH_THREADS + threadIdx.x) >> 5, n_warps = (gridDim.x * PUSH_THREADS) >> 5;
+    for (int item = warp; item < total; item += n_warps) {
+        const int view = item / n_tiles, tile = item - view * n_tiles;
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const size_t tile_off = ((size_t)view * H + (size_t)ty * TILE_H) * W * 3 + (size_t)tx * (TILE_W * 3);
+        const int rows = min(TILE_H, H - ty * TILE_H);
+        // six independent 16-byte loads per lane: piece q = lane + 32 j of the tile's 192 (row q / 6, 16-byte column q % 6)
+        uint4 v[6];
+        auto piece_off = [&](int j) {
+            const int q = lane + 32 * j, row = q / 6, col = q - row * 6;
+            return tile_off + (size_t)min(row, rows - 1) * W * 3 + (size_t)col * 16;
+        };
+#pragma unroll
+        for (int j = 0; j < 6; ++j) v[j] = __ldg(reinterpret_cast<const uint4*>(src + piece_off(j)));
+        const unsigned c = __shfl_sync(0xffffffffu, v[0].x, 0) & 0x00ffffffu;   // colour of the tile's first pixel
+        // A row of a tile filled with colour c = (R, G, B) repeats three words: RGBR GBRG BRGB.  Word k of the piece at
+        // 16-byte column col is word (4 col + k) % 3 = (col + k) % 3 of that pattern.
+        const unsigned c0 = c & 0xffu, c1 = (c >> 8) & 0xffu, c2 = (c >> 16) & 0xffu;
+        const unsigned pat[3] = {c0 | c1 << 8 | c2 << 16 | c0 << 24, c1 | c2 << 8 | c0 << 16 | c1 << 24, c2 | c0 << 8 | c1 << 16 | c2 << 24};
+        const int r0 = lane % 3;   // col % 3 of piece j: (lane + 32 j) % 3 = (r0 + 2 j) % 3
+        bool same = true;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const int q = lane + 32 * j;
+            const int r = (r0 + 2 * j) % 3;
+            const unsigned w0 = r == 0 ? pat[0] : (r == 1 ? pat[1] : pat[2]);
+            const unsigned w1 = r == 0 ? pat[1] : (r == 1 ? pat[2] : pat[0]);
+            const unsigned w2 = r == 0 ? pat[2] : (r == 1 ? pat[0] : pat[1]);
+            same = same && (q / 6 >= rows || (v[j].x == w0 && v[j].y == w1 && v[j].z == w2 && v[j].w == w0));
+        }
+        const bool uniform = __all_sync(0xffffffffu, same);
+        const unsigned tag = 0x01000000u | c;   // "the destination tile holds nothing but colour c"
+        const unsigned held = state[item];
+        if (uniform && held == tag) continue;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const int q = lane + 32 * j;
+            if (q / 6 < rows) *reinterpret_cast<uint4*>(dst + piece_off(j)) = v[j];
+        }
+        if (lane == 0) state[item] = uniform ? tag : 0u;
+    }
 }
 
 }  // namespace b2r

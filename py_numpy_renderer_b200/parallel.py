@@ -144,6 +144,28 @@ class FrameWindow:
         shading kernel's own stores (useful when many ranks would otherwise burst into `dst` at the same moment)."""
         return _DevView(self.block_ptr(slot), self.shape)
 
+    def push(self, slot, frames, stream=None):
+        """Push this rank's finished frames (a CUDA tensor (n, H, W, 3) uint8 on this rank's device) into its block of
+        `slot`, asynchronously on `stream` (a torch.cuda.Stream; default: the current one).  Sparse: 32x32 tiles that hold
+        one colour now and held exactly that after the previous push into the same block are not sent again
+        (`b2r_window_push`, a kernel with peer stores) -- the constant background of a frame crosses NVLink once.  Falls
+        back to a plain copy (copy engines) when the width is not a multiple of 32."""
+        import torch
+        from . import _native
+        n, H, W, _ = self.shape
+        stream = stream or torch.cuda.current_stream()
+        if W % 32 != 0 or frames.data_ptr() % 16 != 0 or self.block_ptr(slot) % 16 != 0:
+            with torch.cuda.stream(stream):
+                torch.as_tensor(self.block(slot), device=frames.device).copy_(frames, non_blocking=True)
+            return
+        if not hasattr(self, "_push_state"):
+            self._push_state = {}
+        st = self._push_state.get(slot)
+        if st is None:   # nothing is known about the block's content yet: every tile of the first push is sent
+            st = self._push_state[slot] = torch.zeros(n * ((H + 31) // 32) * (W // 32), dtype=torch.int32, device=frames.device)
+            stream.wait_stream(torch.cuda.current_stream())   # the zero fill above
+        _native.window_push(frames.data_ptr(), self.block_ptr(slot), n, H, W, st.data_ptr(), stream.cuda_stream)
+
     def frames(self, slot):
         """On `dst`: the assembled (world * n, H, W, 3) frames of `slot` as a zero-copy CUDA array-interface object
         (torch.as_tensor(w.frames(s), device='cuda') wraps it)."""
