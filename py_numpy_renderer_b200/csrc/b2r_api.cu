@@ -66,6 +66,7 @@ struct Context {
     int aux_host = 2, aux_dev = 3;  // how many auxiliary streams the sub-chunks rotate over
     int init_tri_cap = 0, init_quad_cap = 0;  // B2R_TRI_CAP / B2R_QUAD_CAP: first per-view list capacities (tests of the grow path)
     int bin_blocks = 0, bin_share = 64;  // k_bin grid (0 = 2 per SM) and the most warps that share one quad
+    int split_parts = 4;          // B2R_SPLIT: CTAs per tile in launches of one or two views (1 = off)
     bool clip_elide = true;       // B2R_CLIP_ELIDE=0: keep the per-pixel clip test on every (clip-flagged face, tile) pair (A/B)
     bool debug_skip_bg = false;   // B2R_DEBUG_SKIP_BG=1: debug stencil plane from the production (skip-background) stencil path
     bool shade_f32 = true;        // B2R_SHADE_F64=1: the all-float64 shading kernel instead of float32 lighting
@@ -190,6 +191,7 @@ struct b2r_scene {
     DevBuf<int2> pair_list;  // (quad, tile) pairs between the two binning passes
     DevBuf<int> winner;
     DevBuf<unsigned> packed;  // winner | lit << 31 per pixel (B2R_FUSED=2)
+    DevBuf<int> split_st, split_ticket;  // SPLIT launches of the tile kernel: partial stencil counts, tickets
     DevBuf<short> stencil;
     DevBuf<double> zplane;
     DevBuf<float> frame_f32;
@@ -268,6 +270,7 @@ int b2r_init(int device) {
     if (const char* a = std::getenv("B2R_BIN_SHARE")) g.bin_share = std::max(1, std::atoi(a));
     if (const char* a = std::getenv("B2R_PIPE")) g.pipe_views = std::max(1, std::atoi(a));
     if (const char* a = std::getenv("B2R_FUSED")) g.fused = std::atoi(a) != 0;
+    if (const char* a = std::getenv("B2R_SPLIT")) g.split_parts = std::min(8, std::max(1, std::atoi(a)));
     if (const char* a = std::getenv("B2R_CLIP_ELIDE")) g.clip_elide = std::atoi(a) != 0;
     if (const char* a = std::getenv("B2R_DEBUG_SKIP_BG")) g.debug_skip_bg = std::atoi(a) != 0;
     if (const char* a = std::getenv("B2R_SHADE_F64")) g.shade_f32 = std::atoi(a) == 0;
@@ -713,7 +716,7 @@ int b2r_scene_destroy(b2r_scene* sc) {
     sc->sky.release(); sc->edge_v.release(); sc->edge_ptr.release(); sc->edge_inc.release(); sc->edge_model.release();
     sc->sil_state.release(); sc->facing.release(); sc->sil.release(); sc->counters.release(); sc->views.release();
     sc->tris.release(); sc->boxes.release(); sc->coop_list.release(); sc->vrec.release(); sc->vinside.release(); sc->quads.release(); sc->tile_counts.release(); sc->tile_offs.release(); sc->tri_list.release();
-    sc->quad_list.release(); sc->pair_list.release(); sc->overflow.release(); sc->tile_order.release(); sc->winner.release(); sc->packed.release(); sc->stencil.release(); sc->zplane.release();
+    sc->quad_list.release(); sc->pair_list.release(); sc->overflow.release(); sc->tile_order.release(); sc->winner.release(); sc->packed.release(); sc->split_st.release(); sc->split_ticket.release(); sc->stencil.release(); sc->zplane.release();
     sc->status.release(); sc->frame_f32.release(); sc->rgb[0].release(); sc->rgb[1].release();
     delete sc;
     return 0;
@@ -1142,8 +1145,26 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
                         ++g.launches;
                         stage_mark(g, "tile");
                     } else {
-                        k_tile<false><<<dim3((unsigned)sv, (unsigned)n_tiles), RASTER_THREADS, 0, st>>>(
-                            S, dviews, Fr, sc->tris.p, sc->quads.p, E, B, T, v0, sv);
+                        // a launch of one or two views is latency bound (it lasts as long as its heaviest tile): every tile's
+                        // pair list is then cut over g.split_parts CTAs (k_tile<false, true>)
+                        // (decided by the whole batch: its sub-chunks may run concurrently on several streams, so the scratch
+                        // is indexed by the view's position in the batch)
+                        const int parts = ((size_t)nv * n_tiles <= 8192 && E > 0) ? g.split_parts : 1;
+                        if (parts > 1) {
+                            CK(sc->split_st.reserve((size_t)nv * n_tiles * parts * TILE_PX));
+                            CK(sc->split_ticket.reserve((size_t)nv * n_tiles));
+                            const size_t slots = (size_t)sv * n_tiles;
+                            k_zero_words<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>(
+                                reinterpret_cast<unsigned*>(sc->split_ticket.p + (size_t)v0 * n_tiles), slots);
+                            ++g.launches;
+                            TileOut TS = T;
+                            TS.split_st = sc->split_st.p; TS.split_ticket = sc->split_ticket.p; TS.n_parts = parts;
+                            k_tile<false, true><<<dim3((unsigned)sv, (unsigned)n_tiles, (unsigned)parts), RASTER_THREADS, 0, st>>>(
+                                S, dviews, Fr, sc->tris.p, sc->quads.p, E, B, TS, v0, sv);
+                        } else {
+                            k_tile<false><<<dim3((unsigned)sv, (unsigned)n_tiles), RASTER_THREADS, 0, st>>>(
+                                S, dviews, Fr, sc->tris.p, sc->quads.p, E, B, T, v0, sv);
+                        }
                         ++g.launches;
                         stage_mark(g, "raster");
                         if (Fr.shading == B2R_SHADE_GENERAL && g.shade_f32 && !want_f32)

@@ -1542,6 +1542,10 @@ struct TileOut {
     short* stencil;
     double* z;
     uint8_t* status;       // optional (views, F)
+    // SPLIT launches (a handful of views: every tile's pair list is cut over n_parts CTAs, see k_tile)
+    int* split_st;         // (views of the batch, n_tiles, n_parts, 1024) partial stencil counts
+    int* split_ticket;     // (views of the batch, n_tiles) parts that have delivered, zero before the launch
+    int n_parts;
 };
 
 struct TileSmem {
@@ -1560,6 +1564,7 @@ struct TileSmem {
     int uniform;
     int need_full;
     int use_diff;
+    int ticket;
 };
 // One pass over the tile's triangle list.  PASS 1: zbuf + last improver, PASS 3: full winner pass (+ status bits).
 template <int PASS>
@@ -1709,11 +1714,18 @@ __device__ __forceinline__ void store_row(const FrameDev& Fr, uint8_t* __restric
 #ifndef B2R_TILE_MINB_UNFUSED
 #define B2R_TILE_MINB_UNFUSED 9
 #endif
-template <bool FUSED>
+// SPLIT = true (launches of one or two views, i.e. plain scene.render() calls): such a launch is latency bound -- all of
+// its ~1000 active tiles are resident at once and it lasts as long as the heaviest tile under the figure's shadow volume,
+// one CTA walking ~150 (quad, tile) pairs (0.30 ms against 0.028 ms per view in a 64-view launch).  Every tile then gets
+// n_parts CTAs (blockIdx.z): each repeats the (cheap) depth pass and takes one contiguous part of the tile's pair list;
+// the parts leave their partial stencil counts in global memory, and the LAST one to arrive (a ticket per tile) sums them
+// and finishes the tile.  A separate instantiation: the batch kernel carries none of it.
+template <bool FUSED, bool SPLIT = false>
 __global__ void __launch_bounds__(RASTER_THREADS, FUSED ? B2R_TILE_MINB : B2R_TILE_MINB_UNFUSED)
 k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec* __restrict__ tris,
        const QuadRec* __restrict__ quads, int quad_stride, BinDev B, TileOut O, int view0, int n_sub) {
     __shared__ TileSmem sm;
+    const int part = SPLIT ? (int)blockIdx.z : 0, n_parts = SPLIT ? O.n_parts : 1;
     // grid (views of the sub-chunk, tile rank): x runs fastest, so the views stay interleaved within a cost class
     const int view = (int)blockIdx.x + view0;
     // ranks past the active tiles of this view (about half the screen in the headline scene): nothing to do, and
@@ -1738,6 +1750,7 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
 
     if (t_beg == t_end && (q_beg == q_end || !Fr.full_stencil)) {
         // no face can win here: background tile
+        if (SPLIT && part != 0) return;
         if (!FUSED && !(O.winner || O.stencil || O.z)) return;   // k_shade_packed sees the empty lists itself
         const unsigned bg = (!FUSED || Fr.bg_mode == B2R_BG_CUBEMAP) ? 0u : __ldg(O.bg_packed);
         for (int row = wid; row < TILE_H; row += RASTER_WARPS) {
@@ -1833,7 +1846,10 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
     if ((!skip_bg || any_cov) && !(B2R_SKIP & 2)) {
         const int* quad_list = B.quad_list + (size_t)view * B.quad_cap;
         const QuadRec* vquads = quads + (size_t)view * quad_stride;
-        const int n_pairs = q_end - q_beg;
+        // SPLIT: this CTA's contiguous part of the pair list
+        const int qs_beg = SPLIT ? q_beg + (int)(((long long)(q_end - q_beg) * part) / n_parts) : q_beg;
+        const int qs_end = SPLIT ? q_beg + (int)(((long long)(q_end - q_beg) * (part + 1)) / n_parts) : q_end;
+        const int n_pairs = qs_end - qs_beg;
         for (;;) {
             // guided self-scheduling: eight pairs per grab while the list is long, fewer towards its end, so the
             // warps reach the closing barrier together
@@ -1841,12 +1857,12 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
             if (lane == 0) {
                 const int seen = sm.next_quad;  // a stale value only changes the grab size
                 grab = max(1, min(8, (n_pairs - seen) / (2 * RASTER_WARPS)));
-                t0 = q_beg + atomicAdd(&sm.next_quad, grab);
+                t0 = qs_beg + atomicAdd(&sm.next_quad, grab);
             }
             t0 = __shfl_sync(0xffffffffu, t0, 0);
             grab = __shfl_sync(0xffffffffu, grab, 0);
-            if (t0 >= q_end) break;
-            const int t_hi = min(t0 + grab, q_end);
+            if (t0 >= qs_end) break;
+            const int t_hi = min(t0 + grab, qs_end);
             const int tg = t0 + (lane >> 2);
             int g_entry = 0, g_state = 0;  // 0 skip, 1 process, 2 process and every covered pixel passes the z test
             double g_z = 0.0;
@@ -2057,6 +2073,24 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
         __syncthreads();
     }
 
+    if (SPLIT && n_parts > 1) {
+        // partial stencil counts -> global memory; the last part of the tile to arrive sums them and goes on alone
+        const size_t slot = (size_t)view * n_tiles + tile;   // view = position in the batch: concurrent sub-chunks use disjoint slots
+        int* const mine = O.split_st + (slot * n_parts + part) * TILE_PX;
+        for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) mine[i] = sm.st[i];
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) sm.ticket = atomicAdd(O.split_ticket + slot, 1);
+        __syncthreads();
+        if (sm.ticket != n_parts - 1) return;
+        __threadfence();
+        for (int q = 0; q < n_parts; ++q) {
+            if (q == part) continue;
+            const int* other = O.split_st + (slot * n_parts + q) * TILE_PX;
+            for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) sm.st[i] += __ldcg(other + i);
+        }
+        __syncthreads();
+    }
     if (sm.need_full) {
         if (threadIdx.x == 0) B2R_STAT(7, 1);
         for (int i = threadIdx.x; i < TILE_PX; i += RASTER_THREADS) sm.id[i] = -1;
