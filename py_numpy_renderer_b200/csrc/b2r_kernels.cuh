@@ -1748,6 +1748,8 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
     const size_t plane = (size_t)view * Fr.H * Fr.W;
     const double z_bg = rh ? __longlong_as_double(0x7FF0000000000000ll) : __longlong_as_double(0xFFF0000000000000ll);
 
+    const bool solo = SPLIT && q_beg == q_end;   // no shadow quads over this tile: nothing to split, part 0 does it alone
+    if (solo && part != 0) return;
     if (t_beg == t_end && (q_beg == q_end || !Fr.full_stencil)) {
         // no face can win here: background tile
         if (SPLIT && part != 0) return;
@@ -2073,7 +2075,7 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
         __syncthreads();
     }
 
-    if (SPLIT && n_parts > 1) {
+    if (SPLIT && n_parts > 1 && !solo) {
         // partial stencil counts -> global memory; the last part of the tile to arrive sums them and goes on alone
         const size_t slot = (size_t)view * n_tiles + tile;   // view = position in the batch: concurrent sub-chunks use disjoint slots
         int* const mine = O.split_st + (slot * n_parts + part) * TILE_PX;
