@@ -33,6 +33,9 @@
 #ifndef B2R_SKIP
 #define B2R_SKIP 0         // timing experiments only (wrong frames): 1 depth pass, 2 stencil phase, 4 winner verification,
 #endif                     // 8 span search, 16 everything after the span search of a pair (profiles/r02_phase_timing.md)
+#ifndef B2R_CLASSIFY32
+#define B2R_CLASSIFY32 0   // 1: one lane per (quad, tile) pair classifies it, up to 32 pairs per grab (measured: diablo 1.90 against
+#endif                     // 1.84 ms, torus 1.93 against 2.05 ms per 16 views); 0 (production): four lanes per pair, 8 pairs per grab
 #ifndef B2R_ROWDIFF
 #define B2R_ROWDIFF 1      // stencil: row-level depth classification + per-row difference arrays (two atomics per row span)
 #endif
@@ -1853,6 +1856,53 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
         const int qs_end = SPLIT ? q_beg + (int)(((long long)(q_end - q_beg) * (part + 1)) / n_parts) : q_end;
         const int n_pairs = qs_end - qs_beg;
         for (;;) {
+#if B2R_CLASSIFY32
+            // self-scheduling: a share of the remaining pairs per grab, at most 32 -- ONE LANE PER PAIR classifies it (the
+            // four corners of its rectangle one after the other: independent chains of two float64 divisions each), so a
+            // grab is one round of dependent loads (list entry -> quad record) for up to 32 pairs instead of eight
+            int t0 = 0, grab = 0;
+            if (lane == 0) {
+                const int seen = sm.next_quad;  // a stale value only changes the grab size
+                grab = max(1, min(32, (n_pairs - seen) / RASTER_WARPS));
+                t0 = qs_beg + atomicAdd(&sm.next_quad, grab);
+            }
+            t0 = __shfl_sync(0xffffffffu, t0, 0);
+            grab = __shfl_sync(0xffffffffu, grab, 0);
+            if (t0 >= qs_end) break;
+            const int t_hi = min(t0 + grab, qs_end);
+            const int tg = t0 + lane;
+            int g_entry = 0, g_state = 0;  // 0 skip, 1 process, 2 process and every covered pixel passes the z test
+            if (tg < t_hi) {
+                g_entry = quad_list[tg];
+                const QuadRec& G = vquads[g_entry & (QUAD_FULL_BIT - 1)];
+                const int gx0 = max((int)G.bx0, X0), gx1 = min((int)G.bx1, X1) - 1;
+                const int gy0 = max((int)G.by0, Yb0), gy1 = min((int)G.by1, Y1) - 1;
+                if (gx0 <= gx1 && gy0 <= gy1) {
+                    g_state = 1;
+                    if (skip_bg) {
+                        unsigned long long kmin = ~0ull, kmax = 0ull;
+                        int code = 0;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int cx = (c & 1) ? gx1 : gx0, cy = (c & 2) ? gy1 : gy0;
+                            const double z = -(G.nx * (double)cx + G.ny * (double)cy + G.D) / G.nz;
+                            const double den = V.zl_sum - z * V.zl_diff;
+                            const double gz = V.zl_num / den;
+                            const int cc = (gz == gz) ? (den > 0 ? 1 : (den < 0 ? 2 : 3)) : 3;
+                            code = (c == 0 || code == cc) ? cc : 3;
+                            const unsigned long long k = zkey(gz);
+                            kmin = min(kmin, k); kmax = max(kmax, k);
+                        }
+                        if (code != 3) {
+                            if (rh ? (kmin > kb_max) : (kmax < kb_min)) g_state = 0;
+                            else if (rh ? (kmax <= kb_min) : (kmin >= kb_max)) g_state = 2;
+                        }
+                    }
+                }
+                B2R_STAT(0, 1); if (g_state == 0) B2R_STAT(1, 1); if (g_state == 2) B2R_STAT(6, 1);
+            }
+            unsigned todo = __ballot_sync(0xffffffffu, g_state != 0);
+#else
             // guided self-scheduling: eight pairs per grab while the list is long, fewer towards its end, so the
             // warps reach the closing barrier together
             int t0 = 0, grab = 0;
@@ -1901,6 +1951,7 @@ k_tile(SceneDev S, const ViewDev* __restrict__ views, FrameDev Fr, const TriRec*
             }
             if ((lane & 3) == 0 && tg < t_hi) { B2R_STAT(0, 1); if (g_state == 0) B2R_STAT(1, 1); if (g_state == 2) B2R_STAT(6, 1); }
             unsigned todo = __ballot_sync(0xffffffffu, (lane & 3) == 0 && g_state != 0);
+#endif
             while (todo) {
                 const int src = __ffs(todo) - 1;
                 todo &= todo - 1;
