@@ -520,7 +520,7 @@ def config_scenes():
 
     def c5():
         sc, what, radius = build_scene("torus1m", (1080, 1920))
-        return sc, what, orbit(radius), 16, 6
+        return sc, what, orbit(radius), 64, 4   # a quarter of BASELINE's 256-frame orbit per step
 
     return [("config1_800x800", c1), ("config4_4k_skybox_perspective", c4(False)),
             ("config4_4k_skybox_orthographic", c4(True)), ("config5_torus_1m_triangles", c5)]

@@ -38,6 +38,7 @@ struct Context {
     bool ready = false;
     int device = -1;
     int sm_count = 148;
+    size_t scratch_budget = (size_t)6 << 30;   // per-call scratch of a batch: a sixth of the device memory, at most 32 GiB (B200: 30 GiB)
     cudaStream_t stream = nullptr;
     long long launches = 0;
     bool timing = false;
@@ -236,6 +237,8 @@ int b2r_init(int device) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     g.sm_count = prop.multiProcessorCount;
+    g.scratch_budget = std::max((size_t)2 << 30, std::min((size_t)32 << 30, (size_t)prop.totalGlobalMem / 6));
+    if (const char* a = std::getenv("B2R_SCRATCH_GB")) g.scratch_budget = (size_t)std::max(1, std::atoi(a)) << 30;
     // the main stream carries the small, latency-bound set-up launches of the pipeline: highest priority, so that they
     // are not queued behind the tile kernels (auxiliary streams, default priority) they are meant to overlap
     int prio_lo = 0, prio_hi = 0;
@@ -925,7 +928,7 @@ int b2r_render(b2r_scene* sc, const b2r_frame_params* fp, const b2r_view* views,
     const bool want_planes = dbg && (dbg->winner || dbg->stencil);  // debug winner / stencil planes in HBM
     const size_t per_view = (size_t)F * (sizeof(TriRec) + sizeof(TriBox) + sizeof(int)) + (size_t)NV * 33 + (size_t)E * sizeof(QuadRec) + (want_planes ? npx * 6 : 0) +
                             (fused ? 0 : npx * 4) + (want_z ? npx * 8 : 0) + (want_f32 ? npx * 12 : 0);
-    int VB = (int)std::max<size_t>(1, std::min<size_t>(n_views, ((size_t)6 << 30) / std::max<size_t>(per_view, 1)));
+    int VB = (int)std::max<size_t>(1, std::min<size_t>(n_views, g.scratch_budget / std::max<size_t>(per_view, 1)));
     VB = std::min(VB, 64);
     const bool host_out = out_on_device != 1;
     const bool host_async = out_on_device == 2 && !dbg;
